@@ -1,0 +1,129 @@
+/*
+ * synergy_b200.h -- C ABI of the B200 (sm_100a) SynergyNet inference hot path.
+ *
+ * The reference (choyingw/SynergyNet) has no native boundary for this path: it is a Python
+ * nn.Module API (model_building.py:65-165, synergy3DMM.py:70-207) whose arithmetic runs inside
+ * PyTorch.  This library sits *under* a Python shim with the same class/method names
+ * (synergynet_b200/model_building.py, synergynet_b200/synergy3DMM.py) and is bound with ctypes
+ * (synergynet_b200/_lib.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ * Each entry point cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns SYN_OK (0) or a SYN_ERR_* code; no exceptions cross the boundary;
+ *     syn_last_error() returns a thread-local message for the last failing call.
+ *   - plain pointers and sizes only.  "_dev" pointers are device memory on the handle's GPU and
+ *     are owned by the caller; "_host" pointers are host memory.  `stream` is a cudaStream_t
+ *     (passed as void*); work is enqueued on it and NOT synchronised unless stated.
+ *   - one handle per device; a handle is not re-entrant (one call at a time per handle), but
+ *     different handles may be driven from different host threads (nn.DataParallel replicas,
+ *     main_train.py:176).
+ *   - tensors are fp32 and contiguous in the layouts the reference uses.
+ */
+#ifndef SYNERGY_B200_H_
+#define SYNERGY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SYN_ABI_VERSION 1
+
+enum {
+  SYN_OK = 0,
+  SYN_ERR_INVALID = 1,   /* bad argument (null pointer, negative size, unknown layer ...)      */
+  SYN_ERR_CUDA = 2,      /* a CUDA runtime call or kernel launch failed                         */
+  SYN_ERR_STATE = 3,     /* call order violated (e.g. forward before syn_commit)               */
+  SYN_ERR_SHAPE = 4,     /* "length of params mismatch" (model_building.py:116-119) and alike  */
+  SYN_ERR_NOMEM = 5,
+  SYN_ERR_UNSUPPORTED = 6 /* not an sm_100 device, or an engine the build does not contain      */
+};
+
+/* Compute engines for the 1x1 convolutions / basis products (syn_set_engine). */
+enum {
+  SYN_ENGINE_SIMT_FP32 = 0,   /* CUDA-core fp32 FMA everywhere (bring-up / cross-check path)     */
+  SYN_ENGINE_TC_BF16X3 = 1    /* tcgen05.mma, operands split in bf16 hi+lo, 3 MMAs per product,  */
+                              /* fp32 accumulation in TMEM: meets the 1e-4 parity bar            */
+};
+
+typedef struct syn_handle syn_handle_t;
+
+/* Geometry of convolution `layer` (0..51) in execution order; lets the host check a checkpoint
+ * against the compiled-in MobileNetV2 plan (mobilenetv2_backbone.py:108-138). */
+typedef struct {
+  int32_t cin, cout, ksize, stride, groups, relu6, h_in, h_out, residual;
+} syn_conv_desc_t;
+
+int         syn_abi_version(void);
+const char* syn_last_error(void);
+int         syn_num_conv_layers(void);                       /* 52 */
+int         syn_conv_desc(int layer, syn_conv_desc_t* out);
+
+/* Lifetime.  Replaces nn.Module construction + .cuda() (model_building.py:66-101). */
+int  syn_create(int device, syn_handle_t** out);
+void syn_destroy(syn_handle_t* h);
+
+/* ---- weights: host pointers in the reference's own layouts; copied during the call ----------
+ * Conv2d weight is OIHW fp32 (cout, cin/groups, k, k); BatchNorm2d is eval-mode
+ * (weight, bias, running_mean, running_var, eps) and is folded into the convolution by
+ * syn_commit.  Replaces ConvBNReLU / InvertedResidual parameter storage
+ * (mobilenetv2_backbone.py:33-68). */
+int syn_set_conv_bn(syn_handle_t* h, int layer, const float* w_host, int64_t w_numel,
+                    const float* bn_weight_host, const float* bn_bias_host,
+                    const float* bn_mean_host, const float* bn_var_host, float eps);
+/* classifier_ori / classifier_shape / classifier_exp Linear layers, weights (out,1280) row
+ * major (mobilenetv2_backbone.py:147-158). */
+int syn_set_heads(syn_handle_t* h, const float* w_ori_host, const float* b_ori_host,
+                  const float* w_shape_host, const float* b_shape_host,
+                  const float* w_exp_host, const float* b_exp_host);
+/* param_mean / param_std, 62 floats each (model_building.py:87-88). */
+int syn_set_whitening(syn_handle_t* h, const float* mean_host, const float* std_host);
+/* Landmark basis buffers u_base (3*n_pts), w_shp_base (3*n_pts,40), w_exp_base (3*n_pts,10),
+ * rows xyz-interleaved (model_building.py:99-101, utils/params.py:30-32). */
+int syn_set_basis_sparse(syn_handle_t* h, const float* u_base_host, const float* w_shp_base_host,
+                         const float* w_exp_base_host, int n_pts);
+/* Dense basis buffers u (3*n_vert), w_shp (3*n_vert,40), w_exp (3*n_vert,10)
+ * (model_building.py:89-91).  Optional: only needed for dense reconstruction. */
+int syn_set_basis_dense(syn_handle_t* h, const float* u_host, const float* w_shp_host,
+                        const float* w_exp_host, int64_t n_vert);
+/* Fold BN, re-lay-out for the kernels, upload.  Must follow the setters, may be repeated. */
+int syn_commit(syn_handle_t* h);
+
+int syn_set_engine(syn_handle_t* h, int engine);
+int syn_get_engine(const syn_handle_t* h);
+
+/* ---- compute, device buffers ------------------------------------------------------------------
+ * syn_forward: I2P.forward_test / MobileNetV2._forward_impl (model_building.py:59-62,
+ * mobilenetv2_backbone.py:173-189).  x_dev (B,3,120,120) NCHW -> params62_dev (B,62) whitened
+ * parameters [ori12|shape40|exp10]; pool1280_dev (B,1280) may be NULL. */
+int syn_forward(syn_handle_t* h, const float* x_dev, int batch, float* params62_dev,
+                float* pool1280_dev, void* stream);
+/* syn_reconstruct: reconstruct_vertex_62 (model_building.py:106-139; benchmark.py:76-97).
+ * params62_dev (B,62) -> out_dev (B,3,N) with N = n_pts (dense=0) or n_vert (dense=1). */
+int syn_reconstruct(syn_handle_t* h, const float* params62_dev, int batch, int dense,
+                    int whitening, int transform, float* out_dev, void* stream);
+/* forward_test + reconstruct_vertex_62(dense=False) without leaving the device
+ * (benchmark.py:125-127 then :153-166).  params62_dev may be NULL. */
+int syn_forward_landmarks(syn_handle_t* h, const float* x_dev, int batch, float* params62_dev,
+                          float* lmk_dev, void* stream);
+
+/* ---- compute, host buffers (the end-to-end call: H2D of the crops, forward, landmarks, D2H) --
+ * x_host (B,3,120,120) fp32, lmk_host (B,3,68), params62_host (B,62) or NULL.  Pinned host
+ * memory is recommended; chunks are pipelined over internal streams.  Synchronous. */
+int syn_forward_landmarks_host(syn_handle_t* h, const float* x_host, int batch,
+                               float* params62_host, float* lmk_host);
+
+/* ---- introspection ---------------------------------------------------------------------------*/
+/* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
+int64_t syn_launch_count(const syn_handle_t* h);
+/* Run the backbone on x_dev but stop after convolution `layer` (0..51) and copy its NHWC
+ * activation (batch*h_out*h_out*cout floats, residual already added for project convs) to
+ * out_dev.  Per-layer parity tests only. */
+int syn_debug_forward_until(syn_handle_t* h, const float* x_dev, int batch, int layer,
+                            float* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SYNERGY_B200_H_ */

@@ -1,0 +1,221 @@
+"""CPU oracle for the SynergyNet inference hot path.  TEST INFRASTRUCTURE ONLY.
+
+This is a CPU restatement of the reference algorithm, used as the checker by ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py``.  Nothing in ``synergynet_b200/`` may import it: the product path is the sm_100a
+library and fails loudly without it.
+
+Parity status: PINNED.  The reference has no tests or golden vectors of its own for this path
+(SURVEY.md section 4), so the pin is live execution of the unmodified reference modules in the
+build container: ``tests/golden/make_golden.py`` imports ``synergy3DMM.SynergyNet`` from a
+scratch copy of /root/reference, loads the seeded synthetic state dict and stores the reference's
+own outputs in ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this file against
+those vectors.
+
+The floating-point work of the reference runs inside PyTorch (ATen/oneDNN on CPU), which is a
+third-party dependency that the reference leaves unpinned (setup.py:8-11; README.md:34 says
+PyTorch 1.9); here it is torch 2.11.0.  The backbone is therefore restated with
+``torch.nn.functional`` in fp32 on CPU -- the same kernels the reference's ``nn.Module`` calls
+dispatch to -- and the 3DMM reconstruction with numpy fp32.
+
+Each function cites the reference lines it follows (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+from math import asin, atan2, cos, sqrt
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5          # nn.BatchNorm2d default, mobilenetv2_backbone.py:36-40
+STD_SIZE = 120         # utils/params.py:33
+
+# (t, c, n, s) -- mobilenetv2_backbone.py:108-117
+_STAGES = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1),
+           (6, 160, 3, 2), (6, 320, 1, 1))
+
+
+def _bn(x, sd, key):
+    return F.batch_norm(x, sd[key + '.running_mean'], sd[key + '.running_var'],
+                        sd[key + '.weight'], sd[key + '.bias'], False, 0.0, BN_EPS)
+
+
+def _conv_bn_relu6(x, sd, key, stride, groups, pad):
+    """ConvBNReLU, mobilenetv2_backbone.py:33-42."""
+    x = F.conv2d(x, sd[key + '.0.weight'], None, stride, pad, 1, groups)
+    return F.relu6(_bn(x, sd, key + '.1'))
+
+
+@torch.no_grad()
+def mobilenetv2_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = 'I2P.backbone.',
+                        return_features: bool = False):
+    """MobileNetV2._forward_impl, mobilenetv2_backbone.py:173-189 -> (param62, pool1280).
+
+    ``sd`` is a reference-schema state dict (CPU fp32), ``x`` is (B,3,120,120) fp32 NCHW.
+    """
+    sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    feats = []
+    x = _conv_bn_relu6(x, sd, 'features.0', 2, 1, 1)                     # :127
+    feats.append(x)
+    cin, blk = 32, 1
+    for t, c, n, s in _STAGES:                                             # :129-134
+        for i in range(n):
+            stride = s if i == 0 else 1
+            base = f'features.{blk}.conv'
+            y, j = x, 0
+            if t != 1:                                                     # InvertedResidual :58-60
+                y = _conv_bn_relu6(y, sd, f'{base}.0', 1, 1, 0)
+                j = 1
+            y = _conv_bn_relu6(y, sd, f'{base}.{j}', stride, y.shape[1], 1)   # :61-63
+            y = F.conv2d(y, sd[f'{base}.{j + 1}.weight'])                 # :65
+            y = _bn(y, sd, f'{base}.{j + 2}')                              # :66
+            x = x + y if (stride == 1 and cin == c) else y                 # :55,70-74
+            feats.append(x)
+            cin, blk = c, blk + 1
+    x = _conv_bn_relu6(x, sd, f'features.{blk}', 1, 1, 0)                  # :136
+    feats.append(x)
+    pool = F.adaptive_avg_pool2d(x, 1).reshape(x.shape[0], -1)            # :179-180
+    heads = [F.linear(pool, sd[f'{h}.1.weight'], sd[f'{h}.1.bias'])       # :184-186 (Dropout = id)
+             for h in ('classifier_ori', 'classifier_shape', 'classifier_exp')]
+    out = torch.cat(heads, 1)                                              # :188
+    if return_features:
+        return out, pool, feats
+    return out, pool
+
+
+def parse_param_62(param: np.ndarray):
+    """model_building.py:25-32 / benchmark.py:68-74 (views of a (B,62) array)."""
+    p_ = param[:, :12].reshape(-1, 3, 4)
+    p = p_[:, :, :3]
+    offset = p_[:, :, -1].reshape(-1, 3, 1)
+    alpha_shp = param[:, 12:52].reshape(-1, 40, 1)
+    alpha_exp = param[:, 52:62].reshape(-1, 10, 1)
+    return p, offset, alpha_shp, alpha_exp
+
+
+def reconstruct_vertex_62(param: np.ndarray, pack: Dict[str, np.ndarray], whitening: bool = True,
+                          dense: bool = False, transform: bool = True) -> np.ndarray:
+    """model_building.py:106-139 in numpy fp32.  ``pack`` holds param_mean/param_std and either
+    u_base/w_shp_base/w_exp_base (sparse) or u/w_shp/w_exp (dense).  Returns (B,3,N) fp32."""
+    param = np.asarray(param, np.float32)
+    if param.shape[1] != 62:
+        raise RuntimeError('length of params mismatch')                   # :116-119
+    if whitening:
+        param = param * pack['param_std'][:62] + pack['param_mean'][:62]   # :117
+    p, offset, a_shp, a_exp = parse_param_62(param)
+    if dense:
+        u, ws, we = pack['u'], pack['w_shp'], pack['w_exp']
+    else:
+        u, ws, we = pack['u_base'], pack['w_shp_base'], pack['w_exp_base']
+    shape = u.reshape(1, -1, 1) + ws @ a_shp + we @ a_exp                  # :125 / :133
+    n = shape.shape[1] // 3
+    shape = shape.reshape(-1, n, 3).transpose(0, 2, 1)                     # view(-1,N,3).transpose(1,2)
+    vertex = p @ shape + offset
+    if transform:
+        vertex[:, 1, :] = STD_SIZE + 1 - vertex[:, 1, :]                   # :129 / :137
+    return vertex.astype(np.float32)
+
+
+def gather_sparse_basis(pack3dmm: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """ParamsPack, utils/params.py:24-32: u = u_shp + u_exp and the keypoint gathers."""
+    kp = pack3dmm['keypoints']
+    u = pack3dmm['u_shp'] + pack3dmm['u_exp']
+    return dict(param_mean=pack3dmm['param_mean'], param_std=pack3dmm['param_std'], u=u,
+                w_shp=pack3dmm['w_shp'], w_exp=pack3dmm['w_exp'],
+                u_base=u[kp].reshape(-1, 1), w_shp_base=pack3dmm['w_shp'][kp],
+                w_exp_base=pack3dmm['w_exp'][kp], keypoints=kp)
+
+
+# ---- per-face numpy API pieces used by get_all_outputs (utils/inference.py) -----------------
+
+def crop_img(img: np.ndarray, roi_box) -> np.ndarray:
+    """utils/inference.py:95-125: integer-rounded ROI with zero padding (bit-exact index work)."""
+    h, w = img.shape[:2]
+    sx, sy, ex, ey = [int(round(v)) for v in roi_box[:4]]
+    dh, dw = ey - sy, ex - sx
+    res = np.zeros((dh, dw) + img.shape[2:], dtype=np.uint8)
+    dsx = -sx if sx < 0 else 0
+    sx = max(sx, 0)
+    dex = dw - (ex - w) if ex > w else dw
+    ex = min(ex, w)
+    dsy = -sy if sy < 0 else 0
+    sy = max(sy, 0)
+    dey = dh - (ey - h) if ey > h else dh
+    ey = min(ey, h)
+    res[dsy:dey, dsx:dex] = img[sy:ey, sx:ex]
+    return res
+
+
+def rescale_to_image(vertex: np.ndarray, roi_box) -> np.ndarray:
+    """utils/inference.py:127-138 (_predict_vertices after param2vert)."""
+    sx, sy, ex, ey = roi_box[:4]
+    scale_x = (ex - sx) / 120
+    scale_y = (ey - sy) / 120
+    vertex = vertex.copy()
+    vertex[0, :] = vertex[0, :] * scale_x + sx
+    vertex[1, :] = vertex[1, :] * scale_y + sy
+    vertex[2, :] *= (scale_x + scale_y) / 2
+    return vertex
+
+
+def P2sRt(P: np.ndarray):
+    """utils/inference.py:33-43."""
+    t3d = P[:, 3]
+    R1, R2 = P[0:1, :3], P[1:2, :3]
+    s = (np.linalg.norm(R1) + np.linalg.norm(R2)) / 2.0
+    r1 = R1 / np.linalg.norm(R1)
+    r2 = R2 / np.linalg.norm(R2)
+    r3 = np.cross(r1, r2)
+    return s, np.concatenate((r1, r2, r3), 0), t3d
+
+
+def matrix2angle_corr(R: np.ndarray):
+    """utils/inference.py:45-62 (degrees)."""
+    if R[2, 0] != 1 and R[2, 0] != -1:
+        x = asin(R[2, 0])
+        y = atan2(R[1, 2] / cos(x), R[2, 2] / cos(x))
+        z = atan2(R[0, 1] / cos(x), R[0, 0] / cos(x))
+    else:
+        z = 0
+        if R[2, 0] == -1:
+            x = np.pi / 2
+            y = z + atan2(R[0, 1], R[0, 2])
+        else:
+            x = -np.pi / 2
+            y = -z + atan2(-R[0, 1], -R[0, 2])
+    return [x * 180 / np.pi, y * 180 / np.pi, z * 180 / np.pi]
+
+
+def predict_pose(param: np.ndarray, pack, roi_box) -> Tuple[list, np.ndarray]:
+    """utils/inference.py:86-92 + :146-157: (angles[deg], t3d in image coordinates)."""
+    param = param * pack['param_std'][:62] + pack['param_mean'][:62]
+    Ps = param[:12].reshape(3, -1)
+    _, R, t3d = P2sRt(Ps)
+    angles = matrix2angle_corr(R)
+    sx, sy, ex, ey = roi_box[:4]
+    t3d = t3d.copy()
+    t3d[0] = t3d[0] * ((ex - sx) / 120) + sx
+    t3d[1] = t3d[1] * ((ey - sy) / 120) + sy
+    return angles, t3d
+
+
+def nme_vs_reference(lmk_new: np.ndarray, lmk_ref: np.ndarray) -> np.ndarray:
+    """Landmark NME of ``lmk_new`` against ``lmk_ref`` (both (B,>=2,68) in crop coordinates)
+    with the bbox-sqrt-area normaliser of benchmark_aflw2000.py:127-135."""
+    out = []
+    for fit, gt in zip(lmk_new, lmk_ref):
+        minx, maxx = gt[0].min(), gt[0].max()
+        miny, maxy = gt[1].min(), gt[1].max()
+        llength = sqrt(float((maxx - minx) * (maxy - miny)))
+        dis = np.sqrt(((fit[:2] - gt[:2]) ** 2).sum(0)).mean()
+        out.append(dis / llength)
+    return np.asarray(out, np.float32)
+
+
+def max_rel_err(new, ref) -> float:
+    """Parity figure of merit: max|new-ref| / max|ref|."""
+    new = np.asarray(new, np.float64)
+    ref = np.asarray(ref, np.float64)
+    return float(np.abs(new - ref).max() / max(np.abs(ref).max(), 1e-30))

@@ -1,0 +1,90 @@
+"""ctypes binding of ``libsynergy_b200.so`` (include/synergy_b200.h).
+
+There is no fallback: if the library is missing or cannot be loaded, importing the symbols
+raises, and every product entry point above it fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libsynergy_b200.so')
+HEADER_PATH = os.path.join(_PKG, '..', 'include', 'synergy_b200.h')
+
+SYN_OK = 0
+ERR_NAMES = {1: 'SYN_ERR_INVALID', 2: 'SYN_ERR_CUDA', 3: 'SYN_ERR_STATE', 4: 'SYN_ERR_SHAPE',
+             5: 'SYN_ERR_NOMEM', 6: 'SYN_ERR_UNSUPPORTED'}
+ENGINE_SIMT_FP32, ENGINE_TC_BF16X3 = 0, 1
+
+
+class SynergyLibError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f'{ERR_NAMES.get(code, code)}: {msg}')
+        self.code = code
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('cin', 'cout', 'ksize', 'stride', 'groups', 'relu6',
+                                         'h_in', 'h_out', 'residual')]
+
+
+_P, _F, _I, _L = C.c_void_p, C.c_void_p, C.c_int, C.c_int64
+# name -> (restype, argtypes); float*/void* travel as integer addresses (tensor.data_ptr()).
+SIGNATURES = {
+    'syn_abi_version': (_I, []),
+    'syn_last_error': (C.c_char_p, []),
+    'syn_num_conv_layers': (_I, []),
+    'syn_conv_desc': (_I, [_I, C.POINTER(ConvDesc)]),
+    'syn_create': (_I, [_I, C.POINTER(_P)]),
+    'syn_destroy': (None, [_P]),
+    'syn_set_conv_bn': (_I, [_P, _I, _F, _L, _F, _F, _F, _F, C.c_float]),
+    'syn_set_heads': (_I, [_P, _F, _F, _F, _F, _F, _F]),
+    'syn_set_whitening': (_I, [_P, _F, _F]),
+    'syn_set_basis_sparse': (_I, [_P, _F, _F, _F, _I]),
+    'syn_set_basis_dense': (_I, [_P, _F, _F, _F, _L]),
+    'syn_commit': (_I, [_P]),
+    'syn_set_engine': (_I, [_P, _I]),
+    'syn_get_engine': (_I, [_P]),
+    'syn_forward': (_I, [_P, _F, _I, _F, _F, _P]),
+    'syn_reconstruct': (_I, [_P, _F, _I, _I, _I, _I, _F, _P]),
+    'syn_forward_landmarks': (_I, [_P, _F, _I, _F, _F, _P]),
+    'syn_forward_landmarks_host': (_I, [_P, _F, _I, _F, _F]),
+    'syn_launch_count': (_L, [_P]),
+    'syn_debug_forward_until': (_I, [_P, _F, _I, _I, _F, _P]),
+}
+
+
+def declared_symbols(header: str = HEADER_PATH):
+    """Function names declared in include/synergy_b200.h (used by the symbol-export test)."""
+    text = open(header).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(syn_[a-z0-9_]+)\s*\(', text)))
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library once; raise (never fall back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} not found: build it with `python -m synergynet_b200.build` '
+            '(nvcc, sm_100a). There is no CPU or eager fallback for this path.')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.syn_abi_version() != 1:
+        raise RuntimeError('libsynergy_b200.so ABI version mismatch; rebuild')
+    _lib = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != SYN_OK:
+        raise SynergyLibError(code, load().syn_last_error().decode(errors='replace'))

@@ -1,0 +1,532 @@
+// C-ABI implementation of the SynergyNet inference hot path for B200 (sm_100a).
+// See include/synergy_b200.h for the contract and the reference lines each entry replaces.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_simt.cuh"
+
+using namespace syn;
+
+namespace {
+
+struct HostConv {
+  std::vector<float> w, g, b, m, v;
+  float eps = 1e-5f;
+  bool set = false;
+};
+
+struct DevConv {
+  float* w = nullptr;     // SIMT layout (stem [27][32], pointwise [K][N], depthwise [9][C])
+  float* bias = nullptr;  // folded BN bias
+};
+
+}  // namespace
+
+struct syn_handle {
+  int device = 0;
+  int sm_count = 0;
+  int engine = SYN_ENGINE_SIMT_FP32;
+  bool committed = false;
+  int64_t launches = 0;
+
+  HostConv hconv[kNumConv];
+  std::vector<float> h_head_w, h_head_b;       // (62,1280), (62)
+  std::vector<float> h_mean, h_std;            // 62 each
+  std::vector<float> h_sparse;                 // planar [51][3][sp_pad]
+  std::vector<float> h_dense;                  // planar [51][3][dn_pad]
+  int n_pts = 0, sp_pad = 0;
+  int64_t n_vert = 0, dn_pad = 0;
+  bool heads_set = false, whiten_set = false, sparse_dirty = false, dense_dirty = false;
+
+  // device-side constants
+  float* d_weights = nullptr;                  // one slab for all conv weights + biases
+  DevConv dconv[kNumConv];
+  float *d_head_w = nullptr, *d_head_b = nullptr, *d_mean = nullptr, *d_std = nullptr;
+  float *d_sparse = nullptr, *d_dense = nullptr;
+
+  // activation workspace (NHWC fp32), grown on demand
+  int ws_batch = 0;
+  float *buf_io[2] = {nullptr, nullptr}, *buf_hid = nullptr, *buf_dw = nullptr;
+  float* d_params_tmp = nullptr;               // (ws_batch, 62) for the fused landmark call
+
+  // host-buffer pipeline
+  cudaStream_t s_copy = nullptr, s_compute = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  float* d_stage_x[2] = {nullptr, nullptr};
+  float* d_stage_lmk = nullptr;
+  float* d_stage_par = nullptr;
+  int stage_chunk = 0, stage_batch = 0;
+};
+
+namespace {
+
+// per-face activation element counts (floats) of the four workspace buffers
+constexpr size_t kIoPerFace = 60 * 60 * 32;       // stem output is the largest block in/out
+constexpr size_t kHidPerFace = 60 * 60 * 96;      // block 2 expand output
+constexpr size_t kDwPerFace = 30 * 30 * 144;      // block 3 depthwise output (> 60*60*32)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int cur;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int ensure_workspace(syn_handle* h, int batch) {
+  if (batch <= h->ws_batch) return SYN_OK;
+  SYN_CUDA(cudaDeviceSynchronize());
+  cudaFree(h->buf_io[0]); cudaFree(h->buf_io[1]); cudaFree(h->buf_hid); cudaFree(h->buf_dw);
+  cudaFree(h->d_params_tmp);
+  h->buf_io[0] = h->buf_io[1] = h->buf_hid = h->buf_dw = h->d_params_tmp = nullptr;
+  h->ws_batch = 0;
+  const size_t b = (size_t)batch;
+  SYN_CUDA(cudaMalloc(&h->buf_io[0], b * kIoPerFace * sizeof(float)));
+  SYN_CUDA(cudaMalloc(&h->buf_io[1], b * kIoPerFace * sizeof(float)));
+  SYN_CUDA(cudaMalloc(&h->buf_hid, b * kHidPerFace * sizeof(float)));
+  SYN_CUDA(cudaMalloc(&h->buf_dw, b * kDwPerFace * sizeof(float)));
+  SYN_CUDA(cudaMalloc(&h->d_params_tmp, b * kNumParams * sizeof(float)));
+  h->ws_batch = batch;
+  return SYN_OK;
+}
+
+// ---- launches -------------------------------------------------------------------------------
+int launch_pointwise_simt(syn_handle* h, const float* A, const DevConv& w, const float* residual,
+                          float* out, int M, int K, int N, int relu6, cudaStream_t st) {
+  if (N >= 64) {
+    dim3 grid((M + 127) / 128, (N + 63) / 64);
+    pointwise_gemm_kernel<128, 64, 8, 4><<<grid, 256, 0, st>>>(A, w.w, w.bias, residual, out, M, K, N, relu6);
+  } else if (N > 16) {
+    dim3 grid((M + 127) / 128, (N + 31) / 32);
+    pointwise_gemm_kernel<128, 32, 4, 4><<<grid, 256, 0, st>>>(A, w.w, w.bias, residual, out, M, K, N, relu6);
+  } else {
+    dim3 grid((M + 255) / 256, (N + 15) / 16);
+    pointwise_gemm_kernel<256, 16, 4, 4><<<grid, 256, 0, st>>>(A, w.w, w.bias, residual, out, M, K, N, relu6);
+  }
+  SYN_LAUNCH_CHECK("pointwise_gemm_kernel");
+  h->launches++;
+  return SYN_OK;
+}
+
+int launch_pointwise(syn_handle* h, const float* A, int layer, const float* residual, float* out,
+                     int M, cudaStream_t st) {
+  const ConvDesc& c = plan().conv[layer];
+  return launch_pointwise_simt(h, A, h->dconv[layer], residual, out, M, c.cin, c.cout, c.relu6, st);
+}
+
+int launch_depthwise(syn_handle* h, const float* x, int layer, float* y, int batch, cudaStream_t st) {
+  const ConvDesc& c = plan().conv[layer];
+  const size_t total = (size_t)batch * c.h_out * c.h_out * (c.cout / 4);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  depthwise3x3_kernel<<<grid, 256, 0, st>>>(x, h->dconv[layer].w, h->dconv[layer].bias, y, batch,
+                                           c.cout, c.h_in, c.h_out, c.stride);
+  SYN_LAUNCH_CHECK("depthwise3x3_kernel");
+  h->launches++;
+  return SYN_OK;
+}
+
+// Runs the backbone.  When stop_layer >= 0 the activation of that conv is copied to dbg_out and
+// the function returns early.  Otherwise params (B,62) [and pool (B,1280)] are produced.
+int run_backbone(syn_handle* h, const float* x, int batch, float* params, float* pool,
+                 int stop_layer, float* dbg_out, cudaStream_t st) {
+  const Plan& P = plan();
+  int rc = ensure_workspace(h, batch);
+  if (rc != SYN_OK) return rc;
+
+  auto dbg = [&](int layer, const float* buf) -> int {
+    const ConvDesc& c = P.conv[layer];
+    const size_t n = (size_t)batch * c.h_out * c.h_out * c.cout;
+    SYN_CUDA(cudaMemcpyAsync(dbg_out, buf, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return SYN_OK;
+  };
+
+  int cur = 0;
+  stem_conv3x3s2_kernel<<<batch * 60, kStemThreads, 0, st>>>(x, h->dconv[0].w, h->dconv[0].bias,
+                                                            h->buf_io[cur], batch);
+  SYN_LAUNCH_CHECK("stem_conv3x3s2_kernel");
+  h->launches++;
+  if (stop_layer == 0) return dbg(0, h->buf_io[cur]);
+
+  int li = 1;
+  while (P.conv[li].kind != kLast) {
+    const float* block_in = h->buf_io[cur];
+    const float* dw_in = block_in;
+    if (P.conv[li].kind == kExpand) {
+      const ConvDesc& e = P.conv[li];
+      rc = launch_pointwise(h, block_in, li, nullptr, h->buf_hid, batch * e.h_in * e.h_in, st);
+      if (rc != SYN_OK) return rc;
+      if (stop_layer == li) return dbg(li, h->buf_hid);
+      dw_in = h->buf_hid;
+      ++li;
+    }
+    rc = launch_depthwise(h, dw_in, li, h->buf_dw, batch, st);
+    if (rc != SYN_OK) return rc;
+    if (stop_layer == li) return dbg(li, h->buf_dw);
+    ++li;
+    const ConvDesc& p = P.conv[li];
+    rc = launch_pointwise(h, h->buf_dw, li, p.residual ? block_in : nullptr, h->buf_io[cur ^ 1],
+                          batch * p.h_out * p.h_out, st);
+    if (rc != SYN_OK) return rc;
+    cur ^= 1;
+    if (stop_layer == li) return dbg(li, h->buf_io[cur]);
+    ++li;
+  }
+  const ConvDesc& last = P.conv[li];
+  rc = launch_pointwise(h, h->buf_io[cur], li, nullptr, h->buf_hid, batch * last.h_in * last.h_in, st);
+  if (rc != SYN_OK) return rc;
+  if (stop_layer == li) return dbg(li, h->buf_hid);
+
+  pool_heads_kernel<<<batch, 256, 0, st>>>(h->buf_hid, h->d_head_w, h->d_head_b, params, pool,
+                                          last.h_out * last.h_out);
+  SYN_LAUNCH_CHECK("pool_heads_kernel");
+  h->launches++;
+  return SYN_OK;
+}
+
+int run_reconstruct(syn_handle* h, const float* params, int batch, int dense, int whitening,
+                    int transform, float* out, cudaStream_t st) {
+  if (dense) {
+    if (h->d_dense == nullptr) return fail(SYN_ERR_STATE, "dense basis not set (syn_set_basis_dense)");
+    constexpr int F = 16;
+    dim3 grid((unsigned)(h->dn_pad / 128), (batch + F - 1) / F);
+    reconstruct_kernel<F><<<grid, 128, 0, st>>>(h->d_dense, params, h->d_mean, h->d_std, out, batch,
+                                               (int)h->n_vert, (int)h->dn_pad, whitening, transform);
+  } else {
+    if (h->d_sparse == nullptr) return fail(SYN_ERR_STATE, "sparse basis not set (syn_set_basis_sparse)");
+    constexpr int F = 8;
+    dim3 grid(h->sp_pad / 128, (batch + F - 1) / F);
+    reconstruct_kernel<F><<<grid, 128, 0, st>>>(h->d_sparse, params, h->d_mean, h->d_std, out, batch,
+                                               h->n_pts, h->sp_pad, whitening, transform);
+  }
+  SYN_LAUNCH_CHECK("reconstruct_kernel");
+  h->launches++;
+  return SYN_OK;
+}
+
+// planar [51][3][pad] from the reference's interleaved (3N,1)/(3N,40)/(3N,10) buffers
+void pack_basis(std::vector<float>& dst, const float* u, const float* ws, const float* we, int64_t n,
+                int64_t pad) {
+  dst.assign((size_t)(kNumAlpha + 1) * 3 * pad, 0.f);
+  for (int64_t v = 0; v < n; ++v)
+    for (int c = 0; c < 3; ++c) {
+      const int64_t row = 3 * v + c;
+      dst[(size_t)(0 * 3 + c) * pad + v] = u[row];
+      for (int k = 0; k < kNumShp; ++k) dst[(size_t)((1 + k) * 3 + c) * pad + v] = ws[row * kNumShp + k];
+      for (int k = 0; k < kNumExp; ++k)
+        dst[(size_t)((1 + kNumShp + k) * 3 + c) * pad + v] = we[row * kNumExp + k];
+    }
+}
+
+int upload(float** dptr, const std::vector<float>& src) {
+  if (*dptr != nullptr) { cudaFree(*dptr); *dptr = nullptr; }
+  SYN_CUDA(cudaMalloc(dptr, src.size() * sizeof(float)));
+  SYN_CUDA(cudaMemcpy(*dptr, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return SYN_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int syn_abi_version(void) { return SYN_ABI_VERSION; }
+const char* syn_last_error(void) { return last_error_buf(); }
+int syn_num_conv_layers(void) { return kNumConv; }
+
+int syn_conv_desc(int layer, syn_conv_desc_t* out) {
+  if (layer < 0 || layer >= kNumConv || out == nullptr) return fail(SYN_ERR_INVALID, "syn_conv_desc: bad layer %d", layer);
+  const ConvDesc& c = plan().conv[layer];
+  out->cin = c.cin; out->cout = c.cout; out->ksize = c.ksize; out->stride = c.stride;
+  out->groups = c.groups; out->relu6 = c.relu6; out->h_in = c.h_in; out->h_out = c.h_out;
+  out->residual = c.residual;
+  return SYN_OK;
+}
+
+int syn_create(int device, syn_handle_t** out) {
+  if (out == nullptr) return fail(SYN_ERR_INVALID, "syn_create: out is null");
+  *out = nullptr;
+  int ndev = 0;
+  SYN_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(SYN_ERR_INVALID, "syn_create: device %d of %d", device, ndev);
+  cudaDeviceProp prop;
+  SYN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SYN_ERR_UNSUPPORTED, "syn_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(SYN_ERR_CUDA, "syn_create: cannot select device %d", device);
+  syn_handle* h = new (std::nothrow) syn_handle();
+  if (h == nullptr) return fail(SYN_ERR_NOMEM, "syn_create: out of host memory");
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  SYN_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+  SYN_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    SYN_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+    SYN_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+  }
+  *out = h;
+  return SYN_OK;
+}
+
+void syn_destroy(syn_handle_t* h) {
+  if (h == nullptr) return;
+  DeviceGuard g(h->device);
+  cudaDeviceSynchronize();
+  cudaFree(h->d_weights); cudaFree(h->d_head_w); cudaFree(h->d_head_b); cudaFree(h->d_mean);
+  cudaFree(h->d_std); cudaFree(h->d_sparse); cudaFree(h->d_dense);
+  cudaFree(h->buf_io[0]); cudaFree(h->buf_io[1]); cudaFree(h->buf_hid); cudaFree(h->buf_dw);
+  cudaFree(h->d_params_tmp);
+  cudaFree(h->d_stage_x[0]); cudaFree(h->d_stage_x[1]); cudaFree(h->d_stage_lmk); cudaFree(h->d_stage_par);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+  }
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->s_compute) cudaStreamDestroy(h->s_compute);
+  delete h;
+}
+
+int syn_set_conv_bn(syn_handle_t* h, int layer, const float* w, int64_t w_numel, const float* g,
+                    const float* b, const float* m, const float* v, float eps) {
+  if (h == nullptr || w == nullptr || g == nullptr || b == nullptr || m == nullptr || v == nullptr)
+    return fail(SYN_ERR_INVALID, "syn_set_conv_bn: null argument");
+  if (layer < 0 || layer >= kNumConv) return fail(SYN_ERR_INVALID, "syn_set_conv_bn: layer %d out of range", layer);
+  const ConvDesc& c = plan().conv[layer];
+  const int64_t expect = (int64_t)c.cout * (c.cin / c.groups) * c.ksize * c.ksize;
+  if (w_numel != expect)
+    return fail(SYN_ERR_SHAPE, "syn_set_conv_bn: layer %d expects %lld weights, got %lld", layer,
+                (long long)expect, (long long)w_numel);
+  HostConv& hc = h->hconv[layer];
+  hc.w.assign(w, w + w_numel);
+  hc.g.assign(g, g + c.cout); hc.b.assign(b, b + c.cout);
+  hc.m.assign(m, m + c.cout); hc.v.assign(v, v + c.cout);
+  hc.eps = eps;
+  hc.set = true;
+  h->committed = false;
+  return SYN_OK;
+}
+
+int syn_set_heads(syn_handle_t* h, const float* w_ori, const float* b_ori, const float* w_shape,
+                  const float* b_shape, const float* w_exp, const float* b_exp) {
+  if (h == nullptr || !w_ori || !b_ori || !w_shape || !b_shape || !w_exp || !b_exp)
+    return fail(SYN_ERR_INVALID, "syn_set_heads: null argument");
+  h->h_head_w.resize((size_t)kNumParams * kLastCh);
+  h->h_head_b.resize(kNumParams);
+  memcpy(h->h_head_w.data(), w_ori, sizeof(float) * 12 * kLastCh);
+  memcpy(h->h_head_w.data() + 12 * kLastCh, w_shape, sizeof(float) * 40 * kLastCh);
+  memcpy(h->h_head_w.data() + 52 * kLastCh, w_exp, sizeof(float) * 10 * kLastCh);
+  memcpy(h->h_head_b.data(), b_ori, sizeof(float) * 12);
+  memcpy(h->h_head_b.data() + 12, b_shape, sizeof(float) * 40);
+  memcpy(h->h_head_b.data() + 52, b_exp, sizeof(float) * 10);
+  h->heads_set = true;
+  h->committed = false;
+  return SYN_OK;
+}
+
+int syn_set_whitening(syn_handle_t* h, const float* mean, const float* stdv) {
+  if (h == nullptr || mean == nullptr || stdv == nullptr) return fail(SYN_ERR_INVALID, "syn_set_whitening: null argument");
+  h->h_mean.assign(mean, mean + kNumParams);
+  h->h_std.assign(stdv, stdv + kNumParams);
+  h->whiten_set = true;
+  h->committed = false;
+  return SYN_OK;
+}
+
+int syn_set_basis_sparse(syn_handle_t* h, const float* u, const float* ws, const float* we, int n_pts) {
+  if (h == nullptr || !u || !ws || !we || n_pts <= 0) return fail(SYN_ERR_INVALID, "syn_set_basis_sparse: bad argument");
+  h->n_pts = n_pts;
+  h->sp_pad = (n_pts + 127) / 128 * 128;
+  pack_basis(h->h_sparse, u, ws, we, n_pts, h->sp_pad);
+  h->sparse_dirty = true;
+  h->committed = false;
+  return SYN_OK;
+}
+
+int syn_set_basis_dense(syn_handle_t* h, const float* u, const float* ws, const float* we, int64_t n_vert) {
+  if (h == nullptr || !u || !ws || !we || n_vert <= 0 || n_vert > (1 << 28))
+    return fail(SYN_ERR_INVALID, "syn_set_basis_dense: bad argument");
+  h->n_vert = n_vert;
+  h->dn_pad = (n_vert + 127) / 128 * 128;
+  pack_basis(h->h_dense, u, ws, we, n_vert, h->dn_pad);
+  h->dense_dirty = true;
+  h->committed = false;
+  return SYN_OK;
+}
+
+int syn_commit(syn_handle_t* h) {
+  if (h == nullptr) return fail(SYN_ERR_INVALID, "syn_commit: null handle");
+  for (int l = 0; l < kNumConv; ++l)
+    if (!h->hconv[l].set) return fail(SYN_ERR_STATE, "syn_commit: conv layer %d was never set", l);
+  if (!h->heads_set) return fail(SYN_ERR_STATE, "syn_commit: heads not set");
+  if (!h->whiten_set) return fail(SYN_ERR_STATE, "syn_commit: whitening not set");
+  DeviceGuard g(h->device);
+  SYN_CUDA(cudaDeviceSynchronize());
+
+  // ---- fold BN (eval) into conv weight/bias and lay out for the SIMT kernels -----------------
+  const Plan& P = plan();
+  size_t total = 0;
+  size_t w_off[kNumConv], b_off[kNumConv];
+  for (int l = 0; l < kNumConv; ++l) {
+    const ConvDesc& c = P.conv[l];
+    const size_t nw = (size_t)c.cout * (c.cin / c.groups) * c.ksize * c.ksize;
+    w_off[l] = total; total += (nw + 63) / 64 * 64;
+    b_off[l] = total; total += ((size_t)c.cout + 63) / 64 * 64;
+  }
+  std::vector<float> slab(total, 0.f);
+  for (int l = 0; l < kNumConv; ++l) {
+    const ConvDesc& c = P.conv[l];
+    const HostConv& hc = h->hconv[l];
+    float* W = slab.data() + w_off[l];
+    float* B = slab.data() + b_off[l];
+    const int cpg = c.cin / c.groups, kk = c.ksize * c.ksize;
+    for (int co = 0; co < c.cout; ++co) {
+      const double scale = (double)hc.g[co] / sqrt((double)hc.v[co] + (double)hc.eps);
+      B[co] = (float)((double)hc.b[co] - (double)hc.m[co] * scale);
+      for (int ci = 0; ci < cpg; ++ci)
+        for (int t = 0; t < kk; ++t) {
+          const float wf = (float)((double)hc.w[((size_t)co * cpg + ci) * kk + t] * scale);
+          size_t dst;
+          if (c.kind == kStem) dst = (size_t)(ci * kk + t) * c.cout + co;           // [27][32]
+          else if (c.kind == kDepthwise) dst = (size_t)t * c.cout + co;              // [9][C]
+          else dst = (size_t)ci * c.cout + co;                                       // [K][N]
+          W[dst] = wf;
+        }
+    }
+  }
+  if (h->d_weights) { cudaFree(h->d_weights); h->d_weights = nullptr; }
+  SYN_CUDA(cudaMalloc(&h->d_weights, total * sizeof(float)));
+  SYN_CUDA(cudaMemcpy(h->d_weights, slab.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+  for (int l = 0; l < kNumConv; ++l) {
+    h->dconv[l].w = h->d_weights + w_off[l];
+    h->dconv[l].bias = h->d_weights + b_off[l];
+  }
+  int rc;
+  if ((rc = upload(&h->d_head_w, h->h_head_w)) != SYN_OK) return rc;
+  if ((rc = upload(&h->d_head_b, h->h_head_b)) != SYN_OK) return rc;
+  if ((rc = upload(&h->d_mean, h->h_mean)) != SYN_OK) return rc;
+  if ((rc = upload(&h->d_std, h->h_std)) != SYN_OK) return rc;
+  if (h->sparse_dirty) {
+    if ((rc = upload(&h->d_sparse, h->h_sparse)) != SYN_OK) return rc;
+    h->sparse_dirty = false;
+  }
+  if (h->dense_dirty) {
+    if ((rc = upload(&h->d_dense, h->h_dense)) != SYN_OK) return rc;
+    h->dense_dirty = false;
+    std::vector<float>().swap(h->h_dense);       // 32 MB host copy no longer needed
+  }
+  h->committed = true;
+  return SYN_OK;
+}
+
+int syn_set_engine(syn_handle_t* h, int engine) {
+  if (h == nullptr) return fail(SYN_ERR_INVALID, "syn_set_engine: null handle");
+  if (engine != SYN_ENGINE_SIMT_FP32)
+    return fail(SYN_ERR_UNSUPPORTED, "syn_set_engine: engine %d not available in this build", engine);
+  h->engine = engine;
+  return SYN_OK;
+}
+int syn_get_engine(const syn_handle_t* h) { return h ? h->engine : -1; }
+
+#define SYN_CHECK_READY(h, name)                                                         \
+  if ((h) == nullptr) return fail(SYN_ERR_INVALID, name ": null handle");                \
+  if (!(h)->committed) return fail(SYN_ERR_STATE, name ": weights not committed (syn_commit)")
+
+int syn_forward(syn_handle_t* h, const float* x, int batch, float* params, float* pool, void* stream) {
+  SYN_CHECK_READY(h, "syn_forward");
+  if (x == nullptr || params == nullptr || batch <= 0) return fail(SYN_ERR_INVALID, "syn_forward: bad argument");
+  DeviceGuard g(h->device);
+  return run_backbone(h, x, batch, params, pool, -1, nullptr, (cudaStream_t)stream);
+}
+
+int syn_reconstruct(syn_handle_t* h, const float* params, int batch, int dense, int whitening,
+                    int transform, float* out, void* stream) {
+  SYN_CHECK_READY(h, "syn_reconstruct");
+  if (params == nullptr || out == nullptr || batch <= 0) return fail(SYN_ERR_INVALID, "syn_reconstruct: bad argument");
+  DeviceGuard g(h->device);
+  return run_reconstruct(h, params, batch, dense, whitening, transform, out, (cudaStream_t)stream);
+}
+
+int syn_forward_landmarks(syn_handle_t* h, const float* x, int batch, float* params, float* lmk,
+                          void* stream) {
+  SYN_CHECK_READY(h, "syn_forward_landmarks");
+  if (x == nullptr || lmk == nullptr || batch <= 0) return fail(SYN_ERR_INVALID, "syn_forward_landmarks: bad argument");
+  DeviceGuard g(h->device);
+  int rc = ensure_workspace(h, batch);
+  if (rc != SYN_OK) return rc;
+  float* p = params ? params : h->d_params_tmp;
+  rc = run_backbone(h, x, batch, p, nullptr, -1, nullptr, (cudaStream_t)stream);
+  if (rc != SYN_OK) return rc;
+  return run_reconstruct(h, p, batch, 0, 1, 1, lmk, (cudaStream_t)stream);
+}
+
+int syn_forward_landmarks_host(syn_handle_t* h, const float* x_host, int batch, float* params_host,
+                               float* lmk_host) {
+  SYN_CHECK_READY(h, "syn_forward_landmarks_host");
+  if (x_host == nullptr || lmk_host == nullptr || batch <= 0)
+    return fail(SYN_ERR_INVALID, "syn_forward_landmarks_host: bad argument");
+  if (h->n_pts <= 0) return fail(SYN_ERR_STATE, "syn_forward_landmarks_host: sparse basis not set");
+  DeviceGuard g(h->device);
+  const int chunk = std::min(batch, 256);
+  const size_t x_face = (size_t)3 * kImg * kImg;
+  const size_t lmk_face = (size_t)3 * h->n_pts;
+  if (chunk > h->stage_chunk || batch > h->stage_batch) {
+    SYN_CUDA(cudaDeviceSynchronize());
+    cudaFree(h->d_stage_x[0]); cudaFree(h->d_stage_x[1]); cudaFree(h->d_stage_lmk); cudaFree(h->d_stage_par);
+    h->d_stage_x[0] = h->d_stage_x[1] = h->d_stage_lmk = h->d_stage_par = nullptr;
+    h->stage_chunk = h->stage_batch = 0;
+    SYN_CUDA(cudaMalloc(&h->d_stage_x[0], chunk * x_face * sizeof(float)));
+    SYN_CUDA(cudaMalloc(&h->d_stage_x[1], chunk * x_face * sizeof(float)));
+    SYN_CUDA(cudaMalloc(&h->d_stage_lmk, batch * lmk_face * sizeof(float)));
+    SYN_CUDA(cudaMalloc(&h->d_stage_par, (size_t)batch * kNumParams * sizeof(float)));
+    h->stage_chunk = chunk;
+    h->stage_batch = batch;
+  }
+  int rc = ensure_workspace(h, chunk);
+  if (rc != SYN_OK) return rc;
+  int slot = 0, issued = 0;
+  for (int b0 = 0; b0 < batch; b0 += chunk, slot ^= 1, ++issued) {
+    const int nb = std::min(chunk, batch - b0);
+    if (issued >= 2) SYN_CUDA(cudaStreamWaitEvent(h->s_copy, h->ev_done[slot], 0));
+    SYN_CUDA(cudaMemcpyAsync(h->d_stage_x[slot], x_host + (size_t)b0 * x_face, nb * x_face * sizeof(float),
+                             cudaMemcpyHostToDevice, h->s_copy));
+    SYN_CUDA(cudaEventRecord(h->ev_h2d[slot], h->s_copy));
+    SYN_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_h2d[slot], 0));
+    float* par = h->d_stage_par + (size_t)b0 * kNumParams;
+    rc = run_backbone(h, h->d_stage_x[slot], nb, par, nullptr, -1, nullptr, h->s_compute);
+    if (rc != SYN_OK) return rc;
+    SYN_CUDA(cudaEventRecord(h->ev_done[slot], h->s_compute));
+    rc = run_reconstruct(h, par, nb, 0, 1, 1, h->d_stage_lmk + (size_t)b0 * lmk_face, h->s_compute);
+    if (rc != SYN_OK) return rc;
+  }
+  SYN_CUDA(cudaMemcpyAsync(lmk_host, h->d_stage_lmk, batch * lmk_face * sizeof(float),
+                           cudaMemcpyDeviceToHost, h->s_compute));
+  if (params_host != nullptr)
+    SYN_CUDA(cudaMemcpyAsync(params_host, h->d_stage_par, (size_t)batch * kNumParams * sizeof(float),
+                             cudaMemcpyDeviceToHost, h->s_compute));
+  SYN_CUDA(cudaStreamSynchronize(h->s_compute));
+  SYN_CUDA(cudaStreamSynchronize(h->s_copy));
+  return SYN_OK;
+}
+
+int64_t syn_launch_count(const syn_handle_t* h) { return h ? h->launches : -1; }
+
+int syn_debug_forward_until(syn_handle_t* h, const float* x, int batch, int layer, float* out, void* stream) {
+  SYN_CHECK_READY(h, "syn_debug_forward_until");
+  if (x == nullptr || out == nullptr || batch <= 0 || layer < 0 || layer >= kNumConv)
+    return fail(SYN_ERR_INVALID, "syn_debug_forward_until: bad argument");
+  DeviceGuard g(h->device);
+  return run_backbone(h, x, batch, h->d_params_tmp, nullptr, layer, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+"""Drop-in twin of the reference ``model_building.py`` for the inference hot path.
+
+Same class names, constructor arguments, attributes, ``state_dict`` keys and method signatures
+(reference model_building.py:25-32,35-62,65-165,169-306); the arithmetic of ``forward_test`` and
+``reconstruct_vertex_62`` runs in the sm_100a library through ``Engine`` -- no torch conv/matmul is
+executed on the product path and nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+import threading
+import types
+from typing import Callable, Dict, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import backbone as mobilenetv2_backbone
+from .backbone import MLP_for, MLP_rev
+from .engine import Engine
+from .inference import crop_img, predict_pose_batch, rescale_vertices, square_roi
+from .params import ParamsPack, get_param_pack, set_param_pack  # noqa: F401  (re-exported)
+
+_LOSS_KEYS = ('loss_LMK_f0', 'loss_LMK_pointNet', 'loss_Param_In', 'loss_Param_S2', 'loss_Param_S1S2')
+
+
+def parse_param_62(param):
+    """Views of a (B,62) tensor: rotation (B,3,3), offset (B,3,1), alpha_shp (B,40,1),
+    alpha_exp (B,10,1) (reference model_building.py:25-32; index work, bit-exact)."""
+    cam = param[:, :12].reshape(-1, 3, 4)
+    return (cam[:, :, :3], cam[:, :, -1].reshape(-1, 3, 1),
+            param[:, 12:52].reshape(-1, 40, 1), param[:, 52:62].reshape(-1, 10, 1))
+
+
+class _Runtime:
+    """Per-device engines for one model; rebuilt when the parameters they were packed from change
+    (``load_state_dict``, in-place edits, ``.cuda()``)."""
+
+    def __init__(self):
+        self._engines: Dict[int, Engine] = {}
+        self._sig: Dict[int, tuple] = {}
+        self._lock = threading.Lock()
+        self.engine_kind = 0
+
+    @staticmethod
+    def _signature(tensors) -> tuple:
+        return tuple((t.data_ptr(), t._version) for t in tensors)
+
+    def get(self, device: torch.device, backbone_sd: Callable[[], Dict[str, torch.Tensor]],
+            basis: Optional[Callable[[], Dict[str, torch.Tensor]]]) -> Engine:
+        if device.type != 'cuda':
+            raise RuntimeError('synergynet_b200: the forward pass needs inputs on a CUDA device '
+                               '(B200); there is no CPU fallback')
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        sd = backbone_sd()
+        bs = basis() if basis is not None else {}
+        sig = self._signature(list(sd.values()) + list(bs.values()))
+        with self._lock:
+            eng = self._engines.get(idx)
+            if eng is None or self._sig.get(idx) != sig:
+                if eng is None:
+                    eng = Engine(idx)
+                    self._engines[idx] = eng
+                eng.load_backbone(sd, prefix='')
+                if bs:
+                    eng.load_3dmm(bs['param_mean'], bs['param_std'], bs['u_base'], bs['w_shp_base'],
+                                  bs['w_exp_base'], bs.get('u'), bs.get('w_shp'), bs.get('w_exp'))
+                else:   # backbone-only use: identity whitening, dummy one-point basis
+                    z = torch.zeros(62)
+                    eng.load_3dmm(z, z + 1, torch.zeros(3, 1), torch.zeros(3, 40), torch.zeros(3, 10))
+                eng.commit()
+                if self.engine_kind:
+                    eng.set_engine(self.engine_kind)
+                self._sig[idx] = sig
+        return eng
+
+
+class I2P(nn.Module):
+    """Image-to-parameter module (reference model_building.py:35-62)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        if 'mobilenet_v2' in self.args.arch:
+            self.backbone = getattr(mobilenetv2_backbone, args.arch)(pretrained=False)
+        elif any(k in self.args.arch for k in ('mobilenet', 'resnet', 'ghostnet', 'resnest')):
+            raise RuntimeError(f"arch '{args.arch}': only mobilenet_v2 is built for sm_100a in this "
+                               'round (SURVEY.md section 8; the other backbones are not on the hot path)')
+        else:
+            raise RuntimeError("Please choose [mobilenet_v2, mobilenet_1, resnet50, or ghostnet]")
+        object.__setattr__(self, '_rt', _Runtime())
+        object.__setattr__(self, '_basis_provider', None)
+
+    def _backbone_sd(self):
+        return {k: v for k, v in self.backbone.state_dict(keep_vars=True).items()
+                if not k.endswith('num_batches_tracked')}
+
+    def _engine(self, device) -> Engine:
+        return self._rt.get(device, self._backbone_sd, self._basis_provider)
+
+    def forward_test(self, input):
+        """Testing time forward -> (param62, avgpool1280) (model_building.py:59-62)."""
+        params, pool = self._engine(input.device).forward(input, want_pool=True)
+        return params, pool
+
+    def forward(self, input, target):
+        """Training time forward (model_building.py:53-57): same backbone pass, GT cast."""
+        params, pool = self.forward_test(input)
+        return params, target.to(device=input.device, dtype=torch.float32), pool
+
+
+class _SynergyBase(nn.Module):
+    """Everything the two reference wrappers share: buffers, ``data_param``,
+    ``reconstruct_vertex_62``, ``forward_test``, ``load_weights``, ``get_all_outputs``."""
+
+    resize_interpolation = 'lanczos4'          # synergy3DMM.py:188; singleImage.py:77 uses linear
+
+    def _setup(self, args, pack: ParamsPack, device: Optional[str]):
+        tri = pack.tri if pack.tri is not None else np.zeros((3, 0), np.int64)
+        self.triangles = torch.from_numpy(np.asarray(tri).astype(np.int64) - 1).long()
+        self.I2P = I2P(args)
+        self.forwardDirection = MLP_for(68)
+        self.reverseDirection = MLP_rev(68)
+        self.loss = {k: 0.0 for k in _LOSS_KEYS}
+        for name in ('param_mean', 'param_std', 'w_shp', 'u', 'w_exp', 'u_base', 'w_shp_base', 'w_exp_base'):
+            self.register_buffer(name, torch.from_numpy(np.ascontiguousarray(getattr(pack, name))).float())
+        self.keypoints = torch.from_numpy(np.asarray(pack.keypoints)).long()
+        self.std_size = pack.std_size
+        self.face_detector = None
+        if device is not None:
+            self.triangles = self.triangles.to(device)
+            self.to(device)
+        self._refresh_data_param()
+        object.__setattr__(self.I2P, '_basis_provider', self._basis)
+
+    def _refresh_data_param(self):
+        self.data_param = [self.param_mean, self.param_std, self.w_shp_base, self.u_base, self.w_exp_base]
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        if hasattr(self, 'param_mean'):
+            self._refresh_data_param()
+        return out
+
+    def _basis(self):
+        return {n: getattr(self, n) for n in ('param_mean', 'param_std', 'u_base', 'w_shp_base',
+                                              'w_exp_base', 'u', 'w_shp', 'w_exp')}
+
+    def _engine(self, device) -> Engine:
+        return self.I2P._engine(device)
+
+    def set_engine(self, kind: int) -> None:
+        """0 = fp32 CUDA-core engine, 1 = tcgen05 bf16x3 engine (include/synergy_b200.h)."""
+        self.I2P._rt.engine_kind = int(kind)
+        for eng in self.I2P._rt._engines.values():
+            eng.set_engine(int(kind))
+
+    # ---- reference API ---------------------------------------------------------------------------
+    def reconstruct_vertex_62(self, param, whitening=True, dense=False, transform=True, lmk_pts=68):
+        """Whitened param (B,62) -> (B,3,68) landmarks or (B,3,53215) vertices in crop image
+        space (reference model_building.py:106-139)."""
+        if param.shape[1] != 62:
+            raise RuntimeError('length of params mismatch')
+        dev = param.device if param.is_cuda else self.param_mean.device
+        return self._engine(dev).reconstruct(param, dense=dense, whitening=whitening, transform=transform)
+
+    def forward_test(self, input):
+        """test time forward (model_building.py:159-162): whitened (B,62) parameters."""
+        return self._engine(input.device).forward(input)
+
+    def forward_landmarks(self, input):
+        """forward_test + reconstruct_vertex_62(dense=False) in one library call."""
+        return self._engine(input.device).forward_landmarks(input)
+
+    def forward(self, input, target):
+        raise NotImplementedError(
+            'SynergyNet.forward(input, target) is the training forward with the PointNet heads and '
+            'losses (model_building.py:141-157); it is listed as "next" (SURVEY.md section 8 f4) and '
+            'is not part of the inference hot path built here. Use forward_test().')
+
+    def get_losses(self):
+        return self.loss.keys()
+
+    def load_weights(self, path):
+        ckpt = torch.load(path, map_location=lambda storage, loc: storage)['state_dict']
+        merged = self.state_dict()
+        for k, v in ckpt.items():
+            merged[k.replace('module.', '')] = v     # trained under DataParallel (:259-263)
+        self.load_state_dict(merged, strict=False)
+
+    def get_all_outputs(self, input, rects: Optional[Sequence[Sequence[float]]] = None):
+        """3d landmarks, dense meshes and poses of every face in a BGR uint8 image
+        (model_building.py:266-306 / synergy3DMM.py:167-207), batched over faces.
+
+        ``rects`` are detector boxes ``[x0,y0,x1,y1,score]``.  The FaceBoxes detector is outside
+        the hot path: pass ``rects`` or set ``self.face_detector``.
+        """
+        import cv2
+        if rects is None:
+            if self.face_detector is None:
+                raise RuntimeError('no face detector configured: pass rects=[[x0,y0,x1,y1,score],...] '
+                                   'or set model.face_detector to a callable(img)->rects')
+            rects = self.face_detector(input)
+        boxes = [square_roi(list(r)) for r in rects]
+        if not boxes:
+            return [], [], []
+        interp = cv2.INTER_LANCZOS4 if self.resize_interpolation == 'lanczos4' else cv2.INTER_LINEAR
+        crops = [cv2.resize(crop_img(input, b), dsize=(120, 120), interpolation=interp) for b in boxes]
+        batch = torch.from_numpy(np.stack(crops)).permute(0, 3, 1, 2).float()
+        batch = ((batch - 127.5) / 128.0).contiguous()
+        dev = self.param_mean.device
+        eng = self._engine(dev)
+        params = eng.forward(batch.to(dev))
+        lmk = eng.reconstruct(params, dense=False).cpu().numpy()
+        mesh = eng.reconstruct(params, dense=True).cpu().numpy()
+        p_np = params.cpu().numpy().astype(np.float32)
+        poses = predict_pose_batch(p_np, self.param_mean.cpu().numpy(), self.param_std.cpu().numpy(), boxes)
+        pts = [rescale_vertices(lmk[i], boxes[i]) for i in range(len(boxes))]
+        verts = [rescale_vertices(mesh[i], boxes[i]) for i in range(len(boxes))]
+        return pts, verts, poses
+
+
+class SynergyNet(_SynergyBase):
+    """``SynergyNet(args)`` of the reference benchmark/training scripts (model_building.py:65-165):
+    buffers are placed on CUDA at construction like the reference (:69,87-101)."""
+
+    def __init__(self, args, _device: Optional[str] = 'cuda'):
+        super().__init__()
+        self.img_size = args.img_size
+        self._setup(args, get_param_pack(), _device)
+
+
+class WrapUpSynergyNet(_SynergyBase):
+    """No-argument CPU-constructible wrapper (model_building.py:169-306)."""
+
+    def __init__(self, checkpoint_fp: str = 'pretrained/best.pth.tar'):
+        super().__init__()
+        args = types.SimpleNamespace(arch='mobilenet_v2', checkpoint_fp=checkpoint_fp)
+        self._setup(args, get_param_pack(), None)
+        try:
+            print('loading weights from ', args.checkpoint_fp)
+            self.load_weights(args.checkpoint_fp)
+        except Exception:
+            pass
+        self.eval()
