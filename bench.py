@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Headline benchmark: faces/sec of the SynergyNet inference hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W          # this framework (one process per GPU)
+    python bench.py --impl reference --steps K --warmup W  # the reference algorithm on host cores
+
+A step = one pass of the hot path (MobileNetV2 backbone -> 62 3DMM params -> 68 landmarks) over
+one batch of 1024 synthetic 120x120 crops per GPU (BASELINE.json configs[1]); with N > 1 the batch
+is sharded (weak scaling, 1024 faces per GPU) and the step ends with the single all-gather of
+landmarks.  Prints ONE JSON line (see the task contract): `value` is device-resident throughput,
+`e2e` goes through the host-buffer C-ABI call with H2D/D2H inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_FACE = 186_430_744            # 2*(93,204,560 + 10,812) MAC
+X_BYTES_PER_FACE = 3 * 120 * 120 * 4
+LMK_BYTES_PER_FACE = 3 * 68 * 4
+METRIC = 'faces/sec (120x120, batch 1024 per GPU, backbone + 3DMM params + 68 landmarks)'
+
+
+def load_peaks():
+    fp = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(fp):
+        with open(fp) as f:
+            p = json.load(f)
+        return dict(bf16_sustained=p['bf16_tflops_sustained'], bf16_burst=p['bf16_tflops'],
+                    hbm=p['hbm_gbs'], source='measured (MEASURED_PEAKS.json)')
+    return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, reasons, smax = [], set(), None
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                smax = float(parts[1])
+                if t0 - 0.05 <= ts <= t1 + 0.05:
+                    sm.append(float(parts[0]))
+                    for n, v in zip(names, parts[3:7]):
+                        if v.lower().startswith('active'):
+                            reasons.add(n)
+            except ValueError:
+                continue
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': 0}
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def build_model(device: str):
+    """Random-init weights of the reference architecture + seeded synthetic 3DMM (no network)."""
+    from synergynet_b200 import model_building, synthetic
+    from synergynet_b200.params import ParamsPack, set_param_pack
+    set_param_pack(ParamsPack(arrays=synthetic.make_3dmm(seed=0)))
+    args = types.SimpleNamespace(arch='mobilenet_v2', img_size=120, devices_id=[0])
+    model = model_building.SynergyNet(args, _device=device)
+    synthetic.seeded_init_(model, 0)
+    synthetic.randomize_batchnorm_(model, 0)
+    return model.eval()
+
+
+def cpu_reference_throughput(seconds: float, batch: int = 64):
+    """The reference algorithm (oracle port: same ATen CPU kernels as the reference's nn.Modules)
+    on the host cores: forward_test + reconstruct_vertex_62(dense=False)."""
+    from oracle import reference_port as rp
+    from oracle import synth_model
+    from synergynet_b200 import synthetic
+    torch.set_num_threads(os.cpu_count())
+    sd = synth_model.build_state_dict(0)
+    basis = rp.gather_sparse_basis(synthetic.make_3dmm(0))
+    x = synthetic.make_inputs(batch, 0)
+
+    def step():
+        p, _ = rp.mobilenetv2_forward(sd, x)
+        return rp.reconstruct_vertex_62(p.numpy(), basis)
+    step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= seconds and n >= 3:
+            break
+    return {'value': n * batch / el, 'unit': 'faces/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{n} batches of {batch} faces ({el:.1f} s), forward_test + 68-landmark reconstruction, '
+                      f'torch {torch.__version__} CPU fp32'}, step
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    sample = 128      # the reference arm is the oracle port: same ATen CPU kernels as the reference
+    base, step = cpu_reference_throughput(0.0, batch=sample)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    value = args.steps * sample / el
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'faces/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * el / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+        'config': {'workload': 'configs[1]: batch=1024 synthetic 120x120 crops, MobileNetV2 + 3DMM params + '
+                               '68-landmark reconstruction', 'sample_per_step': sample, 'device': 'host CPU'},
+        'cpu_baseline': {'value': value, 'unit': 'faces/s', 'cores': base['cores'], 'kind': 'port',
+                         'sample': f'{sample} faces per step (bounded sample of the 1024-face batch), '
+                                   f'{args.steps} steps'},
+        'e2e': {'value': value, 'unit': 'faces/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from synergynet_b200 import distributed as sdist
+    rank, local_rank, world = sdist.env_rank_world()
+    if world > 1:
+        sdist.init_process_group('nccl')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    B = args.batch
+    model = build_model(f'cuda:{local_rank}')
+    if args.engine is not None:
+        model.set_engine(args.engine)
+    eng = model._engine(dev)
+    peaks = load_peaks()
+
+    from synergynet_b200 import synthetic
+    n_rot = 3                                   # rotate 3 x 177 MB inputs: every step misses the 126 MB L2
+    xs = [synthetic.make_inputs(B, seed=10 * rank + i).to(dev) for i in range(n_rot)]
+    lmk_all = torch.empty((world * B, 3, 68), device=dev, dtype=torch.float32)
+
+    def step(i):
+        lmk = eng.forward_landmarks(xs[i % n_rot])
+        if world > 1:
+            sdist.gather_landmarks(lmk, lmk_all)
+        return lmk
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({'profile_run': True, 'ms_per_step': ms / args.steps, 'gpu_launches': launches}))
+        return
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H timed) ----
+    xh = [synthetic.make_inputs(B, seed=100 + 10 * rank + i).pin_memory() for i in range(2)]
+    lh = torch.empty((B, 3, 68), dtype=torch.float32).pin_memory()
+    for i in range(3):
+        eng.forward_landmarks_host(xh[i % 2], lh)
+    e2e_steps = max(3, min(args.steps, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        eng.forward_landmarks_host(xh[i % 2], lh)       # synchronous: returns when lmk is on the host
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    if rank == 0:
+        faces = world * B * args.steps
+        value = faces / (ms * 1e-3)
+        achieved = FLOP_PER_FACE * B * args.steps / (ms * 1e-3) / 1e12        # per GPU, TFLOP/s
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _ = cpu_reference_throughput(args.cpu_seconds)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'faces/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'configs[1]: batch=1024 synthetic 120x120 crops, MobileNetV2 + 3DMM params + '
+                                   '68-landmark reconstruction' + (' + all-gather of landmarks' if world > 1 else ''),
+                       'batch_per_gpu': B, 'global_batch': world * B,
+                       'engine': {0: 'simt_fp32', 1: 'tcgen05_bf16x3'}.get(eng.engine, eng.engine),
+                       'parallelism': f'dp{world}',
+                       'l2': f'{n_rot} rotating device-resident input batches of {B * X_BYTES_PER_FACE / 1e6:.0f} MB '
+                             '(> 126 MB L2) + >1 GB of activations written per step'},
+            'e2e': {'value': world * B * e2e_steps / e2e_s, 'unit': 'faces/s',
+                    'h2d_bytes_per_step': B * X_BYTES_PER_FACE, 'd2h_bytes_per_step': B * LMK_BYTES_PER_FACE,
+                    'steps': e2e_steps, 'call': 'syn_forward_landmarks_host (pinned fp32 crops in, landmarks out)'},
+            'gpu_launches': launches,
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
+                         'frac': achieved / peaks['bf16_sustained'], 'traffic': None,
+                         'what': 'whole step (all kernels of the fused path): algorithmic 186,430,744 FLOP/face x '
+                                 f'{B} faces / CUDA-event step time; peak = sustained bf16 of {peaks["source"]}'},
+            'cpu_baseline': cpu,
+            'clocks': clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=1024, help='faces per GPU per step')
+    ap.add_argument('--engine', type=int, default=None, help='0 = fp32 CUDA cores, 1 = tcgen05 bf16x3')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='device-resident steps only (for ncu runs)')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

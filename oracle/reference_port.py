@@ -50,15 +50,19 @@ def _conv_bn_relu6(x, sd, key, stride, groups, pad):
 
 @torch.no_grad()
 def mobilenetv2_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = 'I2P.backbone.',
-                        return_features: bool = False):
+                        return_features: bool = False, return_convs: bool = False):
     """MobileNetV2._forward_impl, mobilenetv2_backbone.py:173-189 -> (param62, pool1280).
 
     ``sd`` is a reference-schema state dict (CPU fp32), ``x`` is (B,3,120,120) fp32 NCHW.
+    ``return_features`` adds the 19 ``features[i]`` outputs; ``return_convs`` adds the 52
+    conv+BN(+ReLU6) activations in execution order (project convs with the skip already added),
+    which is what ``syn_debug_forward_until`` exposes on the GPU side.
     """
     sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
-    feats = []
+    feats, convs = [], []
     x = _conv_bn_relu6(x, sd, 'features.0', 2, 1, 1)                     # :127
     feats.append(x)
+    convs.append(x)
     cin, blk = 32, 1
     for t, c, n, s in _STAGES:                                             # :129-134
         for i in range(n):
@@ -67,22 +71,29 @@ def mobilenetv2_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, prefix: st
             y, j = x, 0
             if t != 1:                                                     # InvertedResidual :58-60
                 y = _conv_bn_relu6(y, sd, f'{base}.0', 1, 1, 0)
+                convs.append(y)
                 j = 1
             y = _conv_bn_relu6(y, sd, f'{base}.{j}', stride, y.shape[1], 1)   # :61-63
+            convs.append(y)
             y = F.conv2d(y, sd[f'{base}.{j + 1}.weight'])                 # :65
             y = _bn(y, sd, f'{base}.{j + 2}')                              # :66
             x = x + y if (stride == 1 and cin == c) else y                 # :55,70-74
             feats.append(x)
+            convs.append(x)
             cin, blk = c, blk + 1
     x = _conv_bn_relu6(x, sd, f'features.{blk}', 1, 1, 0)                  # :136
     feats.append(x)
+    convs.append(x)
     pool = F.adaptive_avg_pool2d(x, 1).reshape(x.shape[0], -1)            # :179-180
     heads = [F.linear(pool, sd[f'{h}.1.weight'], sd[f'{h}.1.bias'])       # :184-186 (Dropout = id)
              for h in ('classifier_ori', 'classifier_shape', 'classifier_exp')]
     out = torch.cat(heads, 1)                                              # :188
+    ret = (out, pool)
     if return_features:
-        return out, pool, feats
-    return out, pool
+        ret += (feats,)
+    if return_convs:
+        ret += (convs,)
+    return ret
 
 
 def parse_param_62(param: np.ndarray):
