@@ -117,6 +117,9 @@ int syn_forward_landmarks_host(syn_handle_t* h, const float* x_host, int batch,
 /* ---- introspection ---------------------------------------------------------------------------*/
 /* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
 int64_t syn_launch_count(const syn_handle_t* h);
+/* Synchronise the device and report (then clear) the sticky flag a bounded in-kernel wait raises
+ * when it times out (pipeline protocol bug); *flag_out = 0 means no kernel ever timed out. */
+int syn_poll_error(syn_handle_t* h, int* flag_out);
 /* Run the backbone on x_dev but stop after convolution `layer` (0..51) and copy its NHWC
  * activation (batch*h_out*h_out*cout floats, residual already added for project convs) to
  * out_dev.  Per-layer parity tests only. */

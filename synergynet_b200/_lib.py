@@ -52,6 +52,7 @@ SIGNATURES = {
     'syn_forward_landmarks': (_I, [_P, _F, _I, _F, _F, _P]),
     'syn_forward_landmarks_host': (_I, [_P, _F, _I, _F, _F]),
     'syn_launch_count': (_L, [_P]),
+    'syn_poll_error': (_I, [_P, C.POINTER(C.c_int)]),
     'syn_debug_forward_until': (_I, [_P, _F, _I, _I, _F, _P]),
 }
 

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
 
 using namespace syn;
 
@@ -48,6 +49,13 @@ struct syn_handle {
   DevConv dconv[kNumConv];
   float *d_head_w = nullptr, *d_head_b = nullptr, *d_mean = nullptr, *d_std = nullptr;
   float *d_sparse = nullptr, *d_dense = nullptr;
+
+  // tensor-core engine: bf16 hi/lo weight images of the pointwise convs (kernels_tc.cuh)
+  uint8_t* d_tcw = nullptr;
+  size_t tc_off[kNumConv] = {};
+  int tc_nr[kNumConv] = {}, tc_nranges[kNumConv] = {}, tc_kp[kNumConv] = {};
+  int* d_err = nullptr;                        // raised by a bounded mbarrier wait that timed out
+  bool tc_ready = false;
 
   // activation workspace (NHWC fp32), grown on demand
   int ws_batch = 0;
@@ -118,9 +126,24 @@ int launch_pointwise_simt(syn_handle* h, const float* A, const DevConv& w, const
   return SYN_OK;
 }
 
+int launch_pointwise_tc(syn_handle* h, const float* A, int layer, const float* residual, float* out,
+                        int M, cudaStream_t st) {
+  const ConvDesc& c = plan().conv[layer];
+  TcPointwiseArgs a;
+  a.A = A; a.Wimg = h->d_tcw + h->tc_off[layer]; a.bias = h->dconv[layer].bias; a.residual = residual;
+  a.out = out; a.M = M; a.K = c.cin; a.N = c.cout; a.Kp = h->tc_kp[layer]; a.nr = h->tc_nr[layer];
+  a.relu6 = c.relu6; a.err = h->d_err;
+  dim3 grid((M + 127) / 128, h->tc_nranges[layer]);
+  tc_pointwise_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
+  SYN_LAUNCH_CHECK("tc_pointwise_kernel");
+  h->launches++;
+  return SYN_OK;
+}
+
 int launch_pointwise(syn_handle* h, const float* A, int layer, const float* residual, float* out,
                      int M, cudaStream_t st) {
   const ConvDesc& c = plan().conv[layer];
+  if (h->engine == SYN_ENGINE_TC_BF16X3) return launch_pointwise_tc(h, A, layer, residual, out, M, st);
   return launch_pointwise_simt(h, A, h->dconv[layer], residual, out, M, c.cin, c.cout, c.relu6, st);
 }
 
@@ -213,6 +236,49 @@ int run_reconstruct(syn_handle* h, const float* params, int batch, int dense, in
   return SYN_OK;
 }
 
+// ---- bf16 hi/lo weight images for the tensor-core pointwise kernel --------------------------------
+inline uint16_t f32_to_bf16_rn(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);   // inf / nan
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf16_to_f32(uint16_t b) {
+  const uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// Wkn: folded weights [K][N] fp32 (SIMT layout).  Image: for each n-range, for each K-chunk of 64:
+// hi plane [nr x kc] then lo plane, canonical K-major no-swizzle (SBO = 128, LBO = nr/8*128).
+void pack_tc_pointwise(std::vector<uint8_t>& img, const float* Wkn, int K, int N, int Kp, int nr, int nranges) {
+  img.assign((size_t)nranges * nr * Kp * 4, 0);
+  uint16_t* base = reinterpret_cast<uint16_t*>(img.data());
+  const size_t lbo = (size_t)(nr / 8) * 128;
+  for (int j = 0; j < nranges; ++j)
+    for (int k0 = 0; k0 < Kp; k0 += kTcKChunk) {
+      const int kc = std::min(kTcKChunk, Kp - k0);
+      uint16_t* hi = base + ((size_t)j * nr * Kp * 4 + (size_t)nr * k0 * 4) / 2;
+      uint16_t* lo = hi + (size_t)nr * kc;
+      for (int nl = 0; nl < nr; ++nl) {
+        const int n = j * nr + nl;
+        if (n >= N) continue;
+        for (int kl = 0; kl < kc; ++kl) {
+          const int k = k0 + kl;
+          if (k >= K) continue;
+          const float w = Wkn[(size_t)k * N + n];
+          const uint16_t h = f32_to_bf16_rn(w);
+          const uint16_t l = f32_to_bf16_rn(w - bf16_to_f32(h));
+          const size_t off = ((size_t)(nl / 8) * 128 + (size_t)(kl / 8) * lbo + (nl % 8) * 16 + (kl % 8) * 2) / 2;
+          hi[off] = h;
+          lo[off] = l;
+        }
+      }
+    }
+}
+
 // planar [51][3][pad] from the reference's interleaved (3N,1)/(3N,40)/(3N,10) buffers
 void pack_basis(std::vector<float>& dst, const float* u, const float* ws, const float* we, int64_t n,
                 int64_t pad) {
@@ -284,7 +350,7 @@ void syn_destroy(syn_handle_t* h) {
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   cudaFree(h->d_weights); cudaFree(h->d_head_w); cudaFree(h->d_head_b); cudaFree(h->d_mean);
-  cudaFree(h->d_std); cudaFree(h->d_sparse); cudaFree(h->d_dense);
+  cudaFree(h->d_std); cudaFree(h->d_sparse); cudaFree(h->d_dense); cudaFree(h->d_tcw); cudaFree(h->d_err);
   cudaFree(h->buf_io[0]); cudaFree(h->buf_io[1]); cudaFree(h->buf_hid); cudaFree(h->buf_dw);
   cudaFree(h->d_params_tmp);
   cudaFree(h->d_stage_x[0]); cudaFree(h->d_stage_x[1]); cudaFree(h->d_stage_lmk); cudaFree(h->d_stage_par);
@@ -411,6 +477,30 @@ int syn_commit(syn_handle_t* h) {
     h->dconv[l].w = h->d_weights + w_off[l];
     h->dconv[l].bias = h->d_weights + b_off[l];
   }
+  // ---- tensor-core engine images ---------------------------------------------------------------
+  {
+    std::vector<uint8_t> all;
+    for (int l = 0; l < kNumConv; ++l) {
+      const ConvDesc& c = P.conv[l];
+      if (c.ksize != 1) continue;
+      const int Kp = (c.cin + 15) / 16 * 16, Np = (c.cout + 15) / 16 * 16;
+      const int nranges = (Np + kTcMaxNr - 1) / kTcMaxNr;
+      const int nr = ((Np + nranges - 1) / nranges + 15) / 16 * 16;
+      std::vector<uint8_t> img;
+      pack_tc_pointwise(img, slab.data() + w_off[l], c.cin, c.cout, Kp, nr, nranges);
+      h->tc_off[l] = all.size();
+      h->tc_nr[l] = nr; h->tc_nranges[l] = nranges; h->tc_kp[l] = Kp;
+      all.insert(all.end(), img.begin(), img.end());
+      all.resize((all.size() + 1023) / 1024 * 1024);
+    }
+    if (h->d_tcw) { cudaFree(h->d_tcw); h->d_tcw = nullptr; }
+    SYN_CUDA(cudaMalloc(&h->d_tcw, all.size()));
+    SYN_CUDA(cudaMemcpy(h->d_tcw, all.data(), all.size(), cudaMemcpyHostToDevice));
+    if (h->d_err == nullptr) SYN_CUDA(cudaMalloc(&h->d_err, sizeof(int)));
+    SYN_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+    SYN_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    h->tc_ready = true;
+  }
   int rc;
   if ((rc = upload(&h->d_head_w, h->h_head_w)) != SYN_OK) return rc;
   if ((rc = upload(&h->d_head_b, h->h_head_b)) != SYN_OK) return rc;
@@ -431,7 +521,7 @@ int syn_commit(syn_handle_t* h) {
 
 int syn_set_engine(syn_handle_t* h, int engine) {
   if (h == nullptr) return fail(SYN_ERR_INVALID, "syn_set_engine: null handle");
-  if (engine != SYN_ENGINE_SIMT_FP32)
+  if (engine != SYN_ENGINE_SIMT_FP32 && engine != SYN_ENGINE_TC_BF16X3)
     return fail(SYN_ERR_UNSUPPORTED, "syn_set_engine: engine %d not available in this build", engine);
   h->engine = engine;
   return SYN_OK;
@@ -520,6 +610,18 @@ int syn_forward_landmarks_host(syn_handle_t* h, const float* x_host, int batch, 
 }
 
 int64_t syn_launch_count(const syn_handle_t* h) { return h ? h->launches : -1; }
+
+int syn_poll_error(syn_handle_t* h, int* flag_out) {
+  if (h == nullptr || flag_out == nullptr) return fail(SYN_ERR_INVALID, "syn_poll_error: null handle");
+  DeviceGuard g(h->device);
+  SYN_CUDA(cudaDeviceSynchronize());
+  *flag_out = 0;
+  if (h->d_err != nullptr) {
+    SYN_CUDA(cudaMemcpy(flag_out, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    SYN_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+  }
+  return SYN_OK;
+}
 
 int syn_debug_forward_until(syn_handle_t* h, const float* x, int batch, int layer, float* out, void* stream) {
   SYN_CHECK_READY(h, "syn_debug_forward_until");

@@ -91,6 +91,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.syn_launch_count(self._h))
 
+    def poll_error(self) -> int:
+        """Device sync + sticky in-kernel timeout flag (0 = clean)."""
+        flag = C.c_int(0)
+        _lib.check(self._lib.syn_poll_error(self._h, C.byref(flag)))
+        return int(flag.value)
+
     # ---- compute --------------------------------------------------------------------------------
     def _check_x(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() != 4 or tuple(x.shape[1:]) != (3, 120, 120):

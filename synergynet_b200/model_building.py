@@ -151,9 +151,9 @@ class _SynergyBase(nn.Module):
 
     def set_engine(self, kind: int) -> None:
         """0 = fp32 CUDA-core engine, 1 = tcgen05 bf16x3 engine (include/synergy_b200.h)."""
-        self.I2P._rt.engine_kind = int(kind)
         for eng in self.I2P._rt._engines.values():
             eng.set_engine(int(kind))
+        self.I2P._rt.engine_kind = int(kind)
 
     # ---- reference API ---------------------------------------------------------------------------
     def reconstruct_vertex_62(self, param, whitening=True, dense=False, transform=True, lmk_pts=68):
