@@ -264,7 +264,7 @@ def run_b200(args):
             'config': {'workload': 'configs[1]: batch=1024 synthetic 120x120 crops, MobileNetV2 + 3DMM params + '
                                    '68-landmark reconstruction' + (' + all-gather of landmarks' if world > 1 else ''),
                        'batch_per_gpu': B, 'global_batch': world * B,
-                       'engine': {0: 'simt_fp32', 1: 'tcgen05_bf16x3'}.get(eng.engine, eng.engine),
+                       'engine': {0: 'simt_fp32', 1: 'tcgen05_bf16x3', 2: 'tcgen05_bf16x3_fused'}.get(eng.engine, eng.engine),
                        'parallelism': f'dp{world}',
                        'l2': f'{n_rot} rotating device-resident input batches of {B * X_BYTES_PER_FACE / 1e6:.0f} MB '
                              '(> 126 MB L2) + >1 GB of activations written per step'},
@@ -291,7 +291,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=1024, help='faces per GPU per step')
-    ap.add_argument('--engine', type=int, default=None, help='0 = fp32 CUDA cores, 1 = tcgen05 bf16x3')
+    ap.add_argument('--engine', type=int, default=None, help='0 = fp32 CUDA cores, 1 = tcgen05 bf16x3, 2 = 1 + fused blocks')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile', action='store_true', help='device-resident steps only (for ncu runs)')

@@ -43,8 +43,10 @@ enum {
 /* Compute engines for the 1x1 convolutions / basis products (syn_set_engine). */
 enum {
   SYN_ENGINE_SIMT_FP32 = 0,   /* CUDA-core fp32 FMA everywhere (bring-up / cross-check path)     */
-  SYN_ENGINE_TC_BF16X3 = 1    /* tcgen05.mma, operands split in bf16 hi+lo, 3 MMAs per product,  */
+  SYN_ENGINE_TC_BF16X3 = 1,   /* tcgen05.mma, operands split in bf16 hi+lo, 3 MMAs per product,  */
                               /* fp32 accumulation in TMEM: meets the 1e-4 parity bar            */
+  SYN_ENGINE_TC_FUSED = 2     /* engine 1 + stem/block1 and blocks 2..7 each fused into one      */
+                              /* kernel (expand -> depthwise -> project, hidden tensor on chip)  */
 };
 
 typedef struct syn_handle syn_handle_t;

@@ -1,10 +1,13 @@
 // tcgen05 (5th-gen tensor core) kernels of the SYN_ENGINE_TC_BF16X3 engine.
 //
-// Precision scheme ("bf16x3"): every fp32 operand x is split into hi = bf16(x) and
-// lo = bf16(x - hi); a product a*b is evaluated as hi_a*hi_b + hi_a*lo_b + lo_a*hi_b with fp32
-// accumulation in TMEM (the lo*lo term, <= 2^-16 relative, is dropped).  Three MMAs per algorithmic
-// MAC keep the result within ~1e-5 of fp32, inside the 1e-4 parity bar that single-pass
-// bf16/tf32/fp16 all miss.
+// Precision scheme ("split-16x3"): every fp32 operand x is split into hi = fp16(x) and
+// lo = fp16(x - hi); a product a*b is evaluated as hi_a*hi_b + hi_a*lo_b + lo_a*hi_b with fp32
+// accumulation in TMEM (the lo*lo term, <= 2^-22 relative, is dropped).  Three kind::f16 MMAs per
+// algorithmic MAC keep each product within ~5e-7 of fp32.  A bf16 hi/lo split (8+8 mantissa bits)
+// was measured first: 1.7e-4 on the 62 parameters with a calibrated checkpoint -- outside the 1e-4
+// parity bar, like single-pass bf16/tf32/fp16 -- so the split uses fp16
+// (11+11 bits) with power-of-two pre-scaling: activations by kActScale, weights per output channel
+// (max |w| in [256,512)), both undone exactly by one multiply in the epilogue.
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -36,6 +39,7 @@ struct TcPointwiseArgs {
   const float* A;
   const uint8_t* Wimg;     // packed bf16 hi/lo weight image of this layer
   const float* bias;
+  const float* oscale;     // per output channel: 1 / (kActScale * weight scale)
   const float* residual;   // nullable
   float* out;
   int M, K, N;             // K, N: true sizes;
@@ -111,13 +115,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pointwise_kernel(const TcPoi
         }
         uint32_t h[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v[2 * j], h0, l0);
-          split_bf16(v[2 * j + 1], h1, l1);
-          h[j] = pack_bf16x2(h0, h1);
-          l[j] = pack_bf16x2(l0, l1);
-        }
+        for (int j = 0; j < 4; ++j) split2_f16(v[2 * j] * kActScale, v[2 * j + 1] * kActScale, h[j], l[j]);
         *reinterpret_cast<uint4*>(ah + kg * 2048) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(al + kg * 2048) = make_uint4(l[0], l[1], l[2], l[3]);
       }
@@ -139,7 +137,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pointwise_kernel(const TcPoi
       for (int j = 0; j < 16; j += 4) {
         if (c0 + j >= ncols) break;                       // N is a multiple of 8; ranges of 16
         const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + j);
-        float4 o = make_float4(v[j] + b.x, v[j + 1] + b.y, v[j + 2] + b.z, v[j + 3] + b.w);
+        const float4 sc = *reinterpret_cast<const float4*>(p.oscale + n0 + c0 + j);
+        float4 o = make_float4(fmaf(v[j], sc.x, b.x), fmaf(v[j + 1], sc.y, b.y), fmaf(v[j + 2], sc.z, b.z),
+                               fmaf(v[j + 3], sc.w, b.w));
         if (p.relu6) { o.x = relu6f(o.x); o.y = relu6f(o.y); o.z = relu6f(o.z); o.w = relu6f(o.w); }
         if (rrow) {
           const float4 r = *reinterpret_cast<const float4*>(rrow + c0 + j);
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pointwise_kernel(const TcPoi
     }
   } else if (tid == 128) {
     // ------------------------------ MMA issuer --------------------------------------------------
-    const uint32_t idesc = make_idesc_bf16(128, p.nr);
+    const uint32_t idesc = make_idesc_f16(128, p.nr);
     const uint32_t lbo_b = (uint32_t)(p.nr >> 3) * 128;
     uint32_t acc = 0;
     for (int c = 0; c < nchunks; ++c) {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pointwise_kernel(const TcPoi
         for (int ks = 0; ks < kc / 16; ++ks) {
           const uint64_t ad = make_smem_desc(a_base + ks * 2 * 2048, 2048, 128);
           const uint64_t bd = make_smem_desc(b_base + ks * 2 * lbo_b, lbo_b, 128);
-          umma_bf16(tmem, ad, bd, idesc, acc);
+          umma_f16(tmem, ad, bd, idesc, acc);
           acc = 1;
         }
       }

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_fused.cuh"
 
 using namespace syn;
 
@@ -52,10 +53,15 @@ struct syn_handle {
 
   // tensor-core engine: bf16 hi/lo weight images of the pointwise convs (kernels_tc.cuh)
   uint8_t* d_tcw = nullptr;
+  float* d_tc_oscale = nullptr;                // per layer, per output channel: 1/(kActScale*weight scale)
+  size_t tc_osc_off[kNumConv] = {};
   size_t tc_off[kNumConv] = {};
   int tc_nr[kNumConv] = {}, tc_nranges[kNumConv] = {}, tc_kp[kNumConv] = {};
   int* d_err = nullptr;                        // raised by a bounded mbarrier wait that timed out
   bool tc_ready = false;
+  // fused stem+block1 and blocks 2..7 (kernels_fused.cuh): one weight image per fused launch
+  uint8_t* d_fused = nullptr;
+  size_t fused_off[8] = {};                    // index = features[] index of the block (1..7)
 
   // activation workspace (NHWC fp32), grown on demand
   int ws_batch = 0;
@@ -130,7 +136,7 @@ int launch_pointwise_tc(syn_handle* h, const float* A, int layer, const float* r
                         int M, cudaStream_t st) {
   const ConvDesc& c = plan().conv[layer];
   TcPointwiseArgs a;
-  a.A = A; a.Wimg = h->d_tcw + h->tc_off[layer]; a.bias = h->dconv[layer].bias; a.residual = residual;
+  a.A = A; a.Wimg = h->d_tcw + h->tc_off[layer]; a.bias = h->dconv[layer].bias; a.oscale = h->d_tc_oscale + h->tc_osc_off[layer]; a.residual = residual;
   a.out = out; a.M = M; a.K = c.cin; a.N = c.cout; a.Kp = h->tc_kp[layer]; a.nr = h->tc_nr[layer];
   a.relu6 = c.relu6; a.err = h->d_err;
   dim3 grid((M + 127) / 128, h->tc_nranges[layer]);
@@ -143,7 +149,7 @@ int launch_pointwise_tc(syn_handle* h, const float* A, int layer, const float* r
 int launch_pointwise(syn_handle* h, const float* A, int layer, const float* residual, float* out,
                      int M, cudaStream_t st) {
   const ConvDesc& c = plan().conv[layer];
-  if (h->engine == SYN_ENGINE_TC_BF16X3) return launch_pointwise_tc(h, A, layer, residual, out, M, st);
+  if (h->engine != SYN_ENGINE_SIMT_FP32) return launch_pointwise_tc(h, A, layer, residual, out, M, st);
   return launch_pointwise_simt(h, A, h->dconv[layer], residual, out, M, c.cin, c.cout, c.relu6, st);
 }
 
@@ -157,6 +163,9 @@ int launch_depthwise(syn_handle* h, const float* x, int layer, float* y, int bat
   h->launches++;
   return SYN_OK;
 }
+
+template <class C>
+int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, cudaStream_t st);
 
 // Runs the backbone.  When stop_layer >= 0 the activation of that conv is copied to dbg_out and
 // the function returns early.  Otherwise params (B,62) [and pool (B,1280)] are produced.
@@ -174,13 +183,39 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
   };
 
   int cur = 0;
+  int li = 1;
+  if (h->engine == SYN_ENGINE_TC_FUSED) {
+    // stem + block 1, then blocks 2..7, each one fused launch; only block outputs exist
+    if (stop_layer >= 0 && stop_layer <= 20 && (stop_layer < 2 || (stop_layer - 2) % 3 != 0))
+      return fail(SYN_ERR_UNSUPPORTED, "conv %d lives inside a fused block and is never materialised", stop_layer);
+    struct Step { int block, last_conv; };
+    static const Step steps[7] = {{1, 2}, {2, 5}, {3, 8}, {4, 11}, {5, 14}, {6, 17}, {7, 20}};
+    const float* in = x;
+    for (const Step& s : steps) {
+      float* out = h->buf_io[cur ^ 1];
+      switch (s.block) {
+        case 1: rc = launch_fused<FusedStemB1>(h, in, 1, out, batch, st); break;
+        case 2: rc = launch_fused<FusedB2>(h, in, 2, out, batch, st); break;
+        case 3: rc = launch_fused<FusedB3>(h, in, 3, out, batch, st); break;
+        case 4: rc = launch_fused<FusedB4>(h, in, 4, out, batch, st); break;
+        case 5: rc = launch_fused<FusedB56>(h, in, 5, out, batch, st); break;
+        case 6: rc = launch_fused<FusedB56>(h, in, 6, out, batch, st); break;
+        default: rc = launch_fused<FusedB7>(h, in, 7, out, batch, st); break;
+      }
+      if (rc != SYN_OK) return rc;
+      cur ^= 1;
+      in = h->buf_io[cur];
+      if (stop_layer == s.last_conv) return dbg(s.last_conv, h->buf_io[cur]);
+    }
+    li = 21;
+  } else {
   stem_conv3x3s2_kernel<<<batch * 60, kStemThreads, 0, st>>>(x, h->dconv[0].w, h->dconv[0].bias,
                                                             h->buf_io[cur], batch);
   SYN_LAUNCH_CHECK("stem_conv3x3s2_kernel");
   h->launches++;
   if (stop_layer == 0) return dbg(0, h->buf_io[cur]);
+  }
 
-  int li = 1;
   while (P.conv[li].kind != kLast) {
     const float* block_in = h->buf_io[cur];
     const float* dw_in = block_in;
@@ -236,27 +271,38 @@ int run_reconstruct(syn_handle* h, const float* params, int batch, int dense, in
   return SYN_OK;
 }
 
-// ---- bf16 hi/lo weight images for the tensor-core pointwise kernel --------------------------------
-inline uint16_t f32_to_bf16_rn(float x) {
-  uint32_t u;
-  memcpy(&u, &x, 4);
-  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);   // inf / nan
-  u += 0x7FFFu + ((u >> 16) & 1u);
-  return (uint16_t)(u >> 16);
+// ---- fp16 hi/lo weight images for the tensor-core kernels -------------------------------------------
+inline void split_f16_host(float x, uint16_t& hi, uint16_t& lo) {
+  const __half h = __float2half_rn(x);
+  const __half l = __float2half_rn(x - __half2float(h));
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(l);
 }
-inline float bf16_to_f32(uint16_t b) {
-  const uint32_t u = (uint32_t)b << 16;
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
+// power-of-two scale that brings max|w| of one output channel into [256, 512) (tc_common.cuh)
+inline float channel_scale(const float* w, size_t stride, int count) {
+  float m = 0.f;
+  for (int i = 0; i < count; ++i) m = std::max(m, fabsf(w[(size_t)i * stride]));
+  if (!(m > 0.f) || !std::isfinite(m)) return 1.f;
+  int ex;
+  frexpf(m, &ex);                       // m = f * 2^ex, f in [0.5, 1)
+  return ldexpf(1.f, 9 - ex);
 }
+constexpr float kActScaleHost = 64.0f;   // == tc::kActScale
 
 // Wkn: folded weights [K][N] fp32 (SIMT layout).  Image: for each n-range, for each K-chunk of 64:
 // hi plane [nr x kc] then lo plane, canonical K-major no-swizzle (SBO = 128, LBO = nr/8*128).
-void pack_tc_pointwise(std::vector<uint8_t>& img, const float* Wkn, int K, int N, int Kp, int nr, int nranges) {
+// oscale[n] receives the epilogue multiplier that undoes the activation and weight scales.
+void pack_tc_pointwise(std::vector<uint8_t>& img, std::vector<float>& oscale, const float* Wkn, int K, int N,
+                       int Kp, int nr, int nranges) {
   img.assign((size_t)nranges * nr * Kp * 4, 0);
+  oscale.assign((size_t)nranges * nr, 0.f);
   uint16_t* base = reinterpret_cast<uint16_t*>(img.data());
   const size_t lbo = (size_t)(nr / 8) * 128;
+  std::vector<float> ws(N);
+  for (int n = 0; n < N; ++n) {
+    ws[n] = channel_scale(Wkn + n, (size_t)N, K);
+    oscale[n] = 1.0f / (kActScaleHost * ws[n]);
+  }
   for (int j = 0; j < nranges; ++j)
     for (int k0 = 0; k0 < Kp; k0 += kTcKChunk) {
       const int kc = std::min(kTcKChunk, Kp - k0);
@@ -268,15 +314,69 @@ void pack_tc_pointwise(std::vector<uint8_t>& img, const float* Wkn, int K, int N
         for (int kl = 0; kl < kc; ++kl) {
           const int k = k0 + kl;
           if (k >= K) continue;
-          const float w = Wkn[(size_t)k * N + n];
-          const uint16_t h = f32_to_bf16_rn(w);
-          const uint16_t l = f32_to_bf16_rn(w - bf16_to_f32(h));
           const size_t off = ((size_t)(nl / 8) * 128 + (size_t)(kl / 8) * lbo + (nl % 8) * 16 + (kl % 8) * 2) / 2;
-          hi[off] = h;
-          lo[off] = l;
+          split_f16_host(Wkn[(size_t)k * N + n] * ws[n], hi[off], lo[off]);
         }
       }
     }
+}
+
+// ---- weight image of one fused block (layout documented in FusedCfg) --------------------------------
+// w1: [K][CHID] folded expand (or stem) weights, dw: [9][CHID], w3: [CHID][COUT] folded project weights.
+template <class C>
+void pack_fused(std::vector<uint8_t>& img, const float* w1, int K, const float* b1, const float* dw,
+                const float* bdw, const float* w3, const float* b3) {
+  img.assign(C::W_BYTES, 0);
+  auto put = [&](size_t byte_off, float w, size_t plane_bytes) {
+    uint16_t h, l;
+    split_f16_host(w, h, l);
+    *reinterpret_cast<uint16_t*>(img.data() + byte_off) = h;
+    *reinterpret_cast<uint16_t*>(img.data() + byte_off + plane_bytes) = l;
+  };
+  float* b3p = reinterpret_cast<float*>(img.data() + C::OFF_B3);
+  std::vector<float> s3(C::COUT);
+  for (int n = 0; n < C::COUT; ++n) {
+    s3[n] = channel_scale(w3 + n, (size_t)C::COUT, C::CHID);
+    b3p[n] = b3[n];
+    b3p[C::COUT_P + n] = 1.0f / (kActScaleHost * s3[n]);
+  }
+  for (int c = 0; c < C::NCHUNK; ++c) {
+    float* d = reinterpret_cast<float*>(img.data() + C::OFF_DW) + (size_t)c * C::DW_ROWS * C::NC;
+    for (int n = 0; n < C::NC; ++n) {
+      const int ch = c * C::NC + n;
+      const float s1 = channel_scale(w1 + ch, (size_t)C::CHID, K);
+      for (int k = 0; k < K; ++k) {
+        const size_t off = (size_t)(n / 8) * 128 + (size_t)(k / 8) * ((C::NC / 8) * 128) + (n % 8) * 16 + (k % 8) * 2;
+        put(C::OFF_W1 + (size_t)(2 * c) * C::W1_PLANE + off, w1[(size_t)k * C::CHID + ch] * s1, C::W1_PLANE);
+      }
+      for (int t = 0; t < 9; ++t) d[t * C::NC + n] = dw[(size_t)t * C::CHID + ch];
+      d[9 * C::NC + n] = bdw[ch];
+      d[10 * C::NC + n] = b1[ch];
+      d[11 * C::NC + n] = 1.0f / (kActScaleHost * s1);
+    }
+    for (int n = 0; n < C::COUT; ++n)
+      for (int k = 0; k < C::NC; ++k) {
+        const size_t off = (size_t)(n / 8) * 128 + (size_t)(k / 8) * ((C::COUT_P / 8) * 128) + (n % 8) * 16 + (k % 8) * 2;
+        put(C::OFF_W3 + (size_t)(2 * c) * C::W3_PLANE + off, w3[(size_t)(c * C::NC + k) * C::COUT + n] * s3[n], C::W3_PLANE);
+      }
+  }
+}
+
+template <class C>
+int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, cudaStream_t st) {
+  static bool attr_set[16] = {};
+  if (!attr_set[h->device & 15]) {
+    SYN_CUDA(cudaFuncSetAttribute(fused_mbconv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set[h->device & 15] = true;
+  }
+  FusedArgs a;
+  a.x = x; a.wimg = h->d_fused + h->fused_off[block]; a.y = y; a.batch = batch; a.err = h->d_err;
+  const int ntiles = batch * C::STRIPS;
+  const int grid = std::min(ntiles, h->sm_count);
+  fused_mbconv_kernel<C><<<grid, 160, C::SMEM_BYTES, st>>>(a);
+  SYN_LAUNCH_CHECK("fused_mbconv_kernel");
+  h->launches++;
+  return SYN_OK;
 }
 
 // planar [51][3][pad] from the reference's interleaved (3N,1)/(3N,40)/(3N,10) buffers
@@ -350,7 +450,7 @@ void syn_destroy(syn_handle_t* h) {
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   cudaFree(h->d_weights); cudaFree(h->d_head_w); cudaFree(h->d_head_b); cudaFree(h->d_mean);
-  cudaFree(h->d_std); cudaFree(h->d_sparse); cudaFree(h->d_dense); cudaFree(h->d_tcw); cudaFree(h->d_err);
+  cudaFree(h->d_std); cudaFree(h->d_sparse); cudaFree(h->d_dense); cudaFree(h->d_tcw); cudaFree(h->d_err); cudaFree(h->d_fused); cudaFree(h->d_tc_oscale);
   cudaFree(h->buf_io[0]); cudaFree(h->buf_io[1]); cudaFree(h->buf_hid); cudaFree(h->buf_dw);
   cudaFree(h->d_params_tmp);
   cudaFree(h->d_stage_x[0]); cudaFree(h->d_stage_x[1]); cudaFree(h->d_stage_lmk); cudaFree(h->d_stage_par);
@@ -480,6 +580,7 @@ int syn_commit(syn_handle_t* h) {
   // ---- tensor-core engine images ---------------------------------------------------------------
   {
     std::vector<uint8_t> all;
+    std::vector<float> osc_all, osc;
     for (int l = 0; l < kNumConv; ++l) {
       const ConvDesc& c = P.conv[l];
       if (c.ksize != 1) continue;
@@ -487,7 +588,9 @@ int syn_commit(syn_handle_t* h) {
       const int nranges = (Np + kTcMaxNr - 1) / kTcMaxNr;
       const int nr = ((Np + nranges - 1) / nranges + 15) / 16 * 16;
       std::vector<uint8_t> img;
-      pack_tc_pointwise(img, slab.data() + w_off[l], c.cin, c.cout, Kp, nr, nranges);
+      pack_tc_pointwise(img, osc, slab.data() + w_off[l], c.cin, c.cout, Kp, nr, nranges);
+      h->tc_osc_off[l] = osc_all.size();
+      osc_all.insert(osc_all.end(), osc.begin(), osc.end());
       h->tc_off[l] = all.size();
       h->tc_nr[l] = nr; h->tc_nranges[l] = nranges; h->tc_kp[l] = Kp;
       all.insert(all.end(), img.begin(), img.end());
@@ -496,10 +599,33 @@ int syn_commit(syn_handle_t* h) {
     if (h->d_tcw) { cudaFree(h->d_tcw); h->d_tcw = nullptr; }
     SYN_CUDA(cudaMalloc(&h->d_tcw, all.size()));
     SYN_CUDA(cudaMemcpy(h->d_tcw, all.data(), all.size(), cudaMemcpyHostToDevice));
+    int rc_o = upload(&h->d_tc_oscale, osc_all);
+    if (rc_o != SYN_OK) return rc_o;
     if (h->d_err == nullptr) SYN_CUDA(cudaMalloc(&h->d_err, sizeof(int)));
     SYN_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
     SYN_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     h->tc_ready = true;
+  }
+  // ---- fused-block images: conv indices: stem 0 | b1: dw 1, proj 2 | block k>=2: 3k-3, 3k-2, 3k-1 ------
+  {
+    std::vector<uint8_t> all, img;
+    auto W = [&](int l) { return slab.data() + w_off[l]; };
+    auto Bv = [&](int l) { return slab.data() + b_off[l]; };
+    auto add = [&](int block) {
+      h->fused_off[block] = all.size();
+      all.insert(all.end(), img.begin(), img.end());
+      all.resize((all.size() + 1023) / 1024 * 1024);
+    };
+    pack_fused<FusedStemB1>(img, W(0), 27, Bv(0), W(1), Bv(1), W(2), Bv(2)); add(1);
+    pack_fused<FusedB2>(img, W(3), 16, Bv(3), W(4), Bv(4), W(5), Bv(5)); add(2);
+    pack_fused<FusedB3>(img, W(6), 24, Bv(6), W(7), Bv(7), W(8), Bv(8)); add(3);
+    pack_fused<FusedB4>(img, W(9), 24, Bv(9), W(10), Bv(10), W(11), Bv(11)); add(4);
+    pack_fused<FusedB56>(img, W(12), 32, Bv(12), W(13), Bv(13), W(14), Bv(14)); add(5);
+    pack_fused<FusedB56>(img, W(15), 32, Bv(15), W(16), Bv(16), W(17), Bv(17)); add(6);
+    pack_fused<FusedB7>(img, W(18), 32, Bv(18), W(19), Bv(19), W(20), Bv(20)); add(7);
+    if (h->d_fused) { cudaFree(h->d_fused); h->d_fused = nullptr; }
+    SYN_CUDA(cudaMalloc(&h->d_fused, all.size()));
+    SYN_CUDA(cudaMemcpy(h->d_fused, all.data(), all.size(), cudaMemcpyHostToDevice));
   }
   int rc;
   if ((rc = upload(&h->d_head_w, h->h_head_w)) != SYN_OK) return rc;
@@ -521,7 +647,7 @@ int syn_commit(syn_handle_t* h) {
 
 int syn_set_engine(syn_handle_t* h, int engine) {
   if (h == nullptr) return fail(SYN_ERR_INVALID, "syn_set_engine: null handle");
-  if (engine != SYN_ENGINE_SIMT_FP32 && engine != SYN_ENGINE_TC_BF16X3)
+  if (engine != SYN_ENGINE_SIMT_FP32 && engine != SYN_ENGINE_TC_BF16X3 && engine != SYN_ENGINE_TC_FUSED)
     return fail(SYN_ERR_UNSUPPORTED, "syn_set_engine: engine %d not available in this build", engine);
   h->engine = engine;
   return SYN_OK;

@@ -9,6 +9,7 @@
 // uint128 units).  One tcgen05.mma consumes K = 16 (two core matrices along K).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace syn {
@@ -29,15 +30,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
-// ---- instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, bf16 x bf16 -> f32 ----------
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+// ---- instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, 16-bit x 16-bit -> f32 -------
+__host__ __device__ constexpr uint32_t make_idesc_16b(int M, int N, uint32_t ab_format) {
   return (1u << 4)                     // c_format  = F32
-         | (1u << 7)                   // a_format  = BF16
-         | (1u << 10)                  // b_format  = BF16
+         | (ab_format << 7)            // a_format  (0 = F16, 1 = BF16)
+         | (ab_format << 10)           // b_format
          | (0u << 15) | (0u << 16)     // a_major = b_major = K
          | ((uint32_t)(N >> 3) << 17)  // n_dim
          | ((uint32_t)(M >> 4) << 24); // m_dim
 }
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) { return make_idesc_16b(M, N, 1u); }
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) { return make_idesc_16b(M, N, 0u); }
 
 // ---- mbarrier -------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -63,14 +66,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU (a hung box is a strike); on timeout the
-// caller-provided flag is raised and the wait returns so the kernel can drain.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err_flag) {
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
-    if (mbar_try_wait(bar, parity)) return true;
+// Bounded wait: a protocol bug must not hang the GPU (a hung box is a strike).  After ~2 s of wall
+// clock (or as soon as any other thread has already timed out) the caller-provided sticky flag is
+// raised and the wait returns, so the kernel drains with garbage instead of spinning forever.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* err_flag) {
+  const uint64_t t0 = globaltimer_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (err_flag != nullptr && *reinterpret_cast<volatile int*>(err_flag) != 0) return false;
+    if (globaltimer_ns() - t0 > 2000000000ull) {
+      if (err_flag != nullptr) atomicExch(err_flag, 1);
+      return false;
+    }
   }
-  if (err_flag != nullptr) atomicExch(err_flag, 1);
-  return false;
+  return true;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err_flag) {
+  if (mbar_try_wait(bar, parity)) return true;
+  return mbar_wait_slow(bar, parity, err_flag);
 }
 
 // ---- proxies / fences ----------------------------------------------------------------------------
@@ -99,7 +116,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
 }
 
 // ---- MMA issue / commit (ONE thread) --------------------------------------------------------------
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -149,6 +166,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// ---- fp32 -> (hi, lo) fp16 split: 11 + 11 mantissa bits, |x - hi - lo| <= 2^-22 |x| while lo stays a
+// normal fp16 number.  Callers pre-scale by a power of two (kActScale for activations, a per-channel
+// scale for weights) so that this holds over the value range that matters, and clamp to the fp16 range.
+constexpr float kActScale = 64.0f;           // relu6 range [0,6] -> [0,384]; block inputs: |x| < 1000
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  x = fminf(fmaxf(x, -60000.f), 60000.f);
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+__device__ __forceinline__ uint32_t pack_f16x2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// split two fp32 values (already multiplied by their power-of-two scale) into packed hi and lo words
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __half h0, l0, h1, l1;
+  split_f16(a, h0, l0);
+  split_f16(b, h1, l1);
+  hi = pack_f16x2(h0, h1);
+  lo = pack_f16x2(l0, l1);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* A, const float*
         const uint32_t baddr = smem_u32(b) + (k0 >> 3) * lboB;
         const uint64_t ad = swap_fields ? make_smem_desc(aaddr, sboA, lboA) : make_smem_desc(aaddr, lboA, sboA);
         const uint64_t bd = swap_fields ? make_smem_desc(baddr, sboB, lboB) : make_smem_desc(baddr, lboB, sboB);
-        umma_bf16(tmem, ad, bd, idesc, acc);
+        umma_f16(tmem, ad, bd, idesc, acc);
         acc = 1;
       }
     }
