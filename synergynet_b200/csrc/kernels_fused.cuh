@@ -4,17 +4,20 @@
 // The same kernel, with an im2col loader, fuses the 3x3/s2 stem conv with block 1
 // (mobilenetv2_backbone.py:127 + features[1]).
 //
-// Work item (tile) = RO output rows of one face.  Per tile, for each chunk of NC hidden channels:
+// Work item (tile) = RO output rows of one face (large maps) or FACES whole faces (8x8 / 4x4 maps).
+// Per tile, for each chunk of NC hidden channels:
 //   GEMM1  D1[t] (128 x NC, TMEM)  = Xs[t] (128 input pixels x CIN_P, fp16 hi/lo) * W1c^T   (tensor)
-//   EPI1   Hs[pixel][NC] (fp32, smem, zero halo) = relu6(D1 + b1)                           (CUDA)
+//   EPI1   Hs[pixel][NC] (fp32, smem, zero halo) = relu6(s1 * D1 + b1)                      (CUDA)
 //   DW     A2[out pixel][NC] (fp16 hi/lo, smem)  = split(relu6(dw3x3(Hs) + bdw))            (CUDA)
 //   GEMM2  D2[t] (128 x COUT_P, TMEM) += A2[t] * W3c^T                                      (tensor)
-// and finally EPI2: out = D2 + b3 (+ x).  GEMM1 of chunk c+1 and GEMM2 of chunk c run on the tensor
-// pipe while the 128 worker threads are busy with EPI1/DW, so the CUDA-core work is the critical
-// path.  All of a block's weights (<= 83 KB as fp16 hi/lo) stay resident in shared memory and the
-// CTAs are persistent (grid = #SMs), so weights are fetched once per SM.
+// and finally EPI2: out = s3 * D2 + b3 (+ x).  GEMM1 of chunk c+1 and GEMM2 of chunk c run on the
+// tensor pipe while the 128 worker threads do EPI1/DW, so the CUDA-core work is the critical path.
+// CTAs are persistent (grid = #SMs).  Weights (fp16 hi/lo, split-16x3 scheme of kernels_tc.cuh) are
+// either resident in shared memory for the whole kernel (early blocks, <= 83 KB) or streamed chunk by
+// chunk through a 2-stage bulk-copy (TMA) ring (late blocks).
 //
-// Roles: warps 0-3 = workers (thread = GEMM row / pixel), warp 4 lane 0 = MMA issuer.
+// Roles: warps 0..NWW-1 = workers (thread = GEMM row / pixel; NWW/4 groups share the column chunks),
+// warp NWW lane 0 = MMA issuer + weight loader.
 // Operand tiles use the canonical K-major no-swizzle layout of tc_common.cuh (SBO 128 B,
 // LBO = rows/8 * 128 B).
 #pragma once
@@ -27,47 +30,56 @@ constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 constexpr int round_up_c(int a, int b) { return ceil_div_c(a, b) * b; }
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int CIN_, int CHID_, int NC_, int COUT_, int W_, int STRIDE_, int RO_, bool RES_, bool STEM_>
+template <int CIN_, int CHID_, int NC_, int COUT_, int W_, int STRIDE_, int RO_, int FACES_, bool RES_, bool STEM_,
+          bool WSTREAM_>
 struct FusedCfg {
   static constexpr bool STEM = STEM_;            // GEMM1 = im2col(3x3 s2 stem conv), CIN = 27 taps
   static constexpr bool RES = RES_;
+  static constexpr bool WSTREAM = WSTREAM_;      // weights streamed per chunk instead of resident
   static constexpr int CIN = CIN_;               // channels of the NHWC input (STEM: 27)
   static constexpr int CIN_P = round_up_c(CIN_, 16);
   static constexpr int CHID = CHID_, NC = NC_, NCHUNK = CHID_ / NC_;
   static constexpr int COUT = COUT_, COUT_P = round_up_c(COUT_, 16);
+  static constexpr int NSPLIT = ceil_div_c(COUT_P, 256);                 // MMA N <= 256
+  static constexpr int N2 = COUT_P / NSPLIT;
   static constexpr int W = W_, STRIDE = STRIDE_, WO = (W_ - 1) / STRIDE_ + 1;
-  static constexpr int RO = RO_, STRIPS = WO / RO_;
+  static constexpr int RO = RO_, STRIPS = WO / RO_, FACES = FACES_;
   static constexpr int RWIN = (RO_ - 1) * STRIDE_ + 3;                   // window rows incl. halo
-  static constexpr int M1_MAX = (RWIN < W_ ? RWIN : W_) * W_;
+  static constexpr int ROWS_MAX = (RWIN < W_ ? RWIN : W_);               // valid input rows per face
+  static constexpr int M1_MAX = FACES_ * ROWS_MAX * W_;
   static constexpr int MT1 = ceil_div_c(M1_MAX, 128);
-  static constexpr int M2 = RO_ * WO;
-  static constexpr int MT2 = ceil_div_c(M2, 128);
-  static constexpr int HS_COLS = W_ + 2, HS_PIX = RWIN * HS_COLS, HS_STRIDE = NC_ + 4;
+  static constexpr int M2F = RO_ * WO;                                   // output pixels per face
+  static constexpr int M2_MAX = FACES_ * M2F;
+  static constexpr int MT2 = ceil_div_c(M2_MAX, 128);
+  static constexpr int HS_COLS = W_ + 2, HS_FACE = RWIN * HS_COLS, HS_PIX = FACES_ * HS_FACE, HS_STRIDE = NC_ + 4;
   static constexpr int D2_COL = round_up_c(MT1 * NC_, 32);
   static constexpr int TM_COLS = pow2_cols(D2_COL + MT2 * COUT_P);
-  // ---- weight image (global, then shared) ------------------------------------------------------
-  static constexpr int W1_PLANE = NC_ * CIN_P * 2;                       // bytes, one plane one chunk
+  // ---- weight image: [b3 | s3] then NCHUNK x { W1c hi, W1c lo, W3c hi, W3c lo, DW rows } -----------
+  static constexpr int B3_BYTES = round_up_c(2 * COUT_P * 4, 128);       // [2][COUT_P] fp32: b3, s3
+  static constexpr int W1_PLANE = NC_ * CIN_P * 2;                       // bytes, one plane of one chunk
   static constexpr int W3_PLANE = COUT_P * NC_ * 2;
-  static constexpr int OFF_W1 = 0;
-  static constexpr int OFF_W3 = OFF_W1 + NCHUNK * 2 * W1_PLANE;
   static constexpr int DW_ROWS = 12;   // 9 taps, depthwise bias, expand bias b1, expand output scale s1
-  static constexpr int OFF_DW = OFF_W3 + NCHUNK * 2 * W3_PLANE;          // [NCHUNK][DW_ROWS][NC] fp32
-  static constexpr int OFF_B3 = OFF_DW + NCHUNK * DW_ROWS * NC_ * 4;     // [2][COUT_P] fp32: b3, s3
-  static constexpr int W_BYTES = round_up_c(OFF_B3 + 2 * COUT_P * 4, 128);
+  static constexpr int CH_W1 = 0, CH_W3 = 2 * W1_PLANE, CH_DW = CH_W3 + 2 * W3_PLANE;
+  static constexpr int CHUNK_BYTES = round_up_c(CH_DW + DW_ROWS * NC_ * 4, 128);
+  static constexpr int W_BYTES = B3_BYTES + NCHUNK * CHUNK_BYTES;
+  static constexpr int WSTAGES = WSTREAM_ ? 2 : NCHUNK;                  // chunk slots held in smem
   // ---- shared memory carve-up --------------------------------------------------------------------
   static constexpr int X_PLANE = MT1 * 128 * CIN_P * 2;
   static constexpr int A2_PLANE = MT2 * 128 * NC_ * 2;
-  static constexpr int S_W = 0;
-  static constexpr int S_X = S_W + W_BYTES;
+  static constexpr int S_B3 = 0;
+  static constexpr int S_WCH = S_B3 + B3_BYTES;
+  static constexpr int S_X = S_WCH + WSTAGES * CHUNK_BYTES;
   static constexpr int S_A2 = S_X + 2 * X_PLANE;
   static constexpr int S_H = S_A2 + 2 * A2_PLANE;
   static constexpr int S_TOTAL = S_H + HS_PIX * HS_STRIDE * 4;
   static constexpr int SMEM_BYTES = S_TOTAL + 1024;                      // + alignment slack
   static_assert(CHID_ % NC_ == 0 && NC_ % 16 == 0, "hidden chunking");
   static_assert(WO % RO_ == 0, "strips must tile the output");
+  static_assert(FACES_ == 1 || RO_ == WO, "multi-face tiles hold whole faces");
   static_assert(D2_COL + MT2 * COUT_P <= 512, "TMEM columns");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
-  static_assert(COUT_P <= 256, "single MMA N");
+  static_assert(N2 % 16 == 0 && N2 <= 256, "MMA N");
+  static_assert(!WSTREAM_ || NCHUNK >= 2, "streaming needs at least two chunks");
 };
 
 struct FusedArgs {
@@ -78,80 +90,97 @@ struct FusedArgs {
   int* err;
 };
 
-template <class C>
-__global__ void __launch_bounds__(160, 1) fused_mbconv_kernel(const FusedArgs p) {
+// NWW = worker warps (multiple of 4: TMEM lane quarter = warp % 4); the issuer is warp NWW.
+template <class C, int NWW>
+__global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const FusedArgs p) {
+  constexpr int NWT = NWW * 32;          // worker threads
+  constexpr int NWG = NWW / 4;           // worker groups: group g owns every NWG-th (tile, column-chunk) pair
+  static_assert(NWW % 4 == 0 && NWW >= 4 && NWW <= 16, "worker warps");
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_x, bar_d1, bar_epi1, bar_a2, bar_g2, bar_d2free;
+  __shared__ __align__(8) uint64_t bar_w, bar_wfull[2], bar_x, bar_d1, bar_epi1, bar_a2, bar_g2, bar_d2free;
   __shared__ uint32_t tmem_base_s;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int ntiles = p.batch * C::STRIPS;
+  const int row = tid & 127, wg = tid >> 7;   // GEMM row / TMEM lane of this worker, and its group
+  const int face_groups = (p.batch + C::FACES - 1) / C::FACES;
+  const int ntiles = face_groups * C::STRIPS;
 
   if (tid == 0) {
     mbar_init(smem_u32(&bar_w), 1);
-    mbar_init(smem_u32(&bar_x), 128);
+    mbar_init(smem_u32(&bar_wfull[0]), 1);
+    mbar_init(smem_u32(&bar_wfull[1]), 1);
+    mbar_init(smem_u32(&bar_x), NWT);
     mbar_init(smem_u32(&bar_d1), 1);
-    mbar_init(smem_u32(&bar_epi1), 128);
-    mbar_init(smem_u32(&bar_a2), 128);
+    mbar_init(smem_u32(&bar_epi1), NWT);
+    mbar_init(smem_u32(&bar_a2), NWT);
     mbar_init(smem_u32(&bar_g2), 1);
-    mbar_init(smem_u32(&bar_d2free), 128);
+    mbar_init(smem_u32(&bar_d2free), NWT);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc<C::TM_COLS>(smem_u32(&tmem_base_s));
+  if (warp == NWW) tmem_alloc<C::TM_COLS>(smem_u32(&tmem_base_s));
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
 
-  uint8_t* sW = smem + C::S_W;
+  uint8_t* sWch = smem + C::S_WCH;
   uint8_t* sX = smem + C::S_X;
   uint8_t* sA2 = smem + C::S_A2;
   float* sH = reinterpret_cast<float*>(smem + C::S_H);
+  const float* sB3 = reinterpret_cast<const float*>(smem + C::S_B3);
 
-  if (warp < 4) {
+  if (warp < NWW) {
     // =============================== workers ====================================================
     // zero the whole hidden window once: halo columns are never written afterwards
-    for (int i = tid; i < C::HS_PIX * C::HS_STRIDE / 4; i += 128)
+    for (int i = tid; i < C::HS_PIX * C::HS_STRIDE / 4; i += NWT)
       reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    mbar_wait(smem_u32(&bar_w), 0, p.err);                // weights resident
-    const float* sDW = reinterpret_cast<const float*>(sW + C::OFF_DW);
-    const float* sB3 = reinterpret_cast<const float*>(sW + C::OFF_B3);
-    uint32_t n_d1 = 0, n_g2 = 0;                          // completed-phase counters
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mbar_wait(smem_u32(&bar_w), 0, p.err);                // b3/s3 (and, if resident, all chunks) landed
+    uint32_t n_d1 = 0, n_g2 = 0, g = 0;                   // completed-phase counters; g = chunk counter
+    asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int b = tile / C::STRIPS, sp = tile % C::STRIPS;
+      const int fg = tile / C::STRIPS, sp = tile - fg * C::STRIPS;
+      const int f0 = fg * C::FACES;
+      const int nfaces = min(C::FACES, p.batch - f0);
       const int oy0 = sp * C::RO;
       const int iy0 = oy0 * C::STRIDE - 1;
       const int rf = max(iy0, 0), rl = min(iy0 + C::RWIN - 1, C::W - 1);
-      const int M1 = (rl - rf + 1) * C::W;
+      const int ppf = (rl - rf + 1) * C::W;               // valid input pixels per face
+      const int M1 = nfaces * ppf;
       const int mt1 = (M1 + 127) >> 7;
+      const int M2 = nfaces * C::M2F;
+      const int mt2 = (M2 + 127) >> 7;
 
-      // ---- window rows outside the image must read as zero (they may hold a previous tile) ------
-      if (iy0 < 0)
-        for (int i = tid; i < C::HS_COLS * C::HS_STRIDE / 4; i += 128)
-          reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (iy0 + C::RWIN - 1 > C::W - 1)
-        for (int i = tid; i < C::HS_COLS * C::HS_STRIDE / 4; i += 128)
-          reinterpret_cast<float4*>(sH + (size_t)(C::RWIN - 1) * C::HS_COLS * C::HS_STRIDE)[i] =
-              make_float4(0.f, 0.f, 0.f, 0.f);
+      // ---- strip mode: window rows outside the image must read as zero (may hold a previous tile) --
+      if constexpr (C::STRIPS > 1) {
+        if (iy0 < 0)
+          for (int i = tid; i < C::HS_COLS * C::HS_STRIDE / 4; i += NWT)
+            reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy0 + C::RWIN - 1 > C::W - 1)
+          for (int i = tid; i < C::HS_COLS * C::HS_STRIDE / 4; i += NWT)
+            reinterpret_cast<float4*>(sH + (size_t)(C::RWIN - 1) * C::HS_COLS * C::HS_STRIDE)[i] =
+                make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 
       // ---- X tile -> fp16 hi/lo canonical operand ------------------------------------------------
-      for (int t = 0; t < mt1; ++t) {
-        const int m = t * 128 + tid;
-        uint8_t* xh = sX + t * (128 * C::CIN_P * 2) + (tid >> 3) * 128 + (tid & 7) * 16;
-        uint8_t* xl = xh + C::X_PLANE;
-#pragma unroll
-        for (int kg = 0; kg < C::CIN_P / 8; ++kg) {
+      {
+        constexpr int KG = C::CIN_P / 8;
+        for (int e = wg; e < mt1 * KG; e += NWG) {
+          const int t = e / KG, kg = e - t * KG;
+          const int m = t * 128 + row;
+          const int f = (C::FACES > 1) ? m / ppf : 0;
+          const int mr = m - f * ppf;                     // pixel inside the face's valid rows
+          uint8_t* xh = sX + t * (128 * C::CIN_P * 2) + (row >> 3) * 128 + (row & 7) * 16;
+          uint8_t* xl = xh + C::X_PLANE;
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = 0.f;
           if (m < M1) {
             if constexpr (C::STEM) {
               // im2col of the 3x3 stride-2 pad-1 stem conv on the NCHW crop: k = (ci*3+ky)*3+kx
-              const int y = rf + m / C::W, xx = m % C::W;
+              const int y = rf + mr / C::W, xx = mr % C::W;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const int k = kg * 8 + j;
@@ -159,15 +188,15 @@ __global__ void __launch_bounds__(160, 1) fused_mbconv_kernel(const FusedArgs p)
                   const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
                   const int iy = 2 * y - 1 + ky, ix = 2 * xx - 1 + kx;
                   if (iy >= 0 && iy < kImg && ix >= 0 && ix < kImg)
-                    v[j] = __ldg(p.x + ((size_t)(b * 3 + ci) * kImg + iy) * kImg + ix);
+                    v[j] = __ldg(p.x + ((size_t)((f0 + f) * 3 + ci) * kImg + iy) * kImg + ix);
                 }
               }
             } else {
               if (kg * 8 < C::CIN) {
-                const float* src = p.x + ((size_t)(b * C::W + rf) * C::W + m) * C::CIN + kg * 8;
+                const float* src = p.x + ((size_t)((f0 + f) * C::W + rf) * C::W + mr) * C::CIN + kg * 8;
                 const float4 a = *reinterpret_cast<const float4*>(src);
-                const float4 c = *reinterpret_cast<const float4*>(src + 4);
-                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+                const float4 e4 = *reinterpret_cast<const float4*>(src + 4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = e4.x; v[5] = e4.y; v[6] = e4.z; v[7] = e4.w;
               }
             }
           }
@@ -181,21 +210,26 @@ __global__ void __launch_bounds__(160, 1) fused_mbconv_kernel(const FusedArgs p)
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&bar_x));
 
-      for (int c = 0; c < C::NCHUNK; ++c) {
-        const float* dwc = sDW + c * C::DW_ROWS * C::NC;   // [9][NC] taps, [NC] bdw, [NC] b1, [NC] s1
-        // ---- EPI1: D1 -> relu6(+b1) -> hidden window ---------------------------------------------
+      for (int c = 0; c < C::NCHUNK; ++c, ++g) {
+        const int slot = C::WSTREAM ? (int)(g & 1) : c;
+        if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (g >> 1) & 1, p.err);
+        const float* dwc = reinterpret_cast<const float*>(sWch + slot * C::CHUNK_BYTES + C::CH_DW);
+        // ---- EPI1: D1 -> relu6(s1*D1 + b1) -> hidden window --------------------------------------
         mbar_wait(smem_u32(&bar_d1), n_d1 & 1, p.err);
         ++n_d1;
         tc_fence_after_sync();
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // every worker is done reading Hs (DW c-1)
-        for (int t = 0; t < mt1; ++t) {
-          const int m = t * 128 + tid;
-          const int yl = m / C::W, xx = m - yl * C::W;
-          float* hrow = sH + (size_t)((rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE;
-#pragma unroll
-          for (int j0 = 0; j0 < C::NC; j0 += 16) {
+        asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");     // every worker is done reading Hs (DW c-1)
+        {
+          constexpr int JC = C::NC / 16;
+          for (int e = wg; e < mt1 * JC; e += NWG) {
+            const int t = e / JC, j0 = (e - t * JC) * 16;
+            const int m = t * 128 + row;
+            const int f = (C::FACES > 1) ? m / ppf : 0;
+            const int mr = m - f * ppf;
+            const int yl = mr / C::W, xx = mr - yl * C::W;
+            float* hrow = sH + (size_t)(f * C::HS_FACE + (rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE;
             float v[16];
-            tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + t * C::NC + j0, v);
+            tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * C::NC + j0, v);
             if (m < M1) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
@@ -210,18 +244,19 @@ __global__ void __launch_bounds__(160, 1) fused_mbconv_kernel(const FusedArgs p)
         }
         tc_fence_before_sync();
         mbar_arrive(smem_u32(&bar_epi1));
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // hidden window complete
+        asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");     // hidden window complete
         // ---- DW: 3x3 depthwise on the window -> A2 operand ----------------------------------------
         if (c > 0) {                                        // A2 is free once GEMM2(c-1) has completed
           mbar_wait(smem_u32(&bar_g2), n_g2 & 1, p.err);
           ++n_g2;
         }
         {
-          constexpr int NKG = C::NC / 8, RG = (C::M2 + 7) / 8;
+          constexpr int NKG = C::NC / 8;
+          const int RG = (M2 + 7) >> 3;
           const int q = tid >> 3, l8 = tid & 7;
           int cur_kg = -1;
           float wr[9][8], bd[8];
-          for (int item = q; item < NKG * RG; item += 16) {
+          for (int item = q; item < NKG * RG; item += NWW * 4) {
             const int kg = item / RG, rg = item - kg * RG;
             if (kg != cur_kg) {
               cur_kg = kg;
@@ -237,9 +272,11 @@ __global__ void __launch_bounds__(160, 1) fused_mbconv_kernel(const FusedArgs p)
               bd[0] = a.x; bd[1] = a.y; bd[2] = a.z; bd[3] = a.w; bd[4] = e.x; bd[5] = e.y; bd[6] = e.z; bd[7] = e.w;
             }
             const int m2 = rg * 8 + l8;
-            if (m2 < C::M2) {
-              const int oyl = m2 / C::WO, ox = m2 - oyl * C::WO;
-              const float* h0 = sH + (size_t)((oyl * C::STRIDE) * C::HS_COLS + ox * C::STRIDE) * C::HS_STRIDE + kg * 8;
+            if (m2 < M2) {
+              const int f = (C::FACES > 1) ? m2 / C::M2F : 0;
+              const int mr = m2 - f * C::M2F;
+              const int oyl = mr / C::WO, ox = mr - oyl * C::WO;
+              const float* h0 = sH + (size_t)(f * C::HS_FACE + (oyl * C::STRIDE) * C::HS_COLS + ox * C::STRIDE) * C::HS_STRIDE + kg * 8;
               float acc[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) acc[j] = bd[j];
@@ -270,18 +307,20 @@ __global__ void __launch_bounds__(160, 1) fused_mbconv_kernel(const FusedArgs p)
         mbar_arrive(smem_u32(&bar_a2));
       }
 
-      // ---- EPI2: D2 + b3 (+ skip) -> global NHWC ---------------------------------------------------
+      // ---- EPI2: s3*D2 + b3 (+ skip) -> global NHWC --------------------------------------------------
       mbar_wait(smem_u32(&bar_g2), n_g2 & 1, p.err);
       ++n_g2;
       tc_fence_after_sync();
-      for (int t = 0; t < C::MT2; ++t) {
-        const int m2 = t * 128 + tid;
-        float* orow = p.y + ((size_t)(b * C::WO + oy0) * C::WO + m2) * C::COUT;
-#pragma unroll
-        for (int j0 = 0; j0 < C::COUT_P; j0 += 16) {
+      {
+        constexpr int JC = C::COUT_P / 16;
+        for (int e = wg; e < mt2 * JC; e += NWG) {
+          const int t = e / JC, j0 = (e - t * JC) * 16;
+          const int m2 = t * 128 + row;
+          // tiles are contiguous in NHWC memory: (face f0, output row oy0) + m2 pixels
+          float* orow = p.y + ((size_t)(f0 * C::WO + oy0) * C::WO + m2) * C::COUT;
           float v[16];
-          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + C::D2_COL + t * C::COUT_P + j0, v);
-          if (m2 < C::M2) {
+          tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::D2_COL + t * C::COUT_P + j0, v);
+          if (m2 < M2) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               if (j0 + j < C::COUT) {
@@ -291,7 +330,7 @@ __global__ void __launch_bounds__(160, 1) fused_mbconv_kernel(const FusedArgs p)
                                        fmaf(v[j + 3], sc.w, bb.w));
                 if constexpr (C::RES) {      // stride 1, CIN == COUT: same pixel of the block input
                   const float4 r = *reinterpret_cast<const float4*>(
-                      p.x + ((size_t)(b * C::W + oy0) * C::W + m2) * C::CIN + j0 + j);
+                      p.x + ((size_t)(f0 * C::W + oy0) * C::W + m2) * C::CIN + j0 + j);
                   o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                 }
                 *reinterpret_cast<float4*>(orow + j0 + j) = o;
@@ -303,66 +342,90 @@ __global__ void __launch_bounds__(160, 1) fused_mbconv_kernel(const FusedArgs p)
       tc_fence_before_sync();
       mbar_arrive(smem_u32(&bar_d2free));
     }
-  } else if (tid == 128) {
-    // =============================== MMA issuer ==================================================
-    mbar_expect_tx(smem_u32(&bar_w), C::W_BYTES);
-    bulk_g2s(smem_u32(sW), p.wimg, C::W_BYTES, smem_u32(&bar_w));
+  } else if (tid == NWT) {
+    // =============================== MMA issuer / weight loader ====================================
+    const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint32_t total_chunks = (uint32_t)my_tiles * C::NCHUNK;
+    auto load_chunk = [&](uint32_t gi) {                     // streaming: chunk gi -> slot gi & 1
+      const uint32_t slot = gi & 1, c = gi % C::NCHUNK;
+      mbar_expect_tx(smem_u32(&bar_wfull[slot]), C::CHUNK_BYTES);
+      bulk_g2s(smem_u32(sWch + slot * C::CHUNK_BYTES), p.wimg + C::B3_BYTES + (size_t)c * C::CHUNK_BYTES, C::CHUNK_BYTES,
+               smem_u32(&bar_wfull[slot]));
+    };
+    if constexpr (C::WSTREAM) {
+      mbar_expect_tx(smem_u32(&bar_w), C::B3_BYTES);
+      bulk_g2s(smem_u32(smem + C::S_B3), p.wimg, C::B3_BYTES, smem_u32(&bar_w));
+      if (total_chunks > 0) load_chunk(0);
+      if (total_chunks > 1) load_chunk(1);
+    } else {
+      mbar_expect_tx(smem_u32(&bar_w), C::W_BYTES);
+      bulk_g2s(smem_u32(smem + C::S_B3), p.wimg, C::W_BYTES, smem_u32(&bar_w));
+    }
     mbar_wait(smem_u32(&bar_w), 0, p.err);
     const uint32_t idesc1 = make_idesc_f16(128, C::NC);
-    const uint32_t idesc2 = make_idesc_f16(128, C::COUT_P);
+    const uint32_t idesc2 = make_idesc_f16(128, C::N2);
     constexpr uint32_t LBO_W1 = (C::NC / 8) * 128, LBO_W3 = (C::COUT_P / 8) * 128;
-    uint32_t n_x = 0, n_epi1 = 0, n_a2 = 0, n_free = 0;
+    uint32_t n_x = 0, n_epi1 = 0, n_a2 = 0, n_free = 0, n_g2i = 0;
+    uint32_t g = 0;                                          // chunk counter of the current GEMM2
     int ntile_local = 0;
 
-    auto gemm1 = [&](int c, int mt1) {
+    auto gemm1 = [&](uint32_t gi, int c, int mt1) {
+      const int slot = C::WSTREAM ? (int)(gi & 1) : c;
+      if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (gi >> 1) & 1, p.err);
+      const uint32_t wbase = smem_u32(sWch + slot * C::CHUNK_BYTES) + C::CH_W1;
       for (int t = 0; t < mt1; ++t) {
         uint32_t acc = 0;
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
           const uint32_t a_base = smem_u32(sX) + (pass == 2 ? C::X_PLANE : 0) + t * (128 * C::CIN_P * 2);
-          const uint32_t b_base = smem_u32(sW) + C::OFF_W1 + (2 * c + (pass == 1 ? 1 : 0)) * C::W1_PLANE;
+          const uint32_t b_base = wbase + (pass == 1 ? C::W1_PLANE : 0);
 #pragma unroll
           for (int ks = 0; ks < C::CIN_P / 16; ++ks) {
             umma_f16(tmem + t * C::NC, make_smem_desc(a_base + ks * 4096, 2048, 128),
-                      make_smem_desc(b_base + ks * 2 * LBO_W1, LBO_W1, 128), idesc1, acc);
+                     make_smem_desc(b_base + ks * 2 * LBO_W1, LBO_W1, 128), idesc1, acc);
             acc = 1;
           }
         }
       }
       umma_commit(smem_u32(&bar_d1));
     };
-    auto gemm2 = [&](int c) {
-      for (int t = 0; t < C::MT2; ++t) {
+    auto gemm2 = [&](uint32_t gi, int c, int mt2) {
+      const int slot = C::WSTREAM ? (int)(gi & 1) : c;
+      const uint32_t wbase = smem_u32(sWch + slot * C::CHUNK_BYTES) + C::CH_W3;
+      for (int t = 0; t < mt2; ++t) {
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
           const uint32_t a_base = smem_u32(sA2) + (pass == 2 ? C::A2_PLANE : 0) + t * (128 * C::NC * 2);
-          const uint32_t b_base = smem_u32(sW) + C::OFF_W3 + (2 * c + (pass == 1 ? 1 : 0)) * C::W3_PLANE;
+          const uint32_t b_base = wbase + (pass == 1 ? C::W3_PLANE : 0);
 #pragma unroll
-          for (int ks = 0; ks < C::NC / 16; ++ks) {
-            umma_f16(tmem + C::D2_COL + t * C::COUT_P, make_smem_desc(a_base + ks * 4096, 2048, 128),
-                      make_smem_desc(b_base + ks * 2 * LBO_W3, LBO_W3, 128), idesc2,
-                      (c > 0 || pass > 0 || ks > 0) ? 1u : 0u);
-          }
+          for (int ks = 0; ks < C::NC / 16; ++ks)
+#pragma unroll
+            for (int hh = 0; hh < C::NSPLIT; ++hh)
+              umma_f16(tmem + C::D2_COL + t * C::COUT_P + hh * C::N2, make_smem_desc(a_base + ks * 4096, 2048, 128),
+                       make_smem_desc(b_base + ks * 2 * LBO_W3 + hh * (C::N2 / 8) * 128, LBO_W3, 128), idesc2,
+                       (c > 0 || pass > 0 || ks > 0) ? 1u : 0u);
         }
       }
       umma_commit(smem_u32(&bar_g2));
     };
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ntile_local) {
-      const int sp = tile % C::STRIPS;
+      const int fg = tile / C::STRIPS, sp = tile - fg * C::STRIPS;
+      const int nfaces = min(C::FACES, p.batch - fg * C::FACES);
       const int iy0 = sp * C::RO * C::STRIDE - 1;
       const int rf = max(iy0, 0), rl = min(iy0 + C::RWIN - 1, C::W - 1);
-      const int mt1 = ((rl - rf + 1) * C::W + 127) >> 7;
+      const int mt1 = (nfaces * (rl - rf + 1) * C::W + 127) >> 7;
+      const int mt2 = (nfaces * C::M2F + 127) >> 7;
       mbar_wait(smem_u32(&bar_x), n_x & 1, p.err);
       ++n_x;
       tc_fence_after_sync();
-      gemm1(0, mt1);
-      for (int c = 0; c < C::NCHUNK; ++c) {
+      gemm1(g, 0, mt1);
+      for (int c = 0; c < C::NCHUNK; ++c, ++g) {
         if (c + 1 < C::NCHUNK) {
           mbar_wait(smem_u32(&bar_epi1), n_epi1 & 1, p.err);    // D1 drained by the workers
           ++n_epi1;
           tc_fence_after_sync();
-          gemm1(c + 1, mt1);
+          gemm1(g + 1, c + 1, mt1);
         }
         mbar_wait(smem_u32(&bar_a2), n_a2 & 1, p.err);
         ++n_a2;
@@ -371,7 +434,13 @@ __global__ void __launch_bounds__(160, 1) fused_mbconv_kernel(const FusedArgs p)
           ++n_free;
         }
         tc_fence_after_sync();
-        gemm2(c);
+        gemm2(g, c, mt2);
+        if constexpr (C::WSTREAM) {
+          // slot g&1 may be refilled once GEMM2(g) has read W3c (the workers are already past it)
+          mbar_wait(smem_u32(&bar_g2), n_g2i & 1, p.err);
+          if (g + 2 < total_chunks) load_chunk(g + 2);
+        }
+        ++n_g2i;
       }
       // the last chunk's EPI1 arrival is not consumed above: keep the phase counter in step
       mbar_wait(smem_u32(&bar_epi1), n_epi1 & 1, p.err);
@@ -380,19 +449,25 @@ __global__ void __launch_bounds__(160, 1) fused_mbconv_kernel(const FusedArgs p)
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NWW) {
     __syncwarp();
     tmem_dealloc<C::TM_COLS>(tmem);
   }
 }
 
 // ---- the instantiations used by the backbone (SURVEY.md section 8(a) shape table) -------------------
-//                         CIN CHID NC COUT  W  S RO  RES    STEM
-using FusedStemB1 = FusedCfg<27, 32, 32, 16, 60, 1, 6, false, true>;    // features[0] + features[1]
-using FusedB2 = FusedCfg<16, 96, 32, 24, 60, 2, 5, false, false>;       // features[2]
-using FusedB3 = FusedCfg<24, 144, 16, 24, 30, 1, 15, true, false>;      // features[3]
-using FusedB4 = FusedCfg<24, 144, 48, 32, 30, 2, 5, false, false>;      // features[4]
-using FusedB56 = FusedCfg<32, 192, 32, 32, 15, 1, 15, true, false>;     // features[5], features[6]
-using FusedB7 = FusedCfg<32, 192, 32, 64, 15, 2, 8, false, false>;      // features[7]
+//                          CIN CHID NC COUT  W  S  RO FACES RES    STEM   WSTREAM
+using FusedStemB1 = FusedCfg<27, 32, 32, 16, 60, 1, 6, 1, false, true, false>;    // features[0] + features[1]
+using FusedB2 = FusedCfg<16, 96, 32, 24, 60, 2, 5, 1, false, false, false>;       // features[2]
+using FusedB3 = FusedCfg<24, 144, 16, 24, 30, 1, 15, 1, true, false, false>;      // features[3]
+using FusedB4 = FusedCfg<24, 144, 48, 32, 30, 2, 5, 1, false, false, false>;      // features[4]
+using FusedB56 = FusedCfg<32, 192, 32, 32, 15, 1, 15, 1, true, false, false>;     // features[5], [6]
+using FusedB7 = FusedCfg<32, 192, 32, 64, 15, 2, 8, 1, false, false, false>;      // features[7]
+using FusedB8 = FusedCfg<64, 384, 64, 64, 8, 1, 8, 2, true, false, true>;         // features[8..10]
+using FusedB11 = FusedCfg<64, 384, 64, 96, 8, 1, 8, 2, false, false, true>;       // features[11]
+using FusedB12 = FusedCfg<96, 576, 32, 96, 8, 1, 8, 2, true, false, true>;        // features[12], [13]
+using FusedB14 = FusedCfg<96, 576, 32, 160, 8, 2, 4, 2, false, false, true>;      // features[14]
+using FusedB15 = FusedCfg<160, 960, 32, 160, 4, 1, 4, 8, true, false, true>;      // features[15], [16]
+using FusedB17 = FusedCfg<160, 960, 16, 320, 4, 1, 4, 8, false, false, true>;     // features[17]
 
 }  // namespace syn

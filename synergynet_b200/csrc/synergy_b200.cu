@@ -1,6 +1,7 @@
 // C-ABI implementation of the SynergyNet inference hot path for B200 (sm_100a).
 // See include/synergy_b200.h for the contract and the reference lines each entry replaces.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -61,7 +62,7 @@ struct syn_handle {
   bool tc_ready = false;
   // fused stem+block1 and blocks 2..7 (kernels_fused.cuh): one weight image per fused launch
   uint8_t* d_fused = nullptr;
-  size_t fused_off[8] = {};                    // index = features[] index of the block (1..7)
+  size_t fused_off[18] = {};                   // index = features[] index of the block (1..17)
 
   // activation workspace (NHWC fp32), grown on demand
   int ws_batch = 0;
@@ -186,28 +187,31 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
   int li = 1;
   if (h->engine == SYN_ENGINE_TC_FUSED) {
     // stem + block 1, then blocks 2..7, each one fused launch; only block outputs exist
-    if (stop_layer >= 0 && stop_layer <= 20 && (stop_layer < 2 || (stop_layer - 2) % 3 != 0))
+    if (stop_layer >= 0 && stop_layer <= 50 && (stop_layer < 2 || (stop_layer - 2) % 3 != 0))
       return fail(SYN_ERR_UNSUPPORTED, "conv %d lives inside a fused block and is never materialised", stop_layer);
-    struct Step { int block, last_conv; };
-    static const Step steps[7] = {{1, 2}, {2, 5}, {3, 8}, {4, 11}, {5, 14}, {6, 17}, {7, 20}};
     const float* in = x;
-    for (const Step& s : steps) {
+    for (int b = 1; b <= 17; ++b) {
       float* out = h->buf_io[cur ^ 1];
-      switch (s.block) {
-        case 1: rc = launch_fused<FusedStemB1>(h, in, 1, out, batch, st); break;
-        case 2: rc = launch_fused<FusedB2>(h, in, 2, out, batch, st); break;
-        case 3: rc = launch_fused<FusedB3>(h, in, 3, out, batch, st); break;
-        case 4: rc = launch_fused<FusedB4>(h, in, 4, out, batch, st); break;
-        case 5: rc = launch_fused<FusedB56>(h, in, 5, out, batch, st); break;
-        case 6: rc = launch_fused<FusedB56>(h, in, 6, out, batch, st); break;
-        default: rc = launch_fused<FusedB7>(h, in, 7, out, batch, st); break;
+      switch (b) {
+        case 1: rc = launch_fused<FusedStemB1>(h, in, b, out, batch, st); break;
+        case 2: rc = launch_fused<FusedB2>(h, in, b, out, batch, st); break;
+        case 3: rc = launch_fused<FusedB3>(h, in, b, out, batch, st); break;
+        case 4: rc = launch_fused<FusedB4>(h, in, b, out, batch, st); break;
+        case 5: case 6: rc = launch_fused<FusedB56>(h, in, b, out, batch, st); break;
+        case 7: rc = launch_fused<FusedB7>(h, in, b, out, batch, st); break;
+        case 8: case 9: case 10: rc = launch_fused<FusedB8>(h, in, b, out, batch, st); break;
+        case 11: rc = launch_fused<FusedB11>(h, in, b, out, batch, st); break;
+        case 12: case 13: rc = launch_fused<FusedB12>(h, in, b, out, batch, st); break;
+        case 14: rc = launch_fused<FusedB14>(h, in, b, out, batch, st); break;
+        case 15: case 16: rc = launch_fused<FusedB15>(h, in, b, out, batch, st); break;
+        default: rc = launch_fused<FusedB17>(h, in, b, out, batch, st); break;
       }
       if (rc != SYN_OK) return rc;
       cur ^= 1;
       in = h->buf_io[cur];
-      if (stop_layer == s.last_conv) return dbg(s.last_conv, h->buf_io[cur]);
+      if (stop_layer == 3 * b - 1) return dbg(3 * b - 1, h->buf_io[cur]);
     }
-    li = 21;
+    li = 51;
   } else {
   stem_conv3x3s2_kernel<<<batch * 60, kStemThreads, 0, st>>>(x, h->dconv[0].w, h->dconv[0].bias,
                                                             h->buf_io[cur], batch);
@@ -333,7 +337,7 @@ void pack_fused(std::vector<uint8_t>& img, const float* w1, int K, const float* 
     *reinterpret_cast<uint16_t*>(img.data() + byte_off) = h;
     *reinterpret_cast<uint16_t*>(img.data() + byte_off + plane_bytes) = l;
   };
-  float* b3p = reinterpret_cast<float*>(img.data() + C::OFF_B3);
+  float* b3p = reinterpret_cast<float*>(img.data());                   // [b3 | s3]
   std::vector<float> s3(C::COUT);
   for (int n = 0; n < C::COUT; ++n) {
     s3[n] = channel_scale(w3 + n, (size_t)C::COUT, C::CHID);
@@ -341,13 +345,14 @@ void pack_fused(std::vector<uint8_t>& img, const float* w1, int K, const float* 
     b3p[C::COUT_P + n] = 1.0f / (kActScaleHost * s3[n]);
   }
   for (int c = 0; c < C::NCHUNK; ++c) {
-    float* d = reinterpret_cast<float*>(img.data() + C::OFF_DW) + (size_t)c * C::DW_ROWS * C::NC;
+    const size_t chunk = C::B3_BYTES + (size_t)c * C::CHUNK_BYTES;
+    float* d = reinterpret_cast<float*>(img.data() + chunk + C::CH_DW);
     for (int n = 0; n < C::NC; ++n) {
       const int ch = c * C::NC + n;
       const float s1 = channel_scale(w1 + ch, (size_t)C::CHID, K);
       for (int k = 0; k < K; ++k) {
         const size_t off = (size_t)(n / 8) * 128 + (size_t)(k / 8) * ((C::NC / 8) * 128) + (n % 8) * 16 + (k % 8) * 2;
-        put(C::OFF_W1 + (size_t)(2 * c) * C::W1_PLANE + off, w1[(size_t)k * C::CHID + ch] * s1, C::W1_PLANE);
+        put(chunk + C::CH_W1 + off, w1[(size_t)k * C::CHID + ch] * s1, C::W1_PLANE);
       }
       for (int t = 0; t < 9; ++t) d[t * C::NC + n] = dw[(size_t)t * C::CHID + ch];
       d[9 * C::NC + n] = bdw[ch];
@@ -357,23 +362,46 @@ void pack_fused(std::vector<uint8_t>& img, const float* w1, int K, const float* 
     for (int n = 0; n < C::COUT; ++n)
       for (int k = 0; k < C::NC; ++k) {
         const size_t off = (size_t)(n / 8) * 128 + (size_t)(k / 8) * ((C::COUT_P / 8) * 128) + (n % 8) * 16 + (k % 8) * 2;
-        put(C::OFF_W3 + (size_t)(2 * c) * C::W3_PLANE + off, w3[(size_t)(c * C::NC + k) * C::COUT + n] * s3[n], C::W3_PLANE);
+        put(chunk + C::CH_W3 + off, w3[(size_t)(c * C::NC + k) * C::COUT + n] * s3[n], C::W3_PLANE);
       }
   }
 }
 
-template <class C>
-int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, cudaStream_t st) {
+// Worker warps of the fused kernel: 12 by default (3 per SM sub-partition); SYN_FUSED_WARPS=8|12|16
+// selects another instantiation for tuning runs.
+inline int fused_worker_warps() {
+  static const int v = [] {
+    const char* e = getenv("SYN_FUSED_WARPS");
+    const int n = e ? atoi(e) : 12;
+    return (n == 8 || n == 12 || n == 16) ? n : 12;
+  }();
+  return v;
+}
+
+template <class C, int NWW>
+int launch_fused_nww(syn_handle* h, const FusedArgs& a, int grid, cudaStream_t st) {
   static bool attr_set[16] = {};
   if (!attr_set[h->device & 15]) {
-    SYN_CUDA(cudaFuncSetAttribute(fused_mbconv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    SYN_CUDA(cudaFuncSetAttribute(fused_mbconv_kernel<C, NWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set[h->device & 15] = true;
   }
+  fused_mbconv_kernel<C, NWW><<<grid, (NWW + 1) * 32, C::SMEM_BYTES, st>>>(a);
+  return SYN_OK;
+}
+
+template <class C>
+int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, cudaStream_t st) {
   FusedArgs a;
   a.x = x; a.wimg = h->d_fused + h->fused_off[block]; a.y = y; a.batch = batch; a.err = h->d_err;
-  const int ntiles = batch * C::STRIPS;
+  const int ntiles = (batch + C::FACES - 1) / C::FACES * C::STRIPS;
   const int grid = std::min(ntiles, h->sm_count);
-  fused_mbconv_kernel<C><<<grid, 160, C::SMEM_BYTES, st>>>(a);
+  int rc;
+  switch (fused_worker_warps()) {
+    case 8: rc = launch_fused_nww<C, 8>(h, a, grid, st); break;
+    case 16: rc = launch_fused_nww<C, 16>(h, a, grid, st); break;
+    default: rc = launch_fused_nww<C, 12>(h, a, grid, st); break;
+  }
+  if (rc != SYN_OK) return rc;
   SYN_LAUNCH_CHECK("fused_mbconv_kernel");
   h->launches++;
   return SYN_OK;
@@ -617,12 +645,16 @@ int syn_commit(syn_handle_t* h) {
       all.resize((all.size() + 1023) / 1024 * 1024);
     };
     pack_fused<FusedStemB1>(img, W(0), 27, Bv(0), W(1), Bv(1), W(2), Bv(2)); add(1);
-    pack_fused<FusedB2>(img, W(3), 16, Bv(3), W(4), Bv(4), W(5), Bv(5)); add(2);
-    pack_fused<FusedB3>(img, W(6), 24, Bv(6), W(7), Bv(7), W(8), Bv(8)); add(3);
-    pack_fused<FusedB4>(img, W(9), 24, Bv(9), W(10), Bv(10), W(11), Bv(11)); add(4);
-    pack_fused<FusedB56>(img, W(12), 32, Bv(12), W(13), Bv(13), W(14), Bv(14)); add(5);
-    pack_fused<FusedB56>(img, W(15), 32, Bv(15), W(16), Bv(16), W(17), Bv(17)); add(6);
-    pack_fused<FusedB7>(img, W(18), 32, Bv(18), W(19), Bv(19), W(20), Bv(20)); add(7);
+    auto blk = [&](int b, auto tag) {      // block b >= 2: convs 3b-3 (expand), 3b-2 (dw), 3b-1 (project)
+      using Cfg = decltype(tag);
+      const int e = 3 * b - 3;
+      pack_fused<Cfg>(img, W(e), Cfg::CIN, Bv(e), W(e + 1), Bv(e + 1), W(e + 2), Bv(e + 2));
+      add(b);
+    };
+    blk(2, FusedB2{}); blk(3, FusedB3{}); blk(4, FusedB4{}); blk(5, FusedB56{}); blk(6, FusedB56{});
+    blk(7, FusedB7{}); blk(8, FusedB8{}); blk(9, FusedB8{}); blk(10, FusedB8{}); blk(11, FusedB11{});
+    blk(12, FusedB12{}); blk(13, FusedB12{}); blk(14, FusedB14{}); blk(15, FusedB15{}); blk(16, FusedB15{});
+    blk(17, FusedB17{});
     if (h->d_fused) { cudaFree(h->d_fused); h->d_fused = nullptr; }
     SYN_CUDA(cudaMalloc(&h->d_fused, all.size()));
     SYN_CUDA(cudaMemcpy(h->d_fused, all.data(), all.size(), cudaMemcpyHostToDevice));
