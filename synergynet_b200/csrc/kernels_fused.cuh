@@ -71,7 +71,10 @@ struct FusedCfg {
   static constexpr int S_X = S_WCH + WSTAGES * CHUNK_BYTES;
   static constexpr int S_A2 = S_X + 2 * X_PLANE;
   static constexpr int S_H = S_A2 + 2 * A2_PLANE;
-  static constexpr int S_TOTAL = S_H + HS_PIX * HS_STRIDE * 4;
+  // stem only: staged input rows [3][IN_ROWS][IN_STRIDE] fp32, column c of the crop at index c + 4
+  static constexpr int IN_ROWS = 2 * ROWS_MAX + 1, IN_STRIDE = 128;
+  static constexpr int S_IN = S_H + HS_PIX * HS_STRIDE * 4;
+  static constexpr int S_TOTAL = S_IN + (STEM_ ? 3 * IN_ROWS * IN_STRIDE * 4 : 0);
   static constexpr int SMEM_BYTES = S_TOTAL + 1024;                      // + alignment slack
   static_assert(CHID_ % NC_ == 0 && NC_ % 16 == 0, "hidden chunking");
   static_assert(WO % RO_ == 0, "strips must tile the output");
@@ -101,7 +104,9 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
   __shared__ __align__(8) uint64_t bar_w, bar_wfull[2], bar_x, bar_d1, bar_epi1, bar_a2, bar_g2, bar_d2free;
   __shared__ uint32_t tmem_base_s;
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the pointer in the shared address space (no integer round trip): a generic pointer here
+  // turns every tile access into LD.E/ST.E instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid & 127, wg = tid >> 7;   // GEMM row / TMEM lane of this worker, and its group
   const int face_groups = (p.batch + C::FACES - 1) / C::FACES;
@@ -130,6 +135,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
   uint8_t* sA2 = smem + C::S_A2;
   float* sH = reinterpret_cast<float*>(smem + C::S_H);
   const float* sB3 = reinterpret_cast<const float*>(smem + C::S_B3);
+  float* sIn = reinterpret_cast<float*>(smem + C::S_IN);   // stem variant only
 
   if (warp < NWW) {
     // =============================== workers ====================================================
@@ -164,6 +170,19 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                 make_float4(0.f, 0.f, 0.f, 0.f);
       }
 
+      // ---- stem: stage the crop rows this strip needs (coalesced), zero outside the image ----------
+      if constexpr (C::STEM) {
+        const int iy_first = 2 * rf - 1, nin = 2 * (rl - rf + 1) + 1;
+        for (int i = tid; i < 3 * nin * 31; i += NWT) {
+          const int c4 = i % 31, r = (i / 31) % nin, ci = i / (31 * nin);
+          const int iy = iy_first + r;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);                // c4 == 0: the columns left of the crop
+          if (c4 > 0 && iy >= 0 && iy < kImg)
+            v = *reinterpret_cast<const float4*>(p.x + ((size_t)(f0 * 3 + ci) * kImg + iy) * kImg + (c4 - 1) * 4);
+          *reinterpret_cast<float4*>(sIn + (ci * C::IN_ROWS + r) * C::IN_STRIDE + c4 * 4) = v;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");
+      }
       // ---- X tile -> fp16 hi/lo canonical operand ------------------------------------------------
       {
         constexpr int KG = C::CIN_P / 8;
@@ -179,18 +198,22 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           for (int j = 0; j < 8; ++j) v[j] = 0.f;
           if (m < M1) {
             if constexpr (C::STEM) {
-              // im2col of the 3x3 stride-2 pad-1 stem conv on the NCHW crop: k = (ci*3+ky)*3+kx
-              const int y = rf + mr / C::W, xx = mr % C::W;
+              // im2col of the 3x3 stride-2 pad-1 stem conv from the staged rows: k = (ci*3+ky)*3+kx;
+              // the kg switch makes every tap offset a compile-time constant
+              const int yl = mr / C::W, xx = mr - yl * C::W;
+              const float* base = sIn + (2 * yl) * C::IN_STRIDE + 2 * xx + 3;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int k = kg * 8 + j;
-                if (k < 27) {
-                  const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
-                  const int iy = 2 * y - 1 + ky, ix = 2 * xx - 1 + kx;
-                  if (iy >= 0 && iy < kImg && ix >= 0 && ix < kImg)
-                    v[j] = __ldg(p.x + ((size_t)((f0 + f) * 3 + ci) * kImg + iy) * kImg + ix);
+              for (int kgc = 0; kgc < KG; ++kgc)
+                if (kg == kgc) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const int k = kgc * 8 + j;
+                    if (k < 27) {
+                      const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+                      v[j] = base[(ci * C::IN_ROWS + ky) * C::IN_STRIDE + kx];
+                    }
+                  }
                 }
-              }
             } else {
               if (kg * 8 < C::CIN) {
                 const float* src = p.x + ((size_t)((f0 + f) * C::W + rf) * C::W + mr) * C::CIN + kg * 8;
@@ -220,19 +243,21 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         tc_fence_after_sync();
         asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");     // every worker is done reading Hs (DW c-1)
         {
-          constexpr int JC = C::NC / 16;
+          constexpr int JW = (C::NC % 32 == 0) ? 32 : 16;      // columns per TMEM load
+          constexpr int JC = C::NC / JW;
           for (int e = wg; e < mt1 * JC; e += NWG) {
-            const int t = e / JC, j0 = (e - t * JC) * 16;
+            const int t = e / JC, j0 = (e - t * JC) * JW;
             const int m = t * 128 + row;
             const int f = (C::FACES > 1) ? m / ppf : 0;
             const int mr = m - f * ppf;
             const int yl = mr / C::W, xx = mr - yl * C::W;
             float* hrow = sH + (size_t)(f * C::HS_FACE + (rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE;
-            float v[16];
-            tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * C::NC + j0, v);
+            float v[JW];
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * C::NC + j0;
+            if constexpr (JW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
             if (m < M1) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
+              for (int j = 0; j < JW; j += 4) {
                 const float4 bb = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0 + j);
                 const float4 sc = *reinterpret_cast<const float4*>(dwc + 11 * C::NC + j0 + j);
                 *reinterpret_cast<float4*>(hrow + j0 + j) =
@@ -256,8 +281,10 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           const int q = tid >> 3, l8 = tid & 7;
           int cur_kg = -1;
           float wr[9][8], bd[8];
-          for (int item = q; item < NKG * RG; item += NWW * 4) {
-            const int kg = item / RG, rg = item - kg * RG;
+          // (kg, row-group) pairs, kg-major, dealt round-robin to the quarter-warps without a division
+          int kg = 0, rg = q;
+          while (rg >= RG) { rg -= RG; ++kg; }
+          for (; kg < NKG;) {
             if (kg != cur_kg) {
               cur_kg = kg;
 #pragma unroll
@@ -296,11 +323,13 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
               uint32_t h[4], l[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                split2_f16(relu6f(acc[2 * j]) * kActScale, relu6f(acc[2 * j + 1]) * kActScale, h[j], l[j]);
+                split2_f16<false>(relu6f(acc[2 * j]) * kActScale, relu6f(acc[2 * j + 1]) * kActScale, h[j], l[j]);
               uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16;
               *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
               *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = make_uint4(l[0], l[1], l[2], l[3]);
             }
+            rg += NWW * 4;
+            while (rg >= RG && kg < NKG) { rg -= RG; ++kg; }
           }
         }
         fence_proxy_async_smem();
@@ -312,17 +341,19 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       ++n_g2;
       tc_fence_after_sync();
       {
-        constexpr int JC = C::COUT_P / 16;
+        constexpr int JW = (C::COUT_P % 32 == 0) ? 32 : 16;
+        constexpr int JC = C::COUT_P / JW;
         for (int e = wg; e < mt2 * JC; e += NWG) {
-          const int t = e / JC, j0 = (e - t * JC) * 16;
+          const int t = e / JC, j0 = (e - t * JC) * JW;
           const int m2 = t * 128 + row;
           // tiles are contiguous in NHWC memory: (face f0, output row oy0) + m2 pixels
           float* orow = p.y + ((size_t)(f0 * C::WO + oy0) * C::WO + m2) * C::COUT;
-          float v[16];
-          tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::D2_COL + t * C::COUT_P + j0, v);
+          float v[JW];
+          const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::D2_COL + t * C::COUT_P + j0;
+          if constexpr (JW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
           if (m2 < M2) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
+            for (int j = 0; j < JW; j += 4) {
               if (j0 + j < C::COUT) {
                 const float4 bb = *reinterpret_cast<const float4*>(sB3 + j0 + j);
                 const float4 sc = *reinterpret_cast<const float4*>(sB3 + C::COUT_P + j0 + j);

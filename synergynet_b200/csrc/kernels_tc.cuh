@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pointwise_kernel(const TcPoi
   __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_acc;
   __shared__ uint32_t tmem_base_s;
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the pointer in the shared address space (no integer round trip): a generic pointer here
+  // turns every tile access into LD.E/ST.E instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int m0 = blockIdx.x * 128;
   const int n0 = blockIdx.y * p.nr;

@@ -367,13 +367,13 @@ void pack_fused(std::vector<uint8_t>& img, const float* w1, int K, const float* 
   }
 }
 
-// Worker warps of the fused kernel: 12 by default (3 per SM sub-partition); SYN_FUSED_WARPS=8|12|16
+// Worker warps of the fused kernel: 12 by default (3 per SM sub-partition); SYN_FUSED_WARPS=8|12
 // selects another instantiation for tuning runs.
 inline int fused_worker_warps() {
   static const int v = [] {
     const char* e = getenv("SYN_FUSED_WARPS");
     const int n = e ? atoi(e) : 12;
-    return (n == 8 || n == 12 || n == 16) ? n : 12;
+    return (n == 8 || n == 12) ? n : 12;
   }();
   return v;
 }
@@ -398,7 +398,6 @@ int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, 
   int rc;
   switch (fused_worker_warps()) {
     case 8: rc = launch_fused_nww<C, 8>(h, a, grid, st); break;
-    case 16: rc = launch_fused_nww<C, 16>(h, a, grid, st); break;
     default: rc = launch_fused_nww<C, 12>(h, a, grid, st); break;
   }
   if (rc != SYN_OK) return rc;
