@@ -116,6 +116,15 @@ int syn_forward_landmarks(syn_handle_t* h, const float* x_dev, int batch, float*
 int syn_forward_landmarks_host(syn_handle_t* h, const float* x_host, int batch,
                                float* params62_host, float* lmk_host);
 
+/* ---- uint8 crops: the reference normalises on the host,
+ * `(img - 127.5) / 128` (synergy3DMM.py:192, benchmark.py:116 Normalize(mean=127.5, std=128)); these
+ * entry points take the raw uint8 (B,3,120,120) planar crops and apply the same fp32 arithmetic on the
+ * device (bit-identical values, 4x fewer bytes over PCIe / HBM). */
+int syn_forward_landmarks_u8(syn_handle_t* h, const uint8_t* x_u8_dev, int batch, float* params62_dev,
+                             float* lmk_dev, void* stream);
+int syn_forward_landmarks_host_u8(syn_handle_t* h, const uint8_t* x_u8_host, int batch,
+                                  float* params62_host, float* lmk_host);
+
 /* ---- introspection ---------------------------------------------------------------------------*/
 /* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
 int64_t syn_launch_count(const syn_handle_t* h);

@@ -48,6 +48,13 @@ def main():
                           'faces_per_s': B / ms * 1e3, 'roofline': {'bound': 'hbm', 'achieved': nbytes / ms / 1e6,
                           'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': nbytes / ms / 1e6 / peaks['hbm'],
                           'what': '638,580 B written per face x 1024 / CUDA-event time; ' + peaks['source']}}))
+    elif what == 'h2d':
+        for mb in (44, 177):
+            n = mb * 1000 * 1000 // 4
+            src = torch.empty(n, dtype=torch.float32).pin_memory()
+            dst = torch.empty(n, dtype=torch.float32, device='cuda')
+            ms = time_cuda(lambda: dst.copy_(src, non_blocking=True), iters=10, warmup=3)
+            print(json.dumps({'h2d_pinned_MB': mb, 'ms': ms, 'GBps': n * 4 / ms / 1e6}))
     elif what == 'sparse':
         params = model.forward_test(synthetic.make_inputs(B, 0).cuda())
         ms = time_cuda(lambda: eng.reconstruct(params, dense=False))

@@ -51,6 +51,8 @@ SIGNATURES = {
     'syn_reconstruct': (_I, [_P, _F, _I, _I, _I, _I, _F, _P]),
     'syn_forward_landmarks': (_I, [_P, _F, _I, _F, _F, _P]),
     'syn_forward_landmarks_host': (_I, [_P, _F, _I, _F, _F]),
+    'syn_forward_landmarks_u8': (_I, [_P, _F, _I, _F, _F, _P]),
+    'syn_forward_landmarks_host_u8': (_I, [_P, _F, _I, _F, _F]),
     'syn_launch_count': (_L, [_P]),
     'syn_poll_error': (_I, [_P, C.POINTER(C.c_int)]),
     'syn_debug_forward_until': (_I, [_P, _F, _I, _I, _F, _P]),

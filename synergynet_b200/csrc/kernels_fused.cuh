@@ -87,6 +87,7 @@ struct FusedCfg {
 
 struct FusedArgs {
   const float* x;        // NHWC (B,W,W,CIN) -- or NCHW (B,3,120,120) for the stem variant
+  const uint8_t* x_u8;   // stem variant only: raw uint8 crop, normalised (v-127.5)/128 while staging; else null
   const uint8_t* wimg;   // packed weight image (FusedCfg::W_BYTES)
   float* y;              // NHWC (B,WO,WO,COUT)
   int batch;
@@ -146,30 +147,18 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     uint32_t n_d1 = 0, n_g2 = 0, g = 0;                   // completed-phase counters; g = chunk counter
     asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // Geometry of a tile + "prep": stage / convert its input into the GEMM1 A operand and publish it.
+    // prep(next tile) is issued BEFORE the current tile's EPI2, so the issuer can run GEMM1(next, 0) --
+    // and the global-load latency of the conversion is hidden -- while the workers drain D2.
+    auto prep = [&](int tile) {
       const int fg = tile / C::STRIPS, sp = tile - fg * C::STRIPS;
       const int f0 = fg * C::FACES;
       const int nfaces = min(C::FACES, p.batch - f0);
-      const int oy0 = sp * C::RO;
-      const int iy0 = oy0 * C::STRIDE - 1;
+      const int iy0 = sp * C::RO * C::STRIDE - 1;
       const int rf = max(iy0, 0), rl = min(iy0 + C::RWIN - 1, C::W - 1);
-      const int ppf = (rl - rf + 1) * C::W;               // valid input pixels per face
+      const int ppf = (rl - rf + 1) * C::W;
       const int M1 = nfaces * ppf;
       const int mt1 = (M1 + 127) >> 7;
-      const int M2 = nfaces * C::M2F;
-      const int mt2 = (M2 + 127) >> 7;
-
-      // ---- strip mode: window rows outside the image must read as zero (may hold a previous tile) --
-      if constexpr (C::STRIPS > 1) {
-        if (iy0 < 0)
-          for (int i = tid; i < C::HS_COLS * C::HS_STRIDE / 4; i += NWT)
-            reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (iy0 + C::RWIN - 1 > C::W - 1)
-          for (int i = tid; i < C::HS_COLS * C::HS_STRIDE / 4; i += NWT)
-            reinterpret_cast<float4*>(sH + (size_t)(C::RWIN - 1) * C::HS_COLS * C::HS_STRIDE)[i] =
-                make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-
       // ---- stem: stage the crop rows this strip needs (coalesced), zero outside the image ----------
       if constexpr (C::STEM) {
         const int iy_first = 2 * rf - 1, nin = 2 * (rl - rf + 1) + 1;
@@ -177,8 +166,16 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           const int c4 = i % 31, r = (i / 31) % nin, ci = i / (31 * nin);
           const int iy = iy_first + r;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);                // c4 == 0: the columns left of the crop
-          if (c4 > 0 && iy >= 0 && iy < kImg)
-            v = *reinterpret_cast<const float4*>(p.x + ((size_t)(f0 * 3 + ci) * kImg + iy) * kImg + (c4 - 1) * 4);
+          if (c4 > 0 && iy >= 0 && iy < kImg) {
+            const size_t off = ((size_t)(f0 * 3 + ci) * kImg + iy) * kImg + (c4 - 1) * 4;
+            if (p.x_u8 != nullptr) {
+              const uchar4 u = *reinterpret_cast<const uchar4*>(p.x_u8 + off);
+              v = make_float4(((float)u.x - 127.5f) / 128.0f, ((float)u.y - 127.5f) / 128.0f,
+                              ((float)u.z - 127.5f) / 128.0f, ((float)u.w - 127.5f) / 128.0f);
+            } else {
+              v = *reinterpret_cast<const float4*>(p.x + off);
+            }
+          }
           *reinterpret_cast<float4*>(sIn + (ci * C::IN_ROWS + r) * C::IN_STRIDE + c4 * 4) = v;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");
@@ -233,6 +230,22 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&bar_x));
 
+    };
+    if ((int)blockIdx.x < ntiles) prep(blockIdx.x);
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int fg = tile / C::STRIPS, sp = tile - fg * C::STRIPS;
+      const int f0 = fg * C::FACES;
+      const int nfaces = min(C::FACES, p.batch - f0);
+      const int oy0 = sp * C::RO;
+      const int iy0 = oy0 * C::STRIDE - 1;
+      const int rf = max(iy0, 0), rl = min(iy0 + C::RWIN - 1, C::W - 1);
+      const int ppf = (rl - rf + 1) * C::W;               // valid input pixels per face
+      const int M1 = nfaces * ppf;
+      const int mt1 = (M1 + 127) >> 7;
+      const int M2 = nfaces * C::M2F;
+      const int mt2 = (M2 + 127) >> 7;
+
       for (int c = 0; c < C::NCHUNK; ++c, ++g) {
         const int slot = C::WSTREAM ? (int)(g & 1) : c;
         if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (g >> 1) & 1, p.err);
@@ -242,6 +255,18 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         ++n_d1;
         tc_fence_after_sync();
         asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");     // every worker is done reading Hs (DW c-1)
+        if (c == 0) {
+        // ---- strip mode: window rows outside the image must read as zero (may hold a previous tile) --
+        if constexpr (C::STRIPS > 1) {
+          if (iy0 < 0)
+            for (int i = tid; i < C::HS_COLS * C::HS_STRIDE / 4; i += NWT)
+              reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (iy0 + C::RWIN - 1 > C::W - 1)
+            for (int i = tid; i < C::HS_COLS * C::HS_STRIDE / 4; i += NWT)
+              reinterpret_cast<float4*>(sH + (size_t)(C::RWIN - 1) * C::HS_COLS * C::HS_STRIDE)[i] =
+                  make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        }
         {
           constexpr int JW = (C::NC % 32 == 0) ? 32 : 16;      // columns per TMEM load
           constexpr int JC = C::NC / JW;
@@ -336,6 +361,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         mbar_arrive(smem_u32(&bar_a2));
       }
 
+      if (tile + (int)gridDim.x < ntiles) prep(tile + gridDim.x);   // Xs is free: every GEMM1 of this tile is done
       // ---- EPI2: s3*D2 + b3 (+ skip) -> global NHWC --------------------------------------------------
       mbar_wait(smem_u32(&bar_g2), n_g2 & 1, p.err);
       ++n_g2;

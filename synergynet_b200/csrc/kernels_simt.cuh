@@ -13,6 +13,18 @@
 namespace syn {
 
 // -------------------------------------------------------------------------------------------------
+// uint8 crop -> fp32, `(img - 127.5) / 128` (synergy3DMM.py:192); used by the engines whose stem reads fp32.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out,
+                                                           size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const uchar4 u = reinterpret_cast<const uchar4*>(in)[i];
+  reinterpret_cast<float4*>(out)[i] = make_float4(((float)u.x - 127.5f) / 128.0f, ((float)u.y - 127.5f) / 128.0f,
+                                                   ((float)u.z - 127.5f) / 128.0f, ((float)u.w - 127.5f) / 128.0f);
+}
+
+// -------------------------------------------------------------------------------------------------
 // Stem: (B,3,120,120) NCHW -> (B,60,60,32) NHWC, 3x3 stride 2 pad 1, +bias, ReLU6.
 // One CTA per output row (b, oy); 256 threads = 64 pixel slots x 4 channel groups of 8.
 // Weights packed [27][32] with tap index (ci*3+ky)*3+kx.

@@ -12,6 +12,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_tail.cuh"
 
 using namespace syn;
 
@@ -63,6 +64,13 @@ struct syn_handle {
   // fused stem+block1 and blocks 2..7 (kernels_fused.cuh): one weight image per fused launch
   uint8_t* d_fused = nullptr;
   size_t fused_off[18] = {};                   // index = features[] index of the block (1..17)
+  uint8_t* d_tail_w = nullptr;                 // kernels_tail.cuh weight image (10 x 160 KB)
+  float* d_tail_osc = nullptr;                 // 1280 epilogue scales
+  float* d_pool_tmp = nullptr;                 // (ws_batch, 1280) pooled features
+  float* d_x_f32 = nullptr;                    // (ws_batch,3,120,120) normalised crops for engines 0/1 fed with uint8
+  int x_f32_batch = 0;
+  uint8_t* d_stage_u8[2] = {nullptr, nullptr};
+  int stage_u8_chunk = 0;
 
   // activation workspace (NHWC fp32), grown on demand
   int ws_batch = 0;
@@ -102,8 +110,8 @@ int ensure_workspace(syn_handle* h, int batch) {
   if (batch <= h->ws_batch) return SYN_OK;
   SYN_CUDA(cudaDeviceSynchronize());
   cudaFree(h->buf_io[0]); cudaFree(h->buf_io[1]); cudaFree(h->buf_hid); cudaFree(h->buf_dw);
-  cudaFree(h->d_params_tmp);
-  h->buf_io[0] = h->buf_io[1] = h->buf_hid = h->buf_dw = h->d_params_tmp = nullptr;
+  cudaFree(h->d_params_tmp); cudaFree(h->d_pool_tmp);
+  h->buf_io[0] = h->buf_io[1] = h->buf_hid = h->buf_dw = h->d_params_tmp = h->d_pool_tmp = nullptr;
   h->ws_batch = 0;
   const size_t b = (size_t)batch;
   SYN_CUDA(cudaMalloc(&h->buf_io[0], b * kIoPerFace * sizeof(float)));
@@ -111,6 +119,7 @@ int ensure_workspace(syn_handle* h, int batch) {
   SYN_CUDA(cudaMalloc(&h->buf_hid, b * kHidPerFace * sizeof(float)));
   SYN_CUDA(cudaMalloc(&h->buf_dw, b * kDwPerFace * sizeof(float)));
   SYN_CUDA(cudaMalloc(&h->d_params_tmp, b * kNumParams * sizeof(float)));
+  SYN_CUDA(cudaMalloc(&h->d_pool_tmp, b * kLastCh * sizeof(float)));
   h->ws_batch = batch;
   return SYN_OK;
 }
@@ -166,15 +175,33 @@ int launch_depthwise(syn_handle* h, const float* x, int layer, float* y, int bat
 }
 
 template <class C>
-int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, cudaStream_t st);
+int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, cudaStream_t st,
+                 const uint8_t* x_u8 = nullptr);
 
 // Runs the backbone.  When stop_layer >= 0 the activation of that conv is copied to dbg_out and
 // the function returns early.  Otherwise params (B,62) [and pool (B,1280)] are produced.
 int run_backbone(syn_handle* h, const float* x, int batch, float* params, float* pool,
-                 int stop_layer, float* dbg_out, cudaStream_t st) {
+                 int stop_layer, float* dbg_out, cudaStream_t st, const uint8_t* x_u8 = nullptr) {
   const Plan& P = plan();
   int rc = ensure_workspace(h, batch);
   if (rc != SYN_OK) return rc;
+  if (x_u8 != nullptr && h->engine != SYN_ENGINE_TC_FUSED) {
+    // engines whose stem reads fp32: normalise into a scratch buffer first
+    if (batch > h->x_f32_batch) {
+      SYN_CUDA(cudaDeviceSynchronize());
+      cudaFree(h->d_x_f32);
+      h->d_x_f32 = nullptr;
+      h->x_f32_batch = 0;
+      SYN_CUDA(cudaMalloc(&h->d_x_f32, (size_t)batch * 3 * kImg * kImg * sizeof(float)));
+      h->x_f32_batch = batch;
+    }
+    const size_t n4 = (size_t)batch * 3 * kImg * kImg / 4;
+    normalize_u8_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x_u8, h->d_x_f32, n4);
+    SYN_LAUNCH_CHECK("normalize_u8_kernel");
+    h->launches++;
+    x = h->d_x_f32;
+    x_u8 = nullptr;
+  }
 
   auto dbg = [&](int layer, const float* buf) -> int {
     const ConvDesc& c = P.conv[layer];
@@ -193,7 +220,7 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
     for (int b = 1; b <= 17; ++b) {
       float* out = h->buf_io[cur ^ 1];
       switch (b) {
-        case 1: rc = launch_fused<FusedStemB1>(h, in, b, out, batch, st); break;
+        case 1: rc = launch_fused<FusedStemB1>(h, in, b, out, batch, st, x_u8); break;
         case 2: rc = launch_fused<FusedB2>(h, in, b, out, batch, st); break;
         case 3: rc = launch_fused<FusedB3>(h, in, b, out, batch, st); break;
         case 4: rc = launch_fused<FusedB4>(h, in, b, out, batch, st); break;
@@ -211,7 +238,22 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
       in = h->buf_io[cur];
       if (stop_layer == 3 * b - 1) return dbg(3 * b - 1, h->buf_io[cur]);
     }
-    li = 51;
+    if (stop_layer == 51)
+      return fail(SYN_ERR_UNSUPPORTED, "conv 51 is fused with the average pool and never materialised");
+    {
+      float* pooled = pool ? pool : h->d_pool_tmp;
+      TailArgs t;
+      t.x = h->buf_io[cur]; t.wimg = h->d_tail_w; t.bias = h->dconv[51].bias; t.oscale = h->d_tail_osc;
+      t.pooled = pooled; t.batch = batch; t.err = h->d_err;
+      const int ntiles = (batch + kTailFaces - 1) / kTailFaces;
+      t.ctas_per_slice = std::max(1, std::min(ntiles, h->sm_count / 10));
+      tail_conv_pool_kernel<<<10 * t.ctas_per_slice, kTailThreads, kTailSmem, st>>>(t);
+      SYN_LAUNCH_CHECK("tail_conv_pool_kernel");
+      heads_kernel<<<(batch + 7) / 8, 256, 0, st>>>(pooled, h->d_head_w, h->d_head_b, params, batch);
+      SYN_LAUNCH_CHECK("heads_kernel");
+      h->launches += 2;
+      return SYN_OK;
+    }
   } else {
   stem_conv3x3s2_kernel<<<batch * 60, kStemThreads, 0, st>>>(x, h->dconv[0].w, h->dconv[0].bias,
                                                             h->buf_io[cur], batch);
@@ -390,8 +432,9 @@ int launch_fused_nww(syn_handle* h, const FusedArgs& a, int grid, cudaStream_t s
 }
 
 template <class C>
-int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, cudaStream_t st) {
+int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, cudaStream_t st, const uint8_t* x_u8) {
   FusedArgs a;
+  a.x_u8 = x_u8;
   a.x = x; a.wimg = h->d_fused + h->fused_off[block]; a.y = y; a.batch = batch; a.err = h->d_err;
   const int ntiles = (batch + C::FACES - 1) / C::FACES * C::STRIPS;
   const int grid = std::min(ntiles, h->sm_count);
@@ -479,7 +522,8 @@ void syn_destroy(syn_handle_t* h) {
   cudaFree(h->d_weights); cudaFree(h->d_head_w); cudaFree(h->d_head_b); cudaFree(h->d_mean);
   cudaFree(h->d_std); cudaFree(h->d_sparse); cudaFree(h->d_dense); cudaFree(h->d_tcw); cudaFree(h->d_err); cudaFree(h->d_fused); cudaFree(h->d_tc_oscale);
   cudaFree(h->buf_io[0]); cudaFree(h->buf_io[1]); cudaFree(h->buf_hid); cudaFree(h->buf_dw);
-  cudaFree(h->d_params_tmp);
+  cudaFree(h->d_params_tmp); cudaFree(h->d_pool_tmp); cudaFree(h->d_tail_w); cudaFree(h->d_tail_osc); cudaFree(h->d_x_f32);
+  cudaFree(h->d_stage_u8[0]); cudaFree(h->d_stage_u8[1]);
   cudaFree(h->d_stage_x[0]); cudaFree(h->d_stage_x[1]); cudaFree(h->d_stage_lmk); cudaFree(h->d_stage_par);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -654,6 +698,31 @@ int syn_commit(syn_handle_t* h) {
     blk(7, FusedB7{}); blk(8, FusedB8{}); blk(9, FusedB8{}); blk(10, FusedB8{}); blk(11, FusedB11{});
     blk(12, FusedB12{}); blk(13, FusedB12{}); blk(14, FusedB14{}); blk(15, FusedB15{}); blk(16, FusedB15{});
     blk(17, FusedB17{});
+    {   // tail: features[18] weights as the A operand of the transposed GEMM (kernels_tail.cuh)
+      const float* w = W(51);                       // [K=320][N=1280]
+      std::vector<uint8_t> timg((size_t)10 * kTailWBytes, 0);
+      std::vector<float> tosc(kTailN);
+      for (int n = 0; n < kTailN; ++n) {
+        const float sc = channel_scale(w + n, (size_t)kTailN, kTailK);
+        tosc[n] = 1.0f / (kActScaleHost * sc);
+        const int slice = n / 128, r = n % 128;
+        for (int k = 0; k < kTailK; ++k) {
+          const int kc = k / kTailKC, kl = k % kTailKC;
+          const size_t off = (size_t)slice * kTailWBytes + (size_t)kc * 2 * kTailPlane + (size_t)(r / 8) * 128 +
+                             (size_t)(kl / 8) * 2048 + (r % 8) * 16 + (kl % 8) * 2;
+          uint16_t hi, lo;
+          split_f16_host(w[(size_t)k * kTailN + n] * sc, hi, lo);
+          *reinterpret_cast<uint16_t*>(timg.data() + off) = hi;
+          *reinterpret_cast<uint16_t*>(timg.data() + off + kTailPlane) = lo;
+        }
+      }
+      if (h->d_tail_w) { cudaFree(h->d_tail_w); h->d_tail_w = nullptr; }
+      SYN_CUDA(cudaMalloc(&h->d_tail_w, timg.size()));
+      SYN_CUDA(cudaMemcpy(h->d_tail_w, timg.data(), timg.size(), cudaMemcpyHostToDevice));
+      int rc_t = upload(&h->d_tail_osc, tosc);
+      if (rc_t != SYN_OK) return rc_t;
+      SYN_CUDA(cudaFuncSetAttribute(tail_conv_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem));
+    }
     if (h->d_fused) { cudaFree(h->d_fused); h->d_fused = nullptr; }
     SYN_CUDA(cudaMalloc(&h->d_fused, all.size()));
     SYN_CUDA(cudaMemcpy(h->d_fused, all.data(), all.size(), cudaMemcpyHostToDevice));
@@ -717,27 +786,70 @@ int syn_forward_landmarks(syn_handle_t* h, const float* x, int batch, float* par
   return run_reconstruct(h, p, batch, 0, 1, 1, lmk, (cudaStream_t)stream);
 }
 
+static int forward_landmarks_host_impl(syn_handle_t* h, const void* x_host, int is_u8, int batch,
+                                       float* params_host, float* lmk_host);
+
 int syn_forward_landmarks_host(syn_handle_t* h, const float* x_host, int batch, float* params_host,
                                float* lmk_host) {
   SYN_CHECK_READY(h, "syn_forward_landmarks_host");
   if (x_host == nullptr || lmk_host == nullptr || batch <= 0)
     return fail(SYN_ERR_INVALID, "syn_forward_landmarks_host: bad argument");
-  if (h->n_pts <= 0) return fail(SYN_ERR_STATE, "syn_forward_landmarks_host: sparse basis not set");
+  return forward_landmarks_host_impl(h, x_host, 0, batch, params_host, lmk_host);
+}
+
+int syn_forward_landmarks_u8(syn_handle_t* h, const uint8_t* x_u8, int batch, float* params, float* lmk, void* stream) {
+  SYN_CHECK_READY(h, "syn_forward_landmarks_u8");
+  if (x_u8 == nullptr || lmk == nullptr || batch <= 0) return fail(SYN_ERR_INVALID, "syn_forward_landmarks_u8: bad argument");
+  DeviceGuard g(h->device);
+  int rc = ensure_workspace(h, batch);
+  if (rc != SYN_OK) return rc;
+  float* p = params ? params : h->d_params_tmp;
+  rc = run_backbone(h, nullptr, batch, p, nullptr, -1, nullptr, (cudaStream_t)stream, x_u8);
+  if (rc != SYN_OK) return rc;
+  return run_reconstruct(h, p, batch, 0, 1, 1, lmk, (cudaStream_t)stream);
+}
+
+// Shared host pipeline: chunks of <= 256 faces, H2D on s_copy overlapped with compute on s_compute.
+static int forward_landmarks_host_impl(syn_handle_t* h, const void* x_host, int is_u8, int batch,
+                                       float* params_host, float* lmk_host) {
+  if (h->n_pts <= 0) return fail(SYN_ERR_STATE, "forward_landmarks_host: sparse basis not set");
   DeviceGuard g(h->device);
   const int chunk = std::min(batch, 256);
   const size_t x_face = (size_t)3 * kImg * kImg;
+  const size_t elt = is_u8 ? 1 : sizeof(float);
   const size_t lmk_face = (size_t)3 * h->n_pts;
-  if (chunk > h->stage_chunk || batch > h->stage_batch) {
+  if (batch > h->stage_batch) {
     SYN_CUDA(cudaDeviceSynchronize());
-    cudaFree(h->d_stage_x[0]); cudaFree(h->d_stage_x[1]); cudaFree(h->d_stage_lmk); cudaFree(h->d_stage_par);
-    h->d_stage_x[0] = h->d_stage_x[1] = h->d_stage_lmk = h->d_stage_par = nullptr;
-    h->stage_chunk = h->stage_batch = 0;
-    SYN_CUDA(cudaMalloc(&h->d_stage_x[0], chunk * x_face * sizeof(float)));
-    SYN_CUDA(cudaMalloc(&h->d_stage_x[1], chunk * x_face * sizeof(float)));
+    cudaFree(h->d_stage_lmk); cudaFree(h->d_stage_par);
+    h->d_stage_lmk = h->d_stage_par = nullptr;
+    h->stage_batch = 0;
     SYN_CUDA(cudaMalloc(&h->d_stage_lmk, batch * lmk_face * sizeof(float)));
     SYN_CUDA(cudaMalloc(&h->d_stage_par, (size_t)batch * kNumParams * sizeof(float)));
-    h->stage_chunk = chunk;
     h->stage_batch = batch;
+  }
+  void* stage[2];
+  if (is_u8) {
+    if (chunk > h->stage_u8_chunk) {
+      SYN_CUDA(cudaDeviceSynchronize());
+      cudaFree(h->d_stage_u8[0]); cudaFree(h->d_stage_u8[1]);
+      h->d_stage_u8[0] = h->d_stage_u8[1] = nullptr;
+      h->stage_u8_chunk = 0;
+      SYN_CUDA(cudaMalloc(&h->d_stage_u8[0], chunk * x_face));
+      SYN_CUDA(cudaMalloc(&h->d_stage_u8[1], chunk * x_face));
+      h->stage_u8_chunk = chunk;
+    }
+    stage[0] = h->d_stage_u8[0]; stage[1] = h->d_stage_u8[1];
+  } else {
+    if (chunk > h->stage_chunk) {
+      SYN_CUDA(cudaDeviceSynchronize());
+      cudaFree(h->d_stage_x[0]); cudaFree(h->d_stage_x[1]);
+      h->d_stage_x[0] = h->d_stage_x[1] = nullptr;
+      h->stage_chunk = 0;
+      SYN_CUDA(cudaMalloc(&h->d_stage_x[0], chunk * x_face * sizeof(float)));
+      SYN_CUDA(cudaMalloc(&h->d_stage_x[1], chunk * x_face * sizeof(float)));
+      h->stage_chunk = chunk;
+    }
+    stage[0] = h->d_stage_x[0]; stage[1] = h->d_stage_x[1];
   }
   int rc = ensure_workspace(h, chunk);
   if (rc != SYN_OK) return rc;
@@ -745,25 +857,32 @@ int syn_forward_landmarks_host(syn_handle_t* h, const float* x_host, int batch, 
   for (int b0 = 0; b0 < batch; b0 += chunk, slot ^= 1, ++issued) {
     const int nb = std::min(chunk, batch - b0);
     if (issued >= 2) SYN_CUDA(cudaStreamWaitEvent(h->s_copy, h->ev_done[slot], 0));
-    SYN_CUDA(cudaMemcpyAsync(h->d_stage_x[slot], x_host + (size_t)b0 * x_face, nb * x_face * sizeof(float),
+    SYN_CUDA(cudaMemcpyAsync(stage[slot], (const uint8_t*)x_host + (size_t)b0 * x_face * elt, nb * x_face * elt,
                              cudaMemcpyHostToDevice, h->s_copy));
     SYN_CUDA(cudaEventRecord(h->ev_h2d[slot], h->s_copy));
     SYN_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_h2d[slot], 0));
     float* par = h->d_stage_par + (size_t)b0 * kNumParams;
-    rc = run_backbone(h, h->d_stage_x[slot], nb, par, nullptr, -1, nullptr, h->s_compute);
+    rc = run_backbone(h, is_u8 ? nullptr : (const float*)stage[slot], nb, par, nullptr, -1, nullptr, h->s_compute,
+                      is_u8 ? (const uint8_t*)stage[slot] : nullptr);
     if (rc != SYN_OK) return rc;
     SYN_CUDA(cudaEventRecord(h->ev_done[slot], h->s_compute));
     rc = run_reconstruct(h, par, nb, 0, 1, 1, h->d_stage_lmk + (size_t)b0 * lmk_face, h->s_compute);
     if (rc != SYN_OK) return rc;
   }
-  SYN_CUDA(cudaMemcpyAsync(lmk_host, h->d_stage_lmk, batch * lmk_face * sizeof(float),
-                           cudaMemcpyDeviceToHost, h->s_compute));
+  SYN_CUDA(cudaMemcpyAsync(lmk_host, h->d_stage_lmk, batch * lmk_face * sizeof(float), cudaMemcpyDeviceToHost, h->s_compute));
   if (params_host != nullptr)
     SYN_CUDA(cudaMemcpyAsync(params_host, h->d_stage_par, (size_t)batch * kNumParams * sizeof(float),
                              cudaMemcpyDeviceToHost, h->s_compute));
   SYN_CUDA(cudaStreamSynchronize(h->s_compute));
   SYN_CUDA(cudaStreamSynchronize(h->s_copy));
   return SYN_OK;
+}
+
+int syn_forward_landmarks_host_u8(syn_handle_t* h, const uint8_t* x_host, int batch, float* params_host, float* lmk_host) {
+  SYN_CHECK_READY(h, "syn_forward_landmarks_host_u8");
+  if (x_host == nullptr || lmk_host == nullptr || batch <= 0)
+    return fail(SYN_ERR_INVALID, "syn_forward_landmarks_host_u8: bad argument");
+  return forward_landmarks_host_impl(h, x_host, 1, batch, params_host, lmk_host);
 }
 
 int64_t syn_launch_count(const syn_handle_t* h) { return h ? h->launches : -1; }

@@ -132,6 +132,9 @@ class Engine:
         return out
 
     def forward_landmarks(self, x: torch.Tensor, want_params: bool = False):
+        """x: fp32 normalised crops, or raw uint8 crops (normalised on the device)."""
+        if x.dtype == torch.uint8:
+            return self._forward_landmarks_u8(x, want_params)
         x = self._check_x(x)
         b = x.shape[0]
         lmk = torch.empty((b, 3, self.n_pts), device=self.device, dtype=torch.float32)
@@ -141,15 +144,28 @@ class Engine:
                                                    lmk.data_ptr(), self._stream()))
         return (lmk, params) if want_params else lmk
 
+    def _forward_landmarks_u8(self, x: torch.Tensor, want_params: bool):
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 120, 120) or x.device != self.device:
+            raise RuntimeError(f'expected uint8 (B,3,120,120) on {self.device}, got {tuple(x.shape)} on {x.device}')
+        x = x.contiguous()
+        b = x.shape[0]
+        lmk = torch.empty((b, 3, self.n_pts), device=self.device, dtype=torch.float32)
+        params = torch.empty((b, N_PARAMS), device=self.device, dtype=torch.float32) if want_params else None
+        _lib.check(self._lib.syn_forward_landmarks_u8(self._h, x.data_ptr(), b,
+                                                      params.data_ptr() if want_params else None,
+                                                      lmk.data_ptr(), self._stream()))
+        return (lmk, params) if want_params else lmk
+
     def forward_landmarks_host(self, x_host: torch.Tensor, lmk_host: Optional[torch.Tensor] = None,
                                params_host: Optional[torch.Tensor] = None) -> torch.Tensor:
         """End-to-end call on HOST tensors (pinned recommended): H2D, forward, landmarks, D2H."""
-        if x_host.is_cuda or x_host.dtype != torch.float32 or not x_host.is_contiguous():
-            raise RuntimeError('x_host must be a contiguous fp32 CPU tensor')
+        if x_host.is_cuda or x_host.dtype not in (torch.float32, torch.uint8) or not x_host.is_contiguous():
+            raise RuntimeError('x_host must be a contiguous fp32 (normalised) or uint8 (raw) CPU tensor')
         b = x_host.shape[0]
         if lmk_host is None:
             lmk_host = torch.empty((b, 3, self.n_pts), dtype=torch.float32)
-        _lib.check(self._lib.syn_forward_landmarks_host(
+        fn = self._lib.syn_forward_landmarks_host_u8 if x_host.dtype == torch.uint8 else self._lib.syn_forward_landmarks_host
+        _lib.check(fn(
             self._h, x_host.data_ptr(), b, params_host.data_ptr() if params_host is not None else None,
             lmk_host.data_ptr()))
         return lmk_host

@@ -213,6 +213,19 @@ def test_host_buffer_call_matches_device_call(model, gold, engine_kind):
     assert rp.max_rel_err(par.numpy(), model.forward_test(x.cuda()).cpu().numpy()) < 1e-6
 
 
+def test_uint8_crops_match_host_normalised_floats(model, engine_kind):
+    """`(img - 127.5) / 128` applied on the device (uint8 entry points) is the same fp32 arithmetic as
+    the reference's host-side normalisation (synergy3DMM.py:192): outputs must be bit-identical."""
+    u8 = synthetic.make_structured_crops_u8(70, seed=9)
+    eng = model._engine(torch.device('cuda', 0))
+    want = eng.forward_landmarks(synthetic.normalize_crops(u8).cuda())
+    got = eng.forward_landmarks(u8.cuda())
+    assert torch.equal(got, want)
+    host = eng.forward_landmarks_host(u8.pin_memory())
+    assert torch.equal(host, want.cpu())
+    assert eng.poll_error() == 0
+
+
 def test_get_all_outputs_matches_reference_api(model, gold, engine_kind):
     rects = [list(r) for r in gold['scene_rects']]
     pts, verts, poses = model.get_all_outputs(gold['scene'].copy(), rects=rects)
