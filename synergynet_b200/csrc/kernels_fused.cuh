@@ -304,8 +304,9 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           constexpr int NKG = C::NC / 8;
           const int RG = (M2 + 7) >> 3;
           const int q = tid >> 3, l8 = tid & 7;
+          constexpr bool WREG = (NWW <= 12);   // depthwise taps cached in registers (else read from smem per tap)
           int cur_kg = -1;
-          float wr[9][8], bd[8];
+          float wr[WREG ? 9 : 1][8], bd[8];
           // (kg, row-group) pairs, kg-major, dealt round-robin to the quarter-warps without a division
           int kg = 0, rg = q;
           while (rg >= RG) { rg -= RG; ++kg; }
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
             if (kg != cur_kg) {
               cur_kg = kg;
 #pragma unroll
-              for (int tp = 0; tp < 9; ++tp) {
+              for (int tp = 0; tp < (WREG ? 9 : 0); ++tp) {
                 const float4 a = *reinterpret_cast<const float4*>(dwc + tp * C::NC + kg * 8);
                 const float4 e = *reinterpret_cast<const float4*>(dwc + tp * C::NC + kg * 8 + 4);
                 wr[tp][0] = a.x; wr[tp][1] = a.y; wr[tp][2] = a.z; wr[tp][3] = a.w;
@@ -339,7 +340,15 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                   const float* hp = h0 + (dy * C::HS_COLS + dx) * C::HS_STRIDE;
                   const float4 a = *reinterpret_cast<const float4*>(hp);
                   const float4 e = *reinterpret_cast<const float4*>(hp + 4);
-                  const float* w = wr[dy * 3 + dx];
+                  float w[8];
+                  if constexpr (WREG) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[j] = wr[dy * 3 + dx][j];
+                  } else {
+                    const float4 wa = *reinterpret_cast<const float4*>(dwc + (dy * 3 + dx) * C::NC + kg * 8);
+                    const float4 we = *reinterpret_cast<const float4*>(dwc + (dy * 3 + dx) * C::NC + kg * 8 + 4);
+                    w[0] = wa.x; w[1] = wa.y; w[2] = wa.z; w[3] = wa.w; w[4] = we.x; w[5] = we.y; w[6] = we.z; w[7] = we.w;
+                  }
                   acc[0] = fmaf(a.x, w[0], acc[0]); acc[1] = fmaf(a.y, w[1], acc[1]);
                   acc[2] = fmaf(a.z, w[2], acc[2]); acc[3] = fmaf(a.w, w[3], acc[3]);
                   acc[4] = fmaf(e.x, w[4], acc[4]); acc[5] = fmaf(e.y, w[5], acc[5]);

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_conv_pool_kernel(const T
 
 // -------------------------------------------------------------------------------------------------
 // Heads: params[b, :62] = pooled[b, :1280] . Wh^T + bh   (classifier_ori | shape | exp concatenated).
-// One CTA per 8 faces so that each 1280-float weight row is read once per 8 faces.
+// One CTA per 8 faces x half of the 62 outputs (grid.y = 2): each weight row is read once per 8 faces.
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ pooled, const float* __restrict__ Wh,
                                                     const float* __restrict__ bh, float* __restrict__ params,
@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ po
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
-  for (int j = warp; j < kNumParams; j += 8) {
+  const int j_lo = blockIdx.y * (kNumParams / 2), j_hi = j_lo + kNumParams / 2;
+  for (int j = j_lo + warp; j < j_hi; j += 8) {
     const float* wr = Wh + (size_t)j * kLastCh;
     float acc[F];
 #pragma unroll

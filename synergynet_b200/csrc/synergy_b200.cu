@@ -249,7 +249,7 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
       t.ctas_per_slice = std::max(1, std::min(ntiles, h->sm_count / 10));
       tail_conv_pool_kernel<<<10 * t.ctas_per_slice, kTailThreads, kTailSmem, st>>>(t);
       SYN_LAUNCH_CHECK("tail_conv_pool_kernel");
-      heads_kernel<<<(batch + 7) / 8, 256, 0, st>>>(pooled, h->d_head_w, h->d_head_b, params, batch);
+      heads_kernel<<<dim3((batch + 7) / 8, 2), 256, 0, st>>>(pooled, h->d_head_w, h->d_head_b, params, batch);
       SYN_LAUNCH_CHECK("heads_kernel");
       h->launches += 2;
       return SYN_OK;
@@ -409,13 +409,13 @@ void pack_fused(std::vector<uint8_t>& img, const float* w1, int K, const float* 
   }
 }
 
-// Worker warps of the fused kernel: 12 by default (3 per SM sub-partition); SYN_FUSED_WARPS=8|12
+// Worker warps of the fused kernel: 12 by default (3 per SM sub-partition); SYN_FUSED_WARPS=8|12|16
 // selects another instantiation for tuning runs.
 inline int fused_worker_warps() {
   static const int v = [] {
     const char* e = getenv("SYN_FUSED_WARPS");
     const int n = e ? atoi(e) : 12;
-    return (n == 8 || n == 12) ? n : 12;
+    return (n == 8 || n == 12 || n == 16) ? n : 12;
   }();
   return v;
 }
@@ -441,6 +441,7 @@ int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, 
   int rc;
   switch (fused_worker_warps()) {
     case 8: rc = launch_fused_nww<C, 8>(h, a, grid, st); break;
+    case 16: rc = launch_fused_nww<C, 16>(h, a, grid, st); break;
     default: rc = launch_fused_nww<C, 12>(h, a, grid, st); break;
   }
   if (rc != SYN_OK) return rc;
