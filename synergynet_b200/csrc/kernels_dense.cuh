@@ -1,0 +1,230 @@
+// 3DMM reconstruction on tcgen05 (reference model_building.py:106-139, reconstruct_vertex_62):
+//   S[b, 3v+c] = u[3v+c] + sum_k W[3v+c, k] * alpha[b, k]      (k = 40 shape + 10 expression)
+//   V[b, i, v] = sum_c P[b, i, c] * S[b, 3v+c] + t[b, i];   V[b, 1, v] = 121 - V[b, 1, v]
+// The basis product is a GEMM with M = vertices, N = faces, K = 50 (padded to 64); running it once per
+// coordinate plane (x, y, z) puts the three coordinates of vertex v in the SAME TMEM lane, so the
+// 3x3 pose transform is per-thread arithmetic and the (B,3,N) output rows are written with fully
+// coalesced 128-byte warp stores.  The kernel is HBM-write bound: 638,580 B per face (dense).
+//
+//   dense_alpha_kernel     params (B,62) -> de-whitened pose (B,12) fp32 + alpha as fp16 hi/lo B tiles
+//   dense_recon_tc_kernel  persistent; item = (128-vertex tile, 64-face tile), vertex-tile major; the
+//                          96 KB basis tile (3 planes x hi/lo) stays in smem while the CTA walks over
+//                          the face tiles
+//     warp 8 lane 0: loader + MMA issuer (3 planes x 3 passes x 4 K-steps, N = 64), 2 TMEM buffers
+//     warps 0-7:     epilogue (lane = vertex; two warps per lane quarter split the 64 faces)
+// Split-16x3 precision scheme of kernels_tc.cuh; basis rows are pre-scaled per vertex row and alpha
+// per coefficient (both powers of two, folded back exactly in the epilogue / the basis image).
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace syn {
+
+constexpr int kDnK = 64;                                  // padded coefficient count
+constexpr int kDnFaces = 64;                              // faces per tile (MMA N)
+constexpr int kDnAPlane = 128 * kDnK * 2;                 // 16 KB: one plane (hi or lo) of one coordinate
+constexpr int kDnATile = 3 * 2 * kDnAPlane;               // 96 KB per 128-vertex tile: [x|y|z][hi|lo]
+constexpr int kDnBPlane = kDnFaces * kDnK * 2;            // 8 KB
+constexpr int kDnBTile = 2 * kDnBPlane;                   // 16 KB per face tile: [hi|lo]
+constexpr int kDnPoseTile = kDnFaces * 12 * 4;            // 3 KB
+constexpr int kDnBSlot = kDnBTile + kDnPoseTile;
+constexpr int kDnMetaTile = 128 * 6 * 4;                  // per vertex tile: u[3][128], 1/rowscale[3][128]
+constexpr int kDnSmem = kDnATile + 2 * kDnMetaTile + 2 * kDnBSlot + 1024;
+constexpr int kDnThreads = 9 * 32;
+
+// ---- pre-pass -----------------------------------------------------------------------------------------
+// alpha image: per face tile [hi plane 64 faces x 64 k][lo plane], canonical K-major (SBO 128, LBO 1024);
+// pose: (tiles*64, 12) fp32 rows [R|t] (model_building.py:27-29), zero rows past the batch.
+__global__ void __launch_bounds__(64) dense_alpha_kernel(const float* __restrict__ params, const float* __restrict__ mean,
+                                                         const float* __restrict__ stdv, const float* __restrict__ ascale,
+                                                         uint8_t* __restrict__ aimg, float* __restrict__ pose, int batch,
+                                                         int whitening) {
+  const int f = threadIdx.x, tile = blockIdx.x;
+  const int b = tile * kDnFaces + f;
+  float pr[kNumParams];
+#pragma unroll
+  for (int j = 0; j < kNumParams; ++j) {
+    float v = 0.f;
+    if (b < batch) {
+      v = params[(size_t)b * kNumParams + j];
+      if (whitening) v = v * stdv[j] + mean[j];          // model_building.py:117
+    }
+    pr[j] = v;
+  }
+#pragma unroll
+  for (int j = 0; j < 12; ++j) pose[(size_t)(tile * kDnFaces + f) * 12 + j] = pr[j];
+  uint8_t* hi = aimg + (size_t)tile * kDnBTile + (f >> 3) * 128 + (f & 7) * 16;
+#pragma unroll
+  for (int kg = 0; kg < kDnK / 8; ++kg) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k0 = kg * 8 + 2 * j, k1 = k0 + 1;
+      const float a0 = (k0 < kNumAlpha) ? pr[12 + k0] * ascale[k0] : 0.f;
+      const float a1 = (k1 < kNumAlpha) ? pr[12 + k1] * ascale[k1] : 0.f;
+      tc::split2_f16(a0, a1, h[j], l[j]);
+    }
+    *reinterpret_cast<uint4*>(hi + kg * 1024) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(hi + kDnBPlane + kg * 1024) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+struct DenseArgs {
+  const uint8_t* basis_img;   // [vertex tiles][x|y|z][hi|lo][128 x 64] canonical (SBO 128, LBO 2048)
+  const float* meta;          // [vertex tiles][6][128]: u_x,u_y,u_z, 1/rowscale_x,_y,_z
+  const uint8_t* alpha_img;   // from dense_alpha_kernel
+  const float* pose;
+  float* out;                 // (B,3,nver)
+  int batch, nver, n_vtiles, n_ftiles, transform;
+  int* err;
+};
+
+// Synchronisation (item i uses B slot / TMEM buffer i & 1; `use` = i >> 1 is its per-slot sequence number):
+//   bar_a       basis tile + meta landed (one phase per vertex tile)       loader -> issuer, epilogue
+//   bar_bfull   alpha + pose tile landed                                    loader -> issuer, epilogue
+//   bar_dfull   MMAs of the item complete                                   tcgen05.commit -> epilogue
+//   bar_dfree   epilogue done with the item (TMEM buffer, B slot, and -- at a vertex-tile change --
+//               every epilogue thread has passed its bar_a wait)            256 arrivals -> issuer
+__global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const DenseArgs p) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_a, bar_bfull[2], bar_dfull[2], bar_dfree[2];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  float* sMeta = reinterpret_cast<float*>(smem + kDnATile);          // 2 slots (vertex-tile load parity)
+  uint8_t* sB = smem + kDnATile + 2 * kDnMetaTile;                   // 2 slots of alpha + pose
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int items = p.n_vtiles * p.n_ftiles;
+  const int per = (items + gridDim.x - 1) / gridDim.x;
+  const int it0 = min((int)blockIdx.x * per, items), it1 = min(it0 + per, items);
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_a), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_bfull[i]), 1);
+      mbar_init(smem_u32(&bar_dfull[i]), 1);
+      mbar_init(smem_u32(&bar_dfree[i]), 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc<512>(smem_u32(&tmem_base_s));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < 8) {
+    // ------------------------------ epilogue ------------------------------------------------------
+    const int lane_v = tid & 127, half = tid >> 7;                 // vertex row of the tile, face half
+    int cur_vt = -1;
+    uint32_t n_a = 0;
+    float ux = 0.f, uy = 0.f, uz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+    for (int it = it0, i = 0; it < it1; ++it, ++i) {
+      const int vt = it / p.n_ftiles, ft = it - vt * p.n_ftiles;
+      const int s = i & 1;
+      const uint32_t use_par = (uint32_t)(i >> 1) & 1;
+      if (vt != cur_vt) {                                          // new basis tile: fetch its meta rows
+        cur_vt = vt;
+        mbar_wait(smem_u32(&bar_a), n_a & 1, p.err);
+        const float* m = sMeta + (n_a & 1) * (kDnMetaTile / 4);
+        ++n_a;
+        ux = m[0 * 128 + lane_v]; uy = m[1 * 128 + lane_v]; uz = m[2 * 128 + lane_v];
+        ox = m[3 * 128 + lane_v]; oy = m[4 * 128 + lane_v]; oz = m[5 * 128 + lane_v];
+      }
+      mbar_wait(smem_u32(&bar_bfull[s]), use_par, p.err);          // pose tile visible to this thread
+      mbar_wait(smem_u32(&bar_dfull[s]), use_par, p.err);
+      tc_fence_after_sync();
+      const float* pose = reinterpret_cast<const float*>(sB + s * kDnBSlot + kDnBTile) + half * 32 * 12;
+      const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + s * 192 + half * 32;
+      float sx[32], sy[32], sz[32];
+      tmem_ld32(trow, sx);
+      tmem_ld32(trow + 64, sy);
+      tmem_ld32(trow + 128, sz);
+      const int v = vt * 128 + lane_v;
+      const int b0 = ft * kDnFaces + half * 32;
+      if (v < p.nver) {
+#pragma unroll
+        for (int f = 0; f < 32; ++f) {
+          if (b0 + f < p.batch) {
+            const float4 r0 = *reinterpret_cast<const float4*>(pose + f * 12);
+            const float4 r1 = *reinterpret_cast<const float4*>(pose + f * 12 + 4);
+            const float4 r2 = *reinterpret_cast<const float4*>(pose + f * 12 + 8);
+            const float X = fmaf(sx[f], ox, ux), Y = fmaf(sy[f], oy, uy), Z = fmaf(sz[f], oz, uz);
+            float vx = fmaf(r0.x, X, fmaf(r0.y, Y, r0.z * Z)) + r0.w;
+            float vy = fmaf(r1.x, X, fmaf(r1.y, Y, r1.z * Z)) + r1.w;
+            float vz = fmaf(r2.x, X, fmaf(r2.y, Y, r2.z * Z)) + r2.w;
+            if (p.transform) vy = (float)(kImg + 1) - vy;          // model_building.py:129,137
+            float* o = p.out + (size_t)(b0 + f) * 3 * p.nver + v;
+            o[0] = vx; o[p.nver] = vy; o[2 * (size_t)p.nver] = vz;
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(smem_u32(&bar_dfree[s]));
+    }
+  } else if (tid == 8 * 32) {
+    // ------------------------------ loader + MMA issuer -------------------------------------------
+    const uint32_t idesc = make_idesc_f16(128, kDnFaces);
+    auto load_b = [&](int it, int s) {
+      const int ft = it % p.n_ftiles;
+      uint8_t* dst = sB + s * kDnBSlot;
+      mbar_expect_tx(smem_u32(&bar_bfull[s]), kDnBSlot);
+      bulk_g2s(smem_u32(dst), p.alpha_img + (size_t)ft * kDnBTile, kDnBTile, smem_u32(&bar_bfull[s]));
+      bulk_g2s(smem_u32(dst + kDnBTile), p.pose + (size_t)ft * kDnFaces * 12, kDnPoseTile, smem_u32(&bar_bfull[s]));
+    };
+    auto dfree_wait = [&](int j) {                                   // epilogue finished item j (>= 0)
+      mbar_wait(smem_u32(&bar_dfree[j & 1]), (uint32_t)(j >> 1) & 1, p.err);
+    };
+    int cur_vt = -1;
+    uint32_t n_a = 0;
+    if (it0 < it1) load_b(it0, 0);
+    for (int it = it0, i = 0; it < it1; ++it, ++i) {
+      const int vt = it / p.n_ftiles;
+      const int s = i & 1;
+      if (vt != cur_vt) {
+        // the basis tile in smem is overwritten: every MMA of the previous tile must be complete and every
+        // epilogue thread past its bar_a wait, both implied by the epilogue having finished item i-1
+        if (i >= 1) dfree_wait(i - 1);
+        cur_vt = vt;
+        mbar_expect_tx(smem_u32(&bar_a), kDnATile + kDnMetaTile);
+        bulk_g2s(smem_u32(sA), p.basis_img + (size_t)vt * kDnATile, kDnATile, smem_u32(&bar_a));
+        bulk_g2s(smem_u32(sMeta + (n_a & 1) * (kDnMetaTile / 4)), p.meta + (size_t)vt * 6 * 128, kDnMetaTile,
+                 smem_u32(&bar_a));
+        mbar_wait(smem_u32(&bar_a), n_a & 1, p.err);
+        ++n_a;
+      }
+      mbar_wait(smem_u32(&bar_bfull[s]), (uint32_t)(i >> 1) & 1, p.err);
+      if (i >= 2) dfree_wait(i - 2);                               // TMEM buffer s drained
+      tc_fence_after_sync();
+      const uint32_t b_hi = smem_u32(sB + s * kDnBSlot);
+#pragma unroll
+      for (int plane = 0; plane < 3; ++plane) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a_base = smem_u32(sA) + (plane * 2 + (pass == 2 ? 1 : 0)) * kDnAPlane;   // W: hi,hi,lo
+          const uint32_t b_base = b_hi + (pass == 1 ? kDnBPlane : 0);                             // alpha: hi,lo,hi
+#pragma unroll
+          for (int ks = 0; ks < kDnK / 16; ++ks)
+            umma_f16(tmem + s * 192 + plane * 64, make_smem_desc(a_base + ks * 4096, 2048, 128),
+                     make_smem_desc(b_base + ks * 2048, 1024, 128), idesc, (pass > 0 || ks > 0) ? 1u : 0u);
+        }
+      }
+      umma_commit(smem_u32(&bar_dfull[s]));
+      // prefetch the next item's alpha/pose into the other slot, last used by item i-1 (MMA + epilogue)
+      if (it + 1 < it1) {
+        if (i >= 1) dfree_wait(i - 1);
+        load_b(it + 1, s ^ 1);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+}  // namespace syn

@@ -13,6 +13,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_tail.cuh"
+#include "kernels_dense.cuh"
 
 using namespace syn;
 
@@ -34,7 +35,7 @@ struct DevConv {
 struct syn_handle {
   int device = 0;
   int sm_count = 0;
-  int engine = SYN_ENGINE_SIMT_FP32;
+  int engine = SYN_ENGINE_TC_FUSED;            // default: fused tcgen05 engine; 0/1 remain for cross-checks
   bool committed = false;
   int64_t launches = 0;
 
@@ -67,6 +68,13 @@ struct syn_handle {
   uint8_t* d_tail_w = nullptr;                 // kernels_tail.cuh weight image (10 x 160 KB)
   float* d_tail_osc = nullptr;                 // 1280 epilogue scales
   float* d_pool_tmp = nullptr;                 // (ws_batch, 1280) pooled features
+  // tensor-core reconstruction (kernels_dense.cuh): fp16 hi/lo basis images + per-row meta
+  uint8_t *d_sp_img = nullptr, *d_dn_img = nullptr;
+  float *d_sp_meta = nullptr, *d_dn_meta = nullptr, *d_ascale = nullptr;
+  int sp_vtiles = 0, dn_vtiles = 0;
+  uint8_t* d_alpha_img = nullptr;              // recon workspace: alpha tiles + pose rows
+  float* d_pose = nullptr;
+  int recon_ftiles = 0;
   float* d_x_f32 = nullptr;                    // (ws_batch,3,120,120) normalised crops for engines 0/1 fed with uint8
   int x_f32_batch = 0;
   uint8_t* d_stage_u8[2] = {nullptr, nullptr};
@@ -297,16 +305,45 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
   return SYN_OK;
 }
 
+int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense, int whitening, int transform,
+                       float* out, cudaStream_t st) {
+  const int n_ftiles = (batch + kDnFaces - 1) / kDnFaces;
+  if (n_ftiles > h->recon_ftiles) {
+    SYN_CUDA(cudaDeviceSynchronize());
+    cudaFree(h->d_alpha_img); cudaFree(h->d_pose);
+    h->d_alpha_img = nullptr; h->d_pose = nullptr; h->recon_ftiles = 0;
+    SYN_CUDA(cudaMalloc(&h->d_alpha_img, (size_t)n_ftiles * kDnBTile));
+    SYN_CUDA(cudaMalloc(&h->d_pose, (size_t)n_ftiles * kDnPoseTile));
+    h->recon_ftiles = n_ftiles;
+  }
+  dense_alpha_kernel<<<n_ftiles, 64, 0, st>>>(params, h->d_mean, h->d_std, h->d_ascale, h->d_alpha_img, h->d_pose, batch,
+                                             whitening);
+  SYN_LAUNCH_CHECK("dense_alpha_kernel");
+  DenseArgs a;
+  a.basis_img = dense ? h->d_dn_img : h->d_sp_img;
+  a.meta = dense ? h->d_dn_meta : h->d_sp_meta;
+  a.alpha_img = h->d_alpha_img; a.pose = h->d_pose; a.out = out; a.batch = batch;
+  a.nver = dense ? (int)h->n_vert : h->n_pts;
+  a.n_vtiles = dense ? h->dn_vtiles : h->sp_vtiles;
+  a.n_ftiles = n_ftiles; a.transform = transform; a.err = h->d_err;
+  const int items = a.n_vtiles * a.n_ftiles;
+  dense_recon_tc_kernel<<<std::min(items, h->sm_count), kDnThreads, kDnSmem, st>>>(a);
+  SYN_LAUNCH_CHECK("dense_recon_tc_kernel");
+  h->launches += 2;
+  return SYN_OK;
+}
+
 int run_reconstruct(syn_handle* h, const float* params, int batch, int dense, int whitening,
                     int transform, float* out, cudaStream_t st) {
+  if (dense && h->d_dense == nullptr) return fail(SYN_ERR_STATE, "dense basis not set (syn_set_basis_dense)");
+  if (!dense && h->d_sparse == nullptr) return fail(SYN_ERR_STATE, "sparse basis not set (syn_set_basis_sparse)");
+  if (h->engine != SYN_ENGINE_SIMT_FP32) return run_reconstruct_tc(h, params, batch, dense, whitening, transform, out, st);
   if (dense) {
-    if (h->d_dense == nullptr) return fail(SYN_ERR_STATE, "dense basis not set (syn_set_basis_dense)");
     constexpr int F = 16;
     dim3 grid((unsigned)(h->dn_pad / 128), (batch + F - 1) / F);
     reconstruct_kernel<F><<<grid, 128, 0, st>>>(h->d_dense, params, h->d_mean, h->d_std, out, batch,
                                                (int)h->n_vert, (int)h->dn_pad, whitening, transform);
   } else {
-    if (h->d_sparse == nullptr) return fail(SYN_ERR_STATE, "sparse basis not set (syn_set_basis_sparse)");
     constexpr int F = 8;
     dim3 grid(h->sp_pad / 128, (batch + F - 1) / F);
     reconstruct_kernel<F><<<grid, 128, 0, st>>>(h->d_sparse, params, h->d_mean, h->d_std, out, batch,
@@ -409,13 +446,13 @@ void pack_fused(std::vector<uint8_t>& img, const float* w1, int K, const float* 
   }
 }
 
-// Worker warps of the fused kernel: 12 by default (3 per SM sub-partition); SYN_FUSED_WARPS=8|12|16
+// Worker warps of the fused kernel: 16 by default (4 per SM sub-partition, measured best); SYN_FUSED_WARPS=8|12|16
 // selects another instantiation for tuning runs.
 inline int fused_worker_warps() {
   static const int v = [] {
     const char* e = getenv("SYN_FUSED_WARPS");
-    const int n = e ? atoi(e) : 12;
-    return (n == 8 || n == 12 || n == 16) ? n : 12;
+    const int n = e ? atoi(e) : 16;
+    return (n == 8 || n == 12 || n == 16) ? n : 16;
   }();
   return v;
 }
@@ -441,12 +478,50 @@ int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, 
   int rc;
   switch (fused_worker_warps()) {
     case 8: rc = launch_fused_nww<C, 8>(h, a, grid, st); break;
-    case 16: rc = launch_fused_nww<C, 16>(h, a, grid, st); break;
-    default: rc = launch_fused_nww<C, 12>(h, a, grid, st); break;
+    case 12: rc = launch_fused_nww<C, 12>(h, a, grid, st); break;
+    default: rc = launch_fused_nww<C, 16>(h, a, grid, st); break;
   }
   if (rc != SYN_OK) return rc;
   SYN_LAUNCH_CHECK("fused_mbconv_kernel");
   h->launches++;
+  return SYN_OK;
+}
+
+// ---- tensor-core reconstruction images (kernels_dense.cuh) from the planar [51][3][pad] basis --------------
+// alpha coefficient k is pre-multiplied by ascale[k] on the device, so column k of the basis is divided by it
+// here (exact: powers of two); each (vertex, coordinate) row is then scaled into [256, 512).
+void pack_recon_tc(std::vector<uint8_t>& img, std::vector<float>& meta, const std::vector<float>& planar, int64_t n,
+                   int64_t pad, const float* ascale) {
+  const int64_t vtiles = pad / 128;
+  img.assign((size_t)vtiles * kDnATile, 0);
+  meta.assign((size_t)vtiles * 6 * 128, 0.f);
+  float row[kNumAlpha];
+  for (int64_t vt = 0; vt < vtiles; ++vt)
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 128; ++r) {
+        const int64_t v = vt * 128 + r;
+        float* m = meta.data() + (size_t)vt * 6 * 128;
+        m[(3 + c) * 128 + r] = 1.f;
+        if (v >= n) continue;
+        m[c * 128 + r] = planar[(size_t)(0 * 3 + c) * pad + v];
+        for (int k = 0; k < kNumAlpha; ++k) row[k] = planar[(size_t)((1 + k) * 3 + c) * pad + v] / ascale[k];
+        const float rs = channel_scale(row, 1, kNumAlpha);
+        m[(3 + c) * 128 + r] = 1.0f / rs;
+        uint8_t* base = img.data() + (size_t)vt * kDnATile + (size_t)(c * 2) * kDnAPlane;
+        for (int k = 0; k < kNumAlpha; ++k) {
+          const size_t off = (size_t)(r / 8) * 128 + (size_t)(k / 8) * 2048 + (r % 8) * 16 + (k % 8) * 2;
+          uint16_t hi, lo;
+          split_f16_host(row[k] * rs, hi, lo);
+          *reinterpret_cast<uint16_t*>(base + off) = hi;
+          *reinterpret_cast<uint16_t*>(base + kDnAPlane + off) = lo;
+        }
+      }
+}
+
+int upload_bytes(uint8_t** dptr, const std::vector<uint8_t>& src) {
+  if (*dptr != nullptr) { cudaFree(*dptr); *dptr = nullptr; }
+  SYN_CUDA(cudaMalloc(dptr, src.size()));
+  SYN_CUDA(cudaMemcpy(*dptr, src.data(), src.size(), cudaMemcpyHostToDevice));
   return SYN_OK;
 }
 
@@ -524,6 +599,8 @@ void syn_destroy(syn_handle_t* h) {
   cudaFree(h->d_std); cudaFree(h->d_sparse); cudaFree(h->d_dense); cudaFree(h->d_tcw); cudaFree(h->d_err); cudaFree(h->d_fused); cudaFree(h->d_tc_oscale);
   cudaFree(h->buf_io[0]); cudaFree(h->buf_io[1]); cudaFree(h->buf_hid); cudaFree(h->buf_dw);
   cudaFree(h->d_params_tmp); cudaFree(h->d_pool_tmp); cudaFree(h->d_tail_w); cudaFree(h->d_tail_osc); cudaFree(h->d_x_f32);
+  cudaFree(h->d_sp_img); cudaFree(h->d_dn_img); cudaFree(h->d_sp_meta); cudaFree(h->d_dn_meta); cudaFree(h->d_ascale);
+  cudaFree(h->d_alpha_img); cudaFree(h->d_pose);
   cudaFree(h->d_stage_u8[0]); cudaFree(h->d_stage_u8[1]);
   cudaFree(h->d_stage_x[0]); cudaFree(h->d_stage_x[1]); cudaFree(h->d_stage_lmk); cudaFree(h->d_stage_par);
   for (int i = 0; i < 2; ++i) {
@@ -733,14 +810,35 @@ int syn_commit(syn_handle_t* h) {
   if ((rc = upload(&h->d_head_b, h->h_head_b)) != SYN_OK) return rc;
   if ((rc = upload(&h->d_mean, h->h_mean)) != SYN_OK) return rc;
   if ((rc = upload(&h->d_std, h->h_std)) != SYN_OK) return rc;
-  if (h->sparse_dirty) {
-    if ((rc = upload(&h->d_sparse, h->h_sparse)) != SYN_OK) return rc;
-    h->sparse_dirty = false;
+  // alpha scales of the tensor-core reconstruction: |alpha_k * ascale_k| <= 2^10 within 8 sigma of the mean
+  std::vector<float> ascale(kNumAlpha);
+  for (int k = 0; k < kNumAlpha; ++k) {
+    const float bound = fabsf(h->h_mean[12 + k]) + 8.f * fabsf(h->h_std[12 + k]);
+    int ex = 0;
+    if (bound > 0.f && std::isfinite(bound)) frexpf(bound, &ex);
+    ascale[k] = ldexpf(1.f, 10 - ex);
   }
-  if (h->dense_dirty) {
-    if ((rc = upload(&h->d_dense, h->h_dense)) != SYN_OK) return rc;
-    h->dense_dirty = false;
-    std::vector<float>().swap(h->h_dense);       // 32 MB host copy no longer needed
+  if ((rc = upload(&h->d_ascale, ascale)) != SYN_OK) return rc;
+  {
+    std::vector<uint8_t> img;
+    std::vector<float> meta;
+    if (!h->h_sparse.empty()) {
+      if (h->sparse_dirty && (rc = upload(&h->d_sparse, h->h_sparse)) != SYN_OK) return rc;
+      h->sparse_dirty = false;
+      pack_recon_tc(img, meta, h->h_sparse, h->n_pts, h->sp_pad, ascale.data());
+      h->sp_vtiles = h->sp_pad / 128;
+      if ((rc = upload_bytes(&h->d_sp_img, img)) != SYN_OK) return rc;
+      if ((rc = upload(&h->d_sp_meta, meta)) != SYN_OK) return rc;
+    }
+    if (!h->h_dense.empty()) {                 // kept on the host (32 MB): whitening changes re-scale the image
+      if (h->dense_dirty && (rc = upload(&h->d_dense, h->h_dense)) != SYN_OK) return rc;
+      h->dense_dirty = false;
+      pack_recon_tc(img, meta, h->h_dense, h->n_vert, h->dn_pad, ascale.data());
+      h->dn_vtiles = (int)(h->dn_pad / 128);
+      if ((rc = upload_bytes(&h->d_dn_img, img)) != SYN_OK) return rc;
+      if ((rc = upload(&h->d_dn_meta, meta)) != SYN_OK) return rc;
+    }
+    SYN_CUDA(cudaFuncSetAttribute(dense_recon_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDnSmem));
   }
   h->committed = true;
   return SYN_OK;

@@ -40,7 +40,7 @@ class _Runtime:
         self._engines: Dict[int, Engine] = {}
         self._sig: Dict[int, tuple] = {}
         self._lock = threading.Lock()
-        self.engine_kind = 0
+        self.engine_kind = None      # None: the library default (fused tcgen05 engine)
 
     @staticmethod
     def _signature(tensors) -> tuple:
@@ -69,7 +69,7 @@ class _Runtime:
                     z = torch.zeros(62)
                     eng.load_3dmm(z, z + 1, torch.zeros(3, 1), torch.zeros(3, 40), torch.zeros(3, 10))
                 eng.commit()
-                if self.engine_kind:
+                if self.engine_kind is not None:
                     eng.set_engine(self.engine_kind)
                 self._sig[idx] = sig
         return eng

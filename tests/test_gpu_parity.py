@@ -63,7 +63,7 @@ def engine_kind(request, model):
     if not _engine_available(model, request.param):
         pytest.skip('engine not in this build')
     yield request.param
-    model.set_engine(_lib.ENGINE_SIMT_FP32)
+    model.set_engine(_lib.ENGINE_TC_FUSED)
 
 
 def _x(gold):
