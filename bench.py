@@ -169,7 +169,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': 'faces/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args):
@@ -230,7 +230,7 @@ def run_b200(args):
 
     if args.profile:
         if rank == 0:
-            print(json.dumps({'profile_run': True, 'ms_per_step': ms / args.steps, 'gpu_launches': launches}))
+            emit({'profile_run': True, 'ms_per_step': ms / args.steps, 'gpu_launches': launches})
         return
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H timed) ----
@@ -249,6 +249,21 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+
+    # ---- same call fed with raw uint8 crops (normalised on the device; bit-identical outputs) --------
+    uh = [synthetic.make_crops_u8(B, seed=100 + 10 * rank + i).pin_memory() for i in range(2)]
+    for i in range(3):
+        eng.forward_landmarks_host(uh[i % 2], lh)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        eng.forward_landmarks_host(uh[i % 2], lh)
+    torch.cuda.synchronize(dev)
+    u8_s = time.perf_counter() - t0
+    t = torch.tensor([u8_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    u8_s = float(t.item())
 
     if rank == 0:
         faces = world * B * args.steps
@@ -271,6 +286,9 @@ def run_b200(args):
             'e2e': {'value': world * B * e2e_steps / e2e_s, 'unit': 'faces/s',
                     'h2d_bytes_per_step': B * X_BYTES_PER_FACE, 'd2h_bytes_per_step': B * LMK_BYTES_PER_FACE,
                     'steps': e2e_steps, 'call': 'syn_forward_landmarks_host (pinned fp32 crops in, landmarks out)'},
+            'e2e_u8': {'value': world * B * e2e_steps / u8_s, 'unit': 'faces/s', 'h2d_bytes_per_step': B * X_BYTES_PER_FACE // 4,
+                       'd2h_bytes_per_step': B * LMK_BYTES_PER_FACE, 'steps': e2e_steps,
+                       'call': 'syn_forward_landmarks_host_u8 (pinned uint8 crops in, (img-127.5)/128 on the device, landmarks out)'},
             'gpu_launches': launches,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
                          'frac': achieved / peaks['bf16_sustained'], 'traffic': None,
@@ -279,12 +297,31 @@ def run_b200(args):
             'cpu_baseline': cpu,
             'clocks': clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _protect_stdout():
+    """Third-party code (NCCL banner, torchrun children) may print to fd 1; the contract is ONE JSON
+    line on stdout.  Route fd 1 to stderr for the duration of the run and keep a private handle."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, 'w')
+
+
+_OUT = None
+
+
+def emit(line: dict) -> None:
+    _OUT.write(json.dumps(line) + '\n')
+    _OUT.flush()
+
+
 def main():
+    global _OUT
+    _OUT = _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=30)
