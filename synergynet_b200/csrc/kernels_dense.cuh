@@ -10,8 +10,8 @@
 //   dense_recon_tc_kernel  persistent; item = (128-vertex tile, 64-face tile), vertex-tile major; the
 //                          96 KB basis tile (3 planes x hi/lo) stays in smem while the CTA walks over
 //                          the face tiles
-//     warp 8 lane 0: loader + MMA issuer (3 planes x 3 passes x 4 K-steps, N = 64), 2 TMEM buffers
-//     warps 0-7:     epilogue (lane = vertex; two warps per lane quarter split the 64 faces)
+//     warp 16 lane 0: loader + MMA issuer (3 planes x 3 passes x 4 K-steps, N = 64), 2 TMEM buffers
+//     warps 0-15:     epilogue (lane = vertex; four warps per lane quarter split the 64 faces)
 // Split-16x3 precision scheme of kernels_tc.cuh; basis rows are pre-scaled per vertex row and alpha
 // per coefficient (both powers of two, folded back exactly in the epilogue / the basis image).
 #pragma once
@@ -30,7 +30,8 @@ constexpr int kDnPoseTile = kDnFaces * 12 * 4;            // 3 KB
 constexpr int kDnBSlot = kDnBTile + kDnPoseTile;
 constexpr int kDnMetaTile = 128 * 6 * 4;                  // per vertex tile: u[3][128], 1/rowscale[3][128]
 constexpr int kDnSmem = kDnATile + 2 * kDnMetaTile + 2 * kDnBSlot + 1024;
-constexpr int kDnThreads = 9 * 32;
+constexpr int kDnEpiWarps = 16;                          // 4 per TMEM lane quarter: 16 faces each
+constexpr int kDnThreads = (kDnEpiWarps + 1) * 32;
 
 // ---- pre-pass -----------------------------------------------------------------------------------------
 // alpha image: per face tile [hi plane 64 faces x 64 k][lo plane], canonical K-major (SBO 128, LBO 1024);
@@ -84,7 +85,7 @@ struct DenseArgs {
 //   bar_bfull   alpha + pose tile landed                                    loader -> issuer, epilogue
 //   bar_dfull   MMAs of the item complete                                   tcgen05.commit -> epilogue
 //   bar_dfree   epilogue done with the item (TMEM buffer, B slot, and -- at a vertex-tile change --
-//               every epilogue thread has passed its bar_a wait)            256 arrivals -> issuer
+//               every epilogue thread has passed its bar_a wait)            512 arrivals -> issuer
 __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const DenseArgs p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -105,19 +106,20 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar_bfull[i]), 1);
       mbar_init(smem_u32(&bar_dfull[i]), 1);
-      mbar_init(smem_u32(&bar_dfree[i]), 256);
+      mbar_init(smem_u32(&bar_dfree[i]), kDnEpiWarps * 32);
     }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc<512>(smem_u32(&tmem_base_s));
+  if (warp == kDnEpiWarps) tmem_alloc<512>(smem_u32(&tmem_base_s));
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp < 8) {
+  if (warp < kDnEpiWarps) {
     // ------------------------------ epilogue ------------------------------------------------------
-    const int lane_v = tid & 127, half = tid >> 7;                 // vertex row of the tile, face half
+    constexpr int FPT = kDnFaces / (kDnEpiWarps / 4);              // faces per thread (16)
+    const int lane_v = tid & 127, fq = tid >> 7;                   // vertex row of the tile, face group
     int cur_vt = -1;
     uint32_t n_a = 0;
     float ux = 0.f, uy = 0.f, uz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
@@ -136,17 +138,17 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
       mbar_wait(smem_u32(&bar_bfull[s]), use_par, p.err);          // pose tile visible to this thread
       mbar_wait(smem_u32(&bar_dfull[s]), use_par, p.err);
       tc_fence_after_sync();
-      const float* pose = reinterpret_cast<const float*>(sB + s * kDnBSlot + kDnBTile) + half * 32 * 12;
-      const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + s * 192 + half * 32;
-      float sx[32], sy[32], sz[32];
-      tmem_ld32(trow, sx);
-      tmem_ld32(trow + 64, sy);
-      tmem_ld32(trow + 128, sz);
+      const float* pose = reinterpret_cast<const float*>(sB + s * kDnBSlot + kDnBTile) + fq * FPT * 12;
+      const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + s * 192 + fq * FPT;
+      float sx[FPT], sy[FPT], sz[FPT];
+      tmem_ld16(trow, sx);
+      tmem_ld16(trow + 64, sy);
+      tmem_ld16(trow + 128, sz);
       const int v = vt * 128 + lane_v;
-      const int b0 = ft * kDnFaces + half * 32;
+      const int b0 = ft * kDnFaces + fq * FPT;
       if (v < p.nver) {
 #pragma unroll
-        for (int f = 0; f < 32; ++f) {
+        for (int f = 0; f < FPT; ++f) {
           if (b0 + f < p.batch) {
             const float4 r0 = *reinterpret_cast<const float4*>(pose + f * 12);
             const float4 r1 = *reinterpret_cast<const float4*>(pose + f * 12 + 4);
@@ -157,14 +159,14 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
             float vz = fmaf(r2.x, X, fmaf(r2.y, Y, r2.z * Z)) + r2.w;
             if (p.transform) vy = (float)(kImg + 1) - vy;          // model_building.py:129,137
             float* o = p.out + (size_t)(b0 + f) * 3 * p.nver + v;
-            o[0] = vx; o[p.nver] = vy; o[2 * (size_t)p.nver] = vz;
+            __stcs(o, vx); __stcs(o + p.nver, vy); __stcs(o + 2 * (size_t)p.nver, vz);   // write-once stream
           }
         }
       }
       tc_fence_before_sync();
       mbar_arrive(smem_u32(&bar_dfree[s]));
     }
-  } else if (tid == 8 * 32) {
+  } else if (tid == kDnEpiWarps * 32) {
     // ------------------------------ loader + MMA issuer -------------------------------------------
     const uint32_t idesc = make_idesc_f16(128, kDnFaces);
     auto load_b = [&](int it, int s) {
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kDnEpiWarps) {
     __syncwarp();
     tmem_dealloc<512>(tmem);
   }

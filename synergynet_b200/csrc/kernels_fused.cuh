@@ -7,8 +7,8 @@
 // Work item (tile) = RO output rows of one face (large maps) or FACES whole faces (8x8 / 4x4 maps).
 // Per tile, for each chunk of NC hidden channels:
 //   GEMM1  D1[t] (128 x NC, TMEM)  = Xs[t] (128 input pixels x CIN_P, fp16 hi/lo) * W1c^T   (tensor)
-//   EPI1   Hs[pixel][NC] (fp32, smem, zero halo) = relu6(s1 * D1 + b1)                      (CUDA)
-//   DW     A2[out pixel][NC] (fp16 hi/lo, smem)  = split(relu6(dw3x3(Hs) + bdw))            (CUDA)
+//   EPI1   Hs[pixel][NC] (fp32, smem, zero halo) = relu6(s1 * D1 + b1) / 6  (one FFMA.SAT)   (CUDA)
+//   DW     A2[out pixel][NC] (fp16 hi/lo, smem)  = split(relu6(dw3x3(6 Hs) + bdw))          (CUDA)
 //   GEMM2  D2[t] (128 x COUT_P, TMEM) += A2[t] * W3c^T                                      (tensor)
 // and finally EPI2: out = s3 * D2 + b3 (+ x).  GEMM1 of chunk c+1 and GEMM2 of chunk c run on the
 // tensor pipe while the 128 worker threads do EPI1/DW, so the CUDA-core work is the critical path.
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
   static_assert(NWW % 4 == 0 && NWW >= 4 && NWW <= 16, "worker warps");
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_wfull[2], bar_x, bar_d1, bar_epi1, bar_a2, bar_g2, bar_d2free;
+  __shared__ __align__(8) uint64_t bar_w, bar_wfull[2], bar_x, bar_d1, bar_epi1, bar_a2, bar_g2, bar_d2free, bar_in;
   __shared__ uint32_t tmem_base_s;
 
   // keep the pointer in the shared address space (no integer round trip): a generic pointer here
@@ -123,6 +123,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     mbar_init(smem_u32(&bar_a2), NWT);
     mbar_init(smem_u32(&bar_g2), 1);
     mbar_init(smem_u32(&bar_d2free), NWT);
+    mbar_init(smem_u32(&bar_in), 1);
     fence_mbar_init();
   }
   if (warp == NWW) tmem_alloc<C::TM_COLS>(smem_u32(&tmem_base_s));
@@ -143,8 +144,11 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     // zero the whole hidden window once: halo columns are never written afterwards
     for (int i = tid; i < C::HS_PIX * C::HS_STRIDE / 4; i += NWT)
       reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (C::STEM)                                 // left pad column (and everything else) starts as zero
+      for (int i = tid; i < 3 * C::IN_ROWS * C::IN_STRIDE / 4; i += NWT)
+        reinterpret_cast<float4*>(sIn)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     mbar_wait(smem_u32(&bar_w), 0, p.err);                // b3/s3 (and, if resident, all chunks) landed
-    uint32_t n_d1 = 0, n_g2 = 0, g = 0;                   // completed-phase counters; g = chunk counter
+    uint32_t n_d1 = 0, n_g2 = 0, g = 0, n_in = 0;                   // completed-phase counters; g = chunk counter
     asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");
 
     // Geometry of a tile + "prep": stage / convert its input into the GEMM1 A operand and publish it.
@@ -159,24 +163,31 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       const int ppf = (rl - rf + 1) * C::W;
       const int M1 = nfaces * ppf;
       const int mt1 = (M1 + 127) >> 7;
-      // ---- stem: stage the crop rows this strip needs (coalesced), zero outside the image ----------
+      // ---- stem: the crop rows this strip needs, zero outside the image ------------------------------
       if constexpr (C::STEM) {
         const int iy_first = 2 * rf - 1, nin = 2 * (rl - rf + 1) + 1;
-        for (int i = tid; i < 3 * nin * 31; i += NWT) {
-          const int c4 = i % 31, r = (i / 31) % nin, ci = i / (31 * nin);
-          const int iy = iy_first + r;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);                // c4 == 0: the columns left of the crop
-          if (c4 > 0 && iy >= 0 && iy < kImg) {
-            const size_t off = ((size_t)(f0 * 3 + ci) * kImg + iy) * kImg + (c4 - 1) * 4;
-            if (p.x_u8 != nullptr) {
-              const uchar4 u = *reinterpret_cast<const uchar4*>(p.x_u8 + off);
+        if (p.x_u8 != nullptr) {              // uint8 crops: threads load, normalise and stage
+          for (int i = tid; i < 3 * nin * 31; i += NWT) {
+            const int c4 = i % 31, r = (i / 31) % nin, ci = i / (31 * nin);
+            const int iy = iy_first + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);              // c4 == 0: the columns left of the crop
+            if (c4 > 0 && iy >= 0 && iy < kImg) {
+              const uchar4 u = *reinterpret_cast<const uchar4*>(p.x_u8 + ((size_t)(f0 * 3 + ci) * kImg + iy) * kImg + (c4 - 1) * 4);
               v = make_float4(((float)u.x - 127.5f) / 128.0f, ((float)u.y - 127.5f) / 128.0f,
                               ((float)u.z - 127.5f) / 128.0f, ((float)u.w - 127.5f) / 128.0f);
-            } else {
-              v = *reinterpret_cast<const float4*>(p.x + off);
             }
+            *reinterpret_cast<float4*>(sIn + (ci * C::IN_ROWS + r) * C::IN_STRIDE + c4 * 4) = v;
           }
-          *reinterpret_cast<float4*>(sIn + (ci * C::IN_ROWS + r) * C::IN_STRIDE + c4 * 4) = v;
+        } else {                              // fp32 crops: rows were bulk-copied by the issuer one tile ahead
+          mbar_wait(smem_u32(&bar_in), n_in & 1, p.err);
+          ++n_in;
+          for (int r = 0; r < nin; ++r) {     // rows outside the image are not copied: zero them (edge strips)
+            const int iy = iy_first + r;
+            if (iy < 0 || iy >= kImg)
+              for (int i = tid; i < 3 * 30; i += NWT)
+                *reinterpret_cast<float4*>(sIn + ((i / 30) * C::IN_ROWS + r) * C::IN_STRIDE + 4 + (i % 30) * 4) =
+                    make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");
       }
@@ -268,7 +279,9 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         }
         }
         {
-          constexpr int JW = (C::NC % 32 == 0) ? 32 : 16;      // columns per TMEM load
+          // columns per TMEM load: as wide as possible while every worker group still gets a (tile, chunk) pair
+          constexpr int JW = (C::NC % 32 == 0 && C::MT1 * (C::NC / 32) >= NWG) ? 32
+                             : (C::MT1 * (C::NC / 16) >= NWG) ? 16 : 8;
           constexpr int JC = C::NC / JW;
           for (int e = wg; e < mt1 * JC; e += NWG) {
             const int t = e / JC, j0 = (e - t * JC) * JW;
@@ -279,15 +292,15 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
             float* hrow = sH + (size_t)(f * C::HS_FACE + (rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE;
             float v[JW];
             const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * C::NC + j0;
-            if constexpr (JW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+            if constexpr (JW == 32) tmem_ld32(taddr, v); else if constexpr (JW == 16) tmem_ld16(taddr, v); else tmem_ld8(taddr, v);
             if (m < M1) {
 #pragma unroll
               for (int j = 0; j < JW; j += 4) {
                 const float4 bb = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0 + j);
                 const float4 sc = *reinterpret_cast<const float4*>(dwc + 11 * C::NC + j0 + j);
                 *reinterpret_cast<float4*>(hrow + j0 + j) =
-                    make_float4(relu6f(fmaf(v[j], sc.x, bb.x)), relu6f(fmaf(v[j + 1], sc.y, bb.y)),
-                                relu6f(fmaf(v[j + 2], sc.z, bb.z)), relu6f(fmaf(v[j + 3], sc.w, bb.w)));
+                    make_float4(__saturatef(fmaf(v[j], sc.x, bb.x)), __saturatef(fmaf(v[j + 1], sc.y, bb.y)),
+                                __saturatef(fmaf(v[j + 2], sc.z, bb.z)), __saturatef(fmaf(v[j + 3], sc.w, bb.w)));
               }
             }
           }
@@ -301,69 +314,88 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           ++n_g2;
         }
         {
+          // Item = (8 hidden channels, two vertically adjacent output rows, 8 lanes along x): the 3x3
+          // windows of the two rows share (S=1: 2 of 4, S=2: 1 of 5) input rows and all nine tap vectors,
+          // which cuts the shared-memory loads per output by ~40 % against one pixel per thread.
+          // Hidden values are stored as relu6(h)/6 in [0,1] and the bias row holds bdw/6, so the
+          // activation is a single saturate and the fp16 pre-scale becomes 6 * kActScale.
           constexpr int NKG = C::NC / 8;
-          const int RG = (M2 + 7) >> 3;
-          const int q = tid >> 3, l8 = tid & 7;
-          constexpr bool WREG = (NWW <= 12);   // depthwise taps cached in registers (else read from smem per tap)
-          int cur_kg = -1;
-          float wr[WREG ? 9 : 1][8], bd[8];
-          // (kg, row-group) pairs, kg-major, dealt round-robin to the quarter-warps without a division
-          int kg = 0, rg = q;
-          while (rg >= RG) { rg -= RG; ++kg; }
-          for (; kg < NKG;) {
-            if (kg != cur_kg) {
-              cur_kg = kg;
+          constexpr int GX = (C::WO >= 8) ? 8 : 4, GY = 8 / GX;            // quarter-warp footprint
+          constexpr int XG = (C::WO + GX - 1) / GX;                        // x groups per output row
+          constexpr int RP = (C::RO + 1) / 2, RPG = (RP + GY - 1) / GY;    // row pairs, groups of them
+          constexpr int PER_FACE = XG * RPG;
+          constexpr int NR = C::STRIDE + 3;                                // window rows of a row pair
+          const int per_kg = nfaces * PER_FACE;
+          const int l8 = tid & 7, lx = l8 % GX, ly = l8 / GX;
+          int kg = 0, it = tid >> 3;
+          while (it >= per_kg && kg < NKG) { it -= per_kg; ++kg; }
+          while (kg < NKG) {
+            const int f = it / PER_FACE, r2 = it - f * PER_FACE;
+            const int rpg = r2 / XG, xg = r2 - rpg * XG;
+            const int ox = xg * GX + lx, oy = 2 * (rpg * GY + ly);
+            if (ox < C::WO && oy < C::RO) {
+              const float* wbase = dwc + kg * 8;
+              const float* h0 = sH + (size_t)(f * C::HS_FACE + (oy * C::STRIDE) * C::HS_COLS + ox * C::STRIDE) * C::HS_STRIDE + kg * 8;
+              const bool two = (oy + 1 < C::RO);                           // second output row exists
+              float acc0[8], acc1[8];
+              {
+                const float4 a = *reinterpret_cast<const float4*>(wbase + 9 * C::NC);
+                const float4 e = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + 4);
+                acc0[0] = a.x; acc0[1] = a.y; acc0[2] = a.z; acc0[3] = a.w; acc0[4] = e.x; acc0[5] = e.y; acc0[6] = e.z; acc0[7] = e.w;
 #pragma unroll
-              for (int tp = 0; tp < (WREG ? 9 : 0); ++tp) {
-                const float4 a = *reinterpret_cast<const float4*>(dwc + tp * C::NC + kg * 8);
-                const float4 e = *reinterpret_cast<const float4*>(dwc + tp * C::NC + kg * 8 + 4);
-                wr[tp][0] = a.x; wr[tp][1] = a.y; wr[tp][2] = a.z; wr[tp][3] = a.w;
-                wr[tp][4] = e.x; wr[tp][5] = e.y; wr[tp][6] = e.z; wr[tp][7] = e.w;
+                for (int j = 0; j < 8; ++j) acc1[j] = acc0[j];
               }
-              const float4 a = *reinterpret_cast<const float4*>(dwc + 9 * C::NC + kg * 8);
-              const float4 e = *reinterpret_cast<const float4*>(dwc + 9 * C::NC + kg * 8 + 4);
-              bd[0] = a.x; bd[1] = a.y; bd[2] = a.z; bd[3] = a.w; bd[4] = e.x; bd[5] = e.y; bd[6] = e.z; bd[7] = e.w;
-            }
-            const int m2 = rg * 8 + l8;
-            if (m2 < M2) {
-              const int f = (C::FACES > 1) ? m2 / C::M2F : 0;
-              const int mr = m2 - f * C::M2F;
-              const int oyl = mr / C::WO, ox = mr - oyl * C::WO;
-              const float* h0 = sH + (size_t)(f * C::HS_FACE + (oyl * C::STRIDE) * C::HS_COLS + ox * C::STRIDE) * C::HS_STRIDE + kg * 8;
-              float acc[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[j] = bd[j];
+              for (int dx = 0; dx < 3; ++dx) {
+                float w[3][8];
 #pragma unroll
-              for (int dy = 0; dy < 3; ++dy)
+                for (int dy = 0; dy < 3; ++dy) {
+                  const float4 a = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC);
+                  const float4 e = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + 4);
+                  w[dy][0] = a.x; w[dy][1] = a.y; w[dy][2] = a.z; w[dy][3] = a.w;
+                  w[dy][4] = e.x; w[dy][5] = e.y; w[dy][6] = e.z; w[dy][7] = e.w;
+                }
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                  const float* hp = h0 + (dy * C::HS_COLS + dx) * C::HS_STRIDE;
+                for (int wr = 0; wr < NR; ++wr) {
+                  if (wr >= 3 && !two) continue;                           // rows only the (absent) second pixel needs
+                  const float* hp = h0 + (wr * C::HS_COLS + dx) * C::HS_STRIDE;
                   const float4 a = *reinterpret_cast<const float4*>(hp);
                   const float4 e = *reinterpret_cast<const float4*>(hp + 4);
-                  float w[8];
-                  if constexpr (WREG) {
+                  const float d[8] = {a.x, a.y, a.z, a.w, e.x, e.y, e.z, e.w};
+                  if (wr < 3) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) w[j] = wr[dy * 3 + dx][j];
-                  } else {
-                    const float4 wa = *reinterpret_cast<const float4*>(dwc + (dy * 3 + dx) * C::NC + kg * 8);
-                    const float4 we = *reinterpret_cast<const float4*>(dwc + (dy * 3 + dx) * C::NC + kg * 8 + 4);
-                    w[0] = wa.x; w[1] = wa.y; w[2] = wa.z; w[3] = wa.w; w[4] = we.x; w[5] = we.y; w[6] = we.z; w[7] = we.w;
+                    for (int j = 0; j < 8; ++j) acc0[j] = fmaf(d[j], w[wr][j], acc0[j]);
                   }
-                  acc[0] = fmaf(a.x, w[0], acc[0]); acc[1] = fmaf(a.y, w[1], acc[1]);
-                  acc[2] = fmaf(a.z, w[2], acc[2]); acc[3] = fmaf(a.w, w[3], acc[3]);
-                  acc[4] = fmaf(e.x, w[4], acc[4]); acc[5] = fmaf(e.y, w[5], acc[5]);
-                  acc[6] = fmaf(e.z, w[6], acc[6]); acc[7] = fmaf(e.w, w[7], acc[7]);
-                }
-              uint32_t h[4], l[4];
+                  if (wr >= C::STRIDE) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                split2_f16<false>(relu6f(acc[2 * j]) * kActScale, relu6f(acc[2 * j + 1]) * kActScale, h[j], l[j]);
-              uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16;
-              *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = make_uint4(l[0], l[1], l[2], l[3]);
+                    for (int j = 0; j < 8; ++j) acc1[j] = fmaf(d[j], w[wr - C::STRIDE][j], acc1[j]);
+                  }
+                }
+              }
+              constexpr float kOut = 6.0f * kActScale;                   // relu6(x) * kActScale = sat(x/6) * 384
+              const int m2 = f * C::M2F + oy * C::WO + ox;
+              {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  split2_f16<false>(__saturatef(acc0[2 * j]) * kOut, __saturatef(acc0[2 * j + 1]) * kOut, h[j], l[j]);
+                uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = make_uint4(l[0], l[1], l[2], l[3]);
+              }
+              if (two) {
+                const int m3 = m2 + C::WO;
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  split2_f16<false>(__saturatef(acc1[2 * j]) * kOut, __saturatef(acc1[2 * j + 1]) * kOut, h[j], l[j]);
+                uint8_t* dst = sA2 + (m3 >> 7) * (128 * C::NC * 2) + ((m3 & 127) >> 3) * 128 + kg * 2048 + (m3 & 7) * 16;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = make_uint4(l[0], l[1], l[2], l[3]);
+              }
             }
-            rg += NWW * 4;
-            while (rg >= RG && kg < NKG) { rg -= RG; ++kg; }
+            it += NWW * 4;
+            while (it >= per_kg && kg < NKG) { it -= per_kg; ++kg; }
           }
         }
         fence_proxy_async_smem();
@@ -376,7 +408,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       ++n_g2;
       tc_fence_after_sync();
       {
-        constexpr int JW = (C::COUT_P % 32 == 0) ? 32 : 16;
+        constexpr int JW = (C::COUT_P % 32 == 0 && C::MT2 * (C::COUT_P / 32) >= 2 * NWG) ? 32
+                           : (C::MT2 * (C::COUT_P / 16) >= 2 * NWG) ? 16 : 8;
         constexpr int JC = C::COUT_P / JW;
         for (int e = wg; e < mt2 * JC; e += NWG) {
           const int t = e / JC, j0 = (e - t * JC) * JW;
@@ -385,7 +418,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           float* orow = p.y + ((size_t)(f0 * C::WO + oy0) * C::WO + m2) * C::COUT;
           float v[JW];
           const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::D2_COL + t * C::COUT_P + j0;
-          if constexpr (JW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+          if constexpr (JW == 32) tmem_ld32(taddr, v); else if constexpr (JW == 16) tmem_ld16(taddr, v); else tmem_ld8(taddr, v);
           if (m2 < M2) {
 #pragma unroll
             for (int j = 0; j < JW; j += 4) {
@@ -475,6 +508,28 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       umma_commit(smem_u32(&bar_g2));
     };
 
+    // stem, fp32 crops: bulk-copy (TMA) the crop rows of a tile into sIn, one tile ahead of the workers
+    auto stage_rows = [&](int tile) {
+      if constexpr (C::STEM) {
+        if (p.x_u8 != nullptr || tile >= ntiles) return;
+        const int fgq = tile / C::STRIPS, spq = tile - fgq * C::STRIPS;
+        const int iy0q = spq * C::RO * C::STRIDE - 1;
+        const int rfq = max(iy0q, 0), rlq = min(iy0q + C::RWIN - 1, C::W - 1);
+        const int iy_first = 2 * rfq - 1, nin = 2 * (rlq - rfq + 1) + 1;
+        int nvalid = 0;
+        for (int r = 0; r < nin; ++r) nvalid += (iy_first + r >= 0 && iy_first + r < kImg) ? 1 : 0;
+        mbar_expect_tx(smem_u32(&bar_in), (uint32_t)nvalid * 3 * kImg * 4);
+        for (int ci = 0; ci < 3; ++ci)
+          for (int r = 0; r < nin; ++r) {
+            const int iy = iy_first + r;
+            if (iy < 0 || iy >= kImg) continue;
+            bulk_g2s(smem_u32(sIn + (ci * C::IN_ROWS + r) * C::IN_STRIDE + 4),
+                     p.x + ((size_t)(fgq * 3 + ci) * kImg + iy) * kImg, kImg * 4, smem_u32(&bar_in));
+          }
+      }
+    };
+    stage_rows(blockIdx.x);
+
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ntile_local) {
       const int fg = tile / C::STRIPS, sp = tile - fg * C::STRIPS;
       const int nfaces = min(C::FACES, p.batch - fg * C::FACES);
@@ -485,6 +540,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       mbar_wait(smem_u32(&bar_x), n_x & 1, p.err);
       ++n_x;
       tc_fence_after_sync();
+      stage_rows(tile + gridDim.x);          // sIn is free again: the conversion of this tile has consumed it
       gemm1(g, 0, mt1);
       for (int c = 0; c < C::NCHUNK; ++c, ++g) {
         if (c + 1 < C::NCHUNK) {

@@ -434,9 +434,10 @@ void pack_fused(std::vector<uint8_t>& img, const float* w1, int K, const float* 
         put(chunk + C::CH_W1 + off, w1[(size_t)k * C::CHID + ch] * s1, C::W1_PLANE);
       }
       for (int t = 0; t < 9; ++t) d[t * C::NC + n] = dw[(size_t)t * C::CHID + ch];
-      d[9 * C::NC + n] = bdw[ch];
-      d[10 * C::NC + n] = b1[ch];
-      d[11 * C::NC + n] = 1.0f / (kActScaleHost * s1);
+      // the hidden activation is kept as relu6(h)/6 in [0,1] (kernels_fused.cuh): fold the 1/6 here
+      d[9 * C::NC + n] = bdw[ch] / 6.0f;
+      d[10 * C::NC + n] = b1[ch] / 6.0f;
+      d[11 * C::NC + n] = 1.0f / (6.0f * kActScaleHost * s1);
     }
     for (int n = 0; n < C::COUT; ++n)
       for (int k = 0; k < C::NC; ++k) {
