@@ -127,6 +127,12 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     fence_mbar_init();
   }
   if (warp == NWW) tmem_alloc<C::TM_COLS>(smem_u32(&tmem_base_s));
+  if constexpr (C::STEM) {     // staged-row buffer: the left pad column (and everything else) starts as zero;
+    float* z = reinterpret_cast<float*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u) + C::S_IN);
+    for (int i = threadIdx.x; i < 3 * C::IN_ROWS * C::IN_STRIDE / 4; i += blockDim.x)   // before any bulk copy
+      reinterpret_cast<float4*>(z)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    tc::fence_proxy_async_smem();
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -144,9 +150,6 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     // zero the whole hidden window once: halo columns are never written afterwards
     for (int i = tid; i < C::HS_PIX * C::HS_STRIDE / 4; i += NWT)
       reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (C::STEM)                                 // left pad column (and everything else) starts as zero
-      for (int i = tid; i < 3 * C::IN_ROWS * C::IN_STRIDE / 4; i += NWT)
-        reinterpret_cast<float4*>(sIn)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     mbar_wait(smem_u32(&bar_w), 0, p.err);                // b3/s3 (and, if resident, all chunks) landed
     uint32_t n_d1 = 0, n_g2 = 0, g = 0, n_in = 0;                   // completed-phase counters; g = chunk counter
     asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");
@@ -279,12 +282,24 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         }
         }
         {
-          // columns per TMEM load: as wide as possible while every worker group still gets a (tile, chunk) pair
-          constexpr int JW = (C::NC % 32 == 0 && C::MT1 * (C::NC / 32) >= NWG) ? 32
-                             : (C::MT1 * (C::NC / 16) >= NWG) ? 16 : 8;
+          // 16 (or 8) columns per TMEM load so that every worker group gets a (tile, column-chunk) pair; the
+          // expand scale is one power of two per layer (row 11 is constant) and the chunk's biases stay in
+          // registers, so an element costs one FFMA.SAT plus a quarter of a 16-byte shared store
+          constexpr int JW = (C::MT1 * (C::NC / 16) >= NWG) ? 16 : 8;
           constexpr int JC = C::NC / JW;
+          const float sc1 = dwc[11 * C::NC];
+          int cur_j0 = -1;
+          float bq[JW];
           for (int e = wg; e < mt1 * JC; e += NWG) {
             const int t = e / JC, j0 = (e - t * JC) * JW;
+            if (j0 != cur_j0) {
+              cur_j0 = j0;
+#pragma unroll
+              for (int j = 0; j < JW; j += 4) {
+                const float4 bb = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0 + j);
+                bq[j] = bb.x; bq[j + 1] = bb.y; bq[j + 2] = bb.z; bq[j + 3] = bb.w;
+              }
+            }
             const int m = t * 128 + row;
             const int f = (C::FACES > 1) ? m / ppf : 0;
             const int mr = m - f * ppf;
@@ -292,16 +307,13 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
             float* hrow = sH + (size_t)(f * C::HS_FACE + (rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE;
             float v[JW];
             const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * C::NC + j0;
-            if constexpr (JW == 32) tmem_ld32(taddr, v); else if constexpr (JW == 16) tmem_ld16(taddr, v); else tmem_ld8(taddr, v);
+            if constexpr (JW == 16) tmem_ld16(taddr, v); else tmem_ld8(taddr, v);
             if (m < M1) {
 #pragma unroll
-              for (int j = 0; j < JW; j += 4) {
-                const float4 bb = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0 + j);
-                const float4 sc = *reinterpret_cast<const float4*>(dwc + 11 * C::NC + j0 + j);
+              for (int j = 0; j < JW; j += 4)
                 *reinterpret_cast<float4*>(hrow + j0 + j) =
-                    make_float4(__saturatef(fmaf(v[j], sc.x, bb.x)), __saturatef(fmaf(v[j + 1], sc.y, bb.y)),
-                                __saturatef(fmaf(v[j + 2], sc.z, bb.z)), __saturatef(fmaf(v[j + 3], sc.w, bb.w)));
-              }
+                    make_float4(__saturatef(fmaf(v[j], sc1, bq[j])), __saturatef(fmaf(v[j + 1], sc1, bq[j + 1])),
+                                __saturatef(fmaf(v[j + 2], sc1, bq[j + 2])), __saturatef(fmaf(v[j + 3], sc1, bq[j + 3])));
             }
           }
         }

@@ -423,12 +423,13 @@ void pack_fused(std::vector<uint8_t>& img, const float* w1, int K, const float* 
     b3p[n] = b3[n];
     b3p[C::COUT_P + n] = 1.0f / (kActScaleHost * s3[n]);
   }
+  // one power-of-two scale for the whole expand layer (the kernel keeps it in a register): max |w1| in [256,512)
+  const float s1 = channel_scale(w1, 1, K * C::CHID);
   for (int c = 0; c < C::NCHUNK; ++c) {
     const size_t chunk = C::B3_BYTES + (size_t)c * C::CHUNK_BYTES;
     float* d = reinterpret_cast<float*>(img.data() + chunk + C::CH_DW);
     for (int n = 0; n < C::NC; ++n) {
       const int ch = c * C::NC + n;
-      const float s1 = channel_scale(w1 + ch, (size_t)C::CHID, K);
       for (int k = 0; k < K; ++k) {
         const size_t off = (size_t)(n / 8) * 128 + (size_t)(k / 8) * ((C::NC / 8) * 128) + (n % 8) * 16 + (k % 8) * 2;
         put(chunk + C::CH_W1 + off, w1[(size_t)k * C::CHID + ch] * s1, C::W1_PLANE);
