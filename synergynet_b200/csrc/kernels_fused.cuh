@@ -100,6 +100,15 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
   constexpr int NWT = NWW * 32;          // worker threads
   constexpr int NWG = NWW / 4;           // worker groups: group g owns every NWG-th (tile, column-chunk) pair
   static_assert(NWW % 4 == 0 && NWW >= 4 && NWW <= 16, "worker warps");
+  // Channel groups: the hidden channels of a chunk are split between NG groups of worker warps.  A group
+  // drains ITS channels from TMEM (EPI1) and runs the depthwise conv on ITS channels, so the only
+  // synchronisation between EPI1 and DW is a named barrier among the group's warps, and the groups drift
+  // freely against each other (one can be in EPI1 while another is in DW).
+  constexpr int NKG_ = C::NC / 8;
+  constexpr int NG = (NWG % 4 == 0 && NKG_ % 4 == 0) ? 4 : (NWG % 2 == 0 && NKG_ % 2 == 0) ? 2 : 1;
+  constexpr int WPG = NWW / NG, TPG = WPG * 32;      // warps / threads per group (WPG is a multiple of 4)
+  constexpr int KPG = NKG_ / NG;                       // 8-channel groups owned by a worker group
+  constexpr int SUBS = WPG / 4;                        // sub-groups of 128 threads (one TMEM lane each)
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, bar_wfull[2], bar_x, bar_d1, bar_epi1, bar_a2, bar_g2, bar_d2free, bar_in;
@@ -109,7 +118,9 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
   // turns every tile access into LD.E/ST.E instead of LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int row = tid & 127, wg = tid >> 7;   // GEMM row / TMEM lane of this worker, and its group
+  const int row = tid & 127, wg = tid >> 7;   // GEMM row / TMEM lane of this worker, and its 128-thread slice
+  const int grp = warp / WPG;                  // channel group (workers only)
+  const int gtid = tid - grp * TPG, gsub = gtid >> 7;
   const int face_groups = (p.batch + C::FACES - 1) / C::FACES;
   const int ntiles = face_groups * C::STRIPS;
 
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     mbar_wait(smem_u32(&bar_w), 0, p.err);                // b3/s3 (and, if resident, all chunks) landed
     uint32_t n_d1 = 0, n_g2 = 0, g = 0, n_in = 0;                   // completed-phase counters; g = chunk counter
-    asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");
+    asm volatile("bar.sync 5, %0;" ::"n"(NWT) : "memory");
 
     // Geometry of a tile + "prep": stage / convert its input into the GEMM1 A operand and publish it.
     // prep(next tile) is issued BEFORE the current tile's EPI2, so the issuer can run GEMM1(next, 0) --
@@ -192,7 +203,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                     make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");
+        asm volatile("bar.sync 5, %0;" ::"n"(NWT) : "memory");
       }
       // ---- X tile -> fp16 hi/lo canonical operand ------------------------------------------------
       {
@@ -268,58 +279,57 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         mbar_wait(smem_u32(&bar_d1), n_d1 & 1, p.err);
         ++n_d1;
         tc_fence_after_sync();
-        asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");     // every worker is done reading Hs (DW c-1)
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(TPG) : "memory");   // the group is done reading ITS Hs columns (DW c-1)
         if (c == 0) {
-        // ---- strip mode: window rows outside the image must read as zero (may hold a previous tile) --
-        if constexpr (C::STRIPS > 1) {
-          if (iy0 < 0)
-            for (int i = tid; i < C::HS_COLS * C::HS_STRIDE / 4; i += NWT)
-              reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (iy0 + C::RWIN - 1 > C::W - 1)
-            for (int i = tid; i < C::HS_COLS * C::HS_STRIDE / 4; i += NWT)
-              reinterpret_cast<float4*>(sH + (size_t)(C::RWIN - 1) * C::HS_COLS * C::HS_STRIDE)[i] =
-                  make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+          // ---- strip mode: window rows outside the image must read as zero (may hold a previous tile);
+          //      every group clears its own channel columns
+          if constexpr (C::STRIPS > 1) {
+            constexpr int CQ = KPG * 2;                               // float4 per pixel owned by the group
+            if (iy0 < 0)
+              for (int i = gtid; i < C::HS_COLS * CQ; i += TPG)
+                *reinterpret_cast<float4*>(sH + (size_t)(i / CQ) * C::HS_STRIDE + grp * KPG * 8 + (i % CQ) * 4) =
+                    make_float4(0.f, 0.f, 0.f, 0.f);
+            if (iy0 + C::RWIN - 1 > C::W - 1)
+              for (int i = gtid; i < C::HS_COLS * CQ; i += TPG)
+                *reinterpret_cast<float4*>(sH + (size_t)((C::RWIN - 1) * C::HS_COLS + i / CQ) * C::HS_STRIDE +
+                                           grp * KPG * 8 + (i % CQ) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         {
-          // 16 (or 8) columns per TMEM load so that every worker group gets a (tile, column-chunk) pair; the
-          // expand scale is one power of two per layer (row 11 is constant) and the chunk's biases stay in
-          // registers, so an element costs one FFMA.SAT plus a quarter of a 16-byte shared store
-          constexpr int JW = (C::MT1 * (C::NC / 16) >= NWG) ? 16 : 8;
-          constexpr int JC = C::NC / JW;
+          // EPI1: 8 columns (one channel octet) per TMEM load; the expand scale is one power of two per
+          // layer (row 11 is constant) and the octet's biases stay in registers, so an element costs one
+          // FFMA.SAT plus a quarter of a 16-byte shared store
           const float sc1 = dwc[11 * C::NC];
-          int cur_j0 = -1;
-          float bq[JW];
-          for (int e = wg; e < mt1 * JC; e += NWG) {
-            const int t = e / JC, j0 = (e - t * JC) * JW;
-            if (j0 != cur_j0) {
-              cur_j0 = j0;
-#pragma unroll
-              for (int j = 0; j < JW; j += 4) {
-                const float4 bb = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0 + j);
-                bq[j] = bb.x; bq[j + 1] = bb.y; bq[j + 2] = bb.z; bq[j + 3] = bb.w;
-              }
+          int cur_k = -1;
+          float bq[8];
+          for (int e = gsub; e < mt1 * KPG; e += SUBS) {
+            const int t = e / KPG, kq = grp * KPG + (e - t * KPG), j0 = kq * 8;
+            if (kq != cur_k) {
+              cur_k = kq;
+              const float4 b0 = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0);
+              const float4 b1 = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0 + 4);
+              bq[0] = b0.x; bq[1] = b0.y; bq[2] = b0.z; bq[3] = b0.w; bq[4] = b1.x; bq[5] = b1.y; bq[6] = b1.z; bq[7] = b1.w;
             }
             const int m = t * 128 + row;
             const int f = (C::FACES > 1) ? m / ppf : 0;
             const int mr = m - f * ppf;
             const int yl = mr / C::W, xx = mr - yl * C::W;
-            float* hrow = sH + (size_t)(f * C::HS_FACE + (rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE;
-            float v[JW];
-            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * C::NC + j0;
-            if constexpr (JW == 16) tmem_ld16(taddr, v); else tmem_ld8(taddr, v);
+            float* hrow = sH + (size_t)(f * C::HS_FACE + (rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE + j0;
+            float v[8];
+            tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * C::NC + j0, v);
             if (m < M1) {
-#pragma unroll
-              for (int j = 0; j < JW; j += 4)
-                *reinterpret_cast<float4*>(hrow + j0 + j) =
-                    make_float4(__saturatef(fmaf(v[j], sc1, bq[j])), __saturatef(fmaf(v[j + 1], sc1, bq[j + 1])),
-                                __saturatef(fmaf(v[j + 2], sc1, bq[j + 2])), __saturatef(fmaf(v[j + 3], sc1, bq[j + 3])));
+              *reinterpret_cast<float4*>(hrow) =
+                  make_float4(__saturatef(fmaf(v[0], sc1, bq[0])), __saturatef(fmaf(v[1], sc1, bq[1])),
+                              __saturatef(fmaf(v[2], sc1, bq[2])), __saturatef(fmaf(v[3], sc1, bq[3])));
+              *reinterpret_cast<float4*>(hrow + 4) =
+                  make_float4(__saturatef(fmaf(v[4], sc1, bq[4])), __saturatef(fmaf(v[5], sc1, bq[5])),
+                              __saturatef(fmaf(v[6], sc1, bq[6])), __saturatef(fmaf(v[7], sc1, bq[7])));
             }
           }
         }
         tc_fence_before_sync();
         mbar_arrive(smem_u32(&bar_epi1));
-        asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory");     // hidden window complete
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(TPG) : "memory");   // the group's channel columns of the window are complete
         // ---- DW: 3x3 depthwise on the window -> A2 operand ----------------------------------------
         if (c > 0) {                                        // A2 is free once GEMM2(c-1) has completed
           mbar_wait(smem_u32(&bar_g2), n_g2 & 1, p.err);
@@ -339,9 +349,10 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           constexpr int NR = C::STRIDE + 3;                                // window rows of a row pair
           const int per_kg = nfaces * PER_FACE;
           const int l8 = tid & 7, lx = l8 % GX, ly = l8 / GX;
-          int kg = 0, it = tid >> 3;
-          while (it >= per_kg && kg < NKG) { it -= per_kg; ++kg; }
-          while (kg < NKG) {
+          const int kg_end = (grp + 1) * KPG;                              // this group's channel octets
+          int kg = grp * KPG, it = gtid >> 3;
+          while (it >= per_kg && kg < kg_end) { it -= per_kg; ++kg; }
+          while (kg < kg_end) {
             const int f = it / PER_FACE, r2 = it - f * PER_FACE;
             const int rpg = r2 / XG, xg = r2 - rpg * XG;
             const int ox = xg * GX + lx, oy = 2 * (rpg * GY + ly);
@@ -406,8 +417,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                 *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = make_uint4(l[0], l[1], l[2], l[3]);
               }
             }
-            it += NWW * 4;
-            while (it >= per_kg && kg < NKG) { it -= per_kg; ++kg; }
+            it += TPG / 8;
+            while (it >= per_kg && kg < kg_end) { it -= per_kg; ++kg; }
           }
         }
         fence_proxy_async_smem();
