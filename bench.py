@@ -30,6 +30,15 @@ FLOP_PER_FACE = 186_430_744            # 2*(93,204,560 +
 X_BYTES_PER_FACE = 3 * 120 * 120 * 4
 LMK_BYTES_PER_FACE = 3 * 68 * 4
 METRIC = 'faces/sec (120x120, batch 1024 per GPU, backbone + 3DMM params + 68 landmarks)'
+# algorithmic MAC per face of every launch of the fused engine (SURVEY.md section 8(a) shape table)
+KERNEL_MACS = {
+    'fused_stem_block1': 3_110_400 + 1_036_800 + 1_843_200, 'fused_block2': 8_380_800, 'fused_block3': 7_387_200,
+    'fused_block4': 4_438_800, 'fused_block5': 3_153_600, 'fused_block6': 3_153_600, 'fused_block7': 2_279_424,
+    'fused_block8': 3_366_912, 'fused_block9': 3_366_912, 'fused_block10': 3_366_912, 'fused_block11': 4_153_344,
+    'fused_block12': 7_409_664, 'fused_block13': 7_409_664, 'fused_block14': 5_096_448, 'fused_block15': 5_053_440,
+    'fused_block16': 5_053_440, 'fused_block17': 7_511_040, 'tail_conv_pool_kernel': 6_553_600, 'heads_kernel': 79_360,
+    'dense_recon_tc_kernel': 10_812, 'dense_alpha_kernel': 0,
+}
 
 
 def load_peaks():
@@ -88,6 +97,28 @@ class ClockSampler:
             return {'sm_mhz': None, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': 0}
         sm.sort()
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def dominant_roofline(kernel_ms: dict, batch: int, peaks: dict):
+    """`roofline` of the launch that takes the largest share of the step: algorithmic FLOP of that
+    launch / its CUDA-event duration, against the sustained bf16 peak (it runs inside a long step).
+    `traffic` = DRAM bytes of one launch from the committed ncu capture (profiles/kernel_traffic.json)."""
+    if not kernel_ms:
+        return None
+    name = max(kernel_ms, key=kernel_ms.get)
+    flop = 2.0 * KERNEL_MACS.get(name, 0) * batch
+    ms = kernel_ms[name]
+    achieved = flop / (ms * 1e-3) / 1e12
+    traffic = None
+    fp = os.path.join(ROOT, 'profiles', 'kernel_traffic.json')
+    if os.path.exists(fp):
+        with open(fp) as f:
+            traffic = json.load(f).get(name)
+    return {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
+            'frac': achieved / peaks['bf16_sustained'], 'traffic': traffic, 'ms_per_launch': ms,
+            'share_of_step': ms / sum(kernel_ms.values()),
+            'what': f'algorithmic {KERNEL_MACS.get(name, 0):,} MAC/face x 2 x {batch} faces / CUDA-event time of one launch; '
+                    f'peak = sustained bf16 of {peaks["source"]}'}
 
 
 def build_model(device: str):
@@ -228,6 +259,16 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
 
+    # ---- per-kernel device times (CUDA events behind every launch, outside the timed region) -------------
+    kernel_ms = {}
+    eng.set_timing(True)
+    n_t = 5
+    for i in range(n_t):
+        eng.forward_landmarks(xs[i % n_rot])
+        for name, t_ms in eng.timings():
+            kernel_ms[name] = kernel_ms.get(name, 0.0) + t_ms / n_t
+    eng.set_timing(False)
+
     if args.profile:
         if rank == 0:
             emit({'profile_run': True, 'ms_per_step': ms / args.steps, 'gpu_launches': launches})
@@ -290,7 +331,9 @@ def run_b200(args):
                        'd2h_bytes_per_step': B * LMK_BYTES_PER_FACE, 'steps': e2e_steps,
                        'call': 'syn_forward_landmarks_host_u8 (pinned uint8 crops in, (img-127.5)/128 on the device, landmarks out)'},
             'gpu_launches': launches,
-            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
+            'roofline': dominant_roofline(kernel_ms, B, peaks),
+            'kernels_ms': {k: round(v, 4) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])},
+            'roofline_step': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
                          'frac': achieved / peaks['bf16_sustained'], 'traffic': None,
                          'what': 'whole step (all kernels of the fused path): algorithmic 186,430,744 FLOP/face x '
                                  f'{B} faces / CUDA-event step time; peak = sustained bf16 of {peaks["source"]}'},

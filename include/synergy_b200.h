@@ -128,6 +128,12 @@ int syn_forward_landmarks_host_u8(syn_handle_t* h, const uint8_t* x_u8_host, int
 /* ---- introspection ---------------------------------------------------------------------------*/
 /* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
 int64_t syn_launch_count(const syn_handle_t* h);
+/* Per-launch device timing of the LAST device-buffer call (syn_forward / syn_forward_landmarks[_u8] /
+ * syn_reconstruct): with timing on, a CUDA event is recorded on the caller's stream behind every kernel.
+ * syn_get_timings synchronises and returns up to max_entries durations (ms) with the kernel labels
+ * (static strings; names_out may be NULL).  Used by bench.py for the per-kernel roofline. */
+int syn_set_timing(syn_handle_t* h, int on);
+int syn_get_timings(syn_handle_t* h, float* ms_out, const char** names_out, int max_entries, int* n_out);
 /* Synchronise the device and report (then clear) the sticky flag a bounded in-kernel wait raises
  * when it times out (pipeline protocol bug); *flag_out = 0 means no kernel ever timed out. */
 int syn_poll_error(syn_handle_t* h, int* flag_out);

@@ -54,6 +54,8 @@ SIGNATURES = {
     'syn_forward_landmarks_u8': (_I, [_P, _F, _I, _F, _F, _P]),
     'syn_forward_landmarks_host_u8': (_I, [_P, _F, _I, _F, _F]),
     'syn_launch_count': (_L, [_P]),
+    'syn_set_timing': (_I, [_P, _I]),
+    'syn_get_timings': (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_char_p), _I, C.POINTER(C.c_int)]),
     'syn_poll_error': (_I, [_P, C.POINTER(C.c_int)]),
     'syn_debug_forward_until': (_I, [_P, _F, _I, _I, _F, _P]),
 }

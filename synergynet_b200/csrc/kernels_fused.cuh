@@ -71,8 +71,9 @@ struct FusedCfg {
   static constexpr int S_X = S_WCH + WSTAGES * CHUNK_BYTES;
   static constexpr int S_A2 = S_X + 2 * X_PLANE;
   static constexpr int S_H = S_A2 + 2 * A2_PLANE;
-  // stem only: staged input rows [3][IN_ROWS][IN_STRIDE] fp32, column c of the crop at index c + 4
-  static constexpr int IN_ROWS = 2 * ROWS_MAX + 1, IN_STRIDE = 128;
+  // stem only: staged input rows [3][IN_ROWS][120] fp32, exactly as they lie in the NCHW crop (one bulk
+  // copy per channel); the left zero-pad column is a predicate in the im2col gather
+  static constexpr int IN_ROWS = 2 * ROWS_MAX + 1, IN_STRIDE = 120;
   static constexpr int S_IN = S_H + HS_PIX * HS_STRIDE * 4;
   static constexpr int S_TOTAL = S_IN + (STEM_ ? 3 * IN_ROWS * IN_STRIDE * 4 : 0);
   static constexpr int SMEM_BYTES = S_TOTAL + 1024;                      // + alignment slack
@@ -181,12 +182,12 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       if constexpr (C::STEM) {
         const int iy_first = 2 * rf - 1, nin = 2 * (rl - rf + 1) + 1;
         if (p.x_u8 != nullptr) {              // uint8 crops: threads load, normalise and stage
-          for (int i = tid; i < 3 * nin * 31; i += NWT) {
-            const int c4 = i % 31, r = (i / 31) % nin, ci = i / (31 * nin);
+          for (int i = tid; i < 3 * nin * 30; i += NWT) {
+            const int c4 = i % 30, r = (i / 30) % nin, ci = i / (30 * nin);
             const int iy = iy_first + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);              // c4 == 0: the columns left of the crop
-            if (c4 > 0 && iy >= 0 && iy < kImg) {
-              const uchar4 u = *reinterpret_cast<const uchar4*>(p.x_u8 + ((size_t)(f0 * 3 + ci) * kImg + iy) * kImg + (c4 - 1) * 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (iy >= 0 && iy < kImg) {
+              const uchar4 u = *reinterpret_cast<const uchar4*>(p.x_u8 + ((size_t)(f0 * 3 + ci) * kImg + iy) * kImg + c4 * 4);
               v = make_float4(((float)u.x - 127.5f) / 128.0f, ((float)u.y - 127.5f) / 128.0f,
                               ((float)u.z - 127.5f) / 128.0f, ((float)u.w - 127.5f) / 128.0f);
             }
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
             const int iy = iy_first + r;
             if (iy < 0 || iy >= kImg)
               for (int i = tid; i < 3 * 30; i += NWT)
-                *reinterpret_cast<float4*>(sIn + ((i / 30) * C::IN_ROWS + r) * C::IN_STRIDE + 4 + (i % 30) * 4) =
+                *reinterpret_cast<float4*>(sIn + ((i / 30) * C::IN_ROWS + r) * C::IN_STRIDE + (i % 30) * 4) =
                     make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
               // im2col of the 3x3 stride-2 pad-1 stem conv from the staged rows: k = (ci*3+ky)*3+kx;
               // the kg switch makes every tap offset a compile-time constant
               const int yl = mr / C::W, xx = mr - yl * C::W;
-              const float* base = sIn + (2 * yl) * C::IN_STRIDE + 2 * xx + 3;
+              const float* base = sIn + (2 * yl) * C::IN_STRIDE + 2 * xx - 1;   // column 2xx-1+kx; -1 is the zero pad
 #pragma unroll
               for (int kgc = 0; kgc < KG; ++kgc)
                 if (kg == kgc) {
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                     const int k = kgc * 8 + j;
                     if (k < 27) {
                       const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
-                      v[j] = base[(ci * C::IN_ROWS + ky) * C::IN_STRIDE + kx];
+                      if (kx > 0 || xx > 0) v[j] = base[(ci * C::IN_ROWS + ky) * C::IN_STRIDE + kx];
                     }
                   }
                 }
@@ -302,28 +303,43 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           const float sc1 = dwc[11 * C::NC];
           int cur_k = -1;
           float bq[8];
-          for (int e = gsub; e < mt1 * KPG; e += SUBS) {
-            const int t = e / KPG, kq = grp * KPG + (e - t * KPG), j0 = kq * 8;
-            if (kq != cur_k) {
-              cur_k = kq;
-              const float4 b0 = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0);
-              const float4 b1 = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0 + 4);
-              bq[0] = b0.x; bq[1] = b0.y; bq[2] = b0.z; bq[3] = b0.w; bq[4] = b1.x; bq[5] = b1.y; bq[6] = b1.z; bq[7] = b1.w;
+          const int n_e = mt1 * KPG;
+          for (int e0 = gsub; e0 < n_e; e0 += 4 * SUBS) {
+            uint32_t vr[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                   // up to four TMEM loads in flight, one wait
+              const int e = e0 + u * SUBS;
+              if (e < n_e) {                                // warp-uniform
+                const int t = e / KPG, kq = grp * KPG + (e - t * KPG);
+                tmem_ld8_async(tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * C::NC + kq * 8, vr[u]);
+              }
             }
-            const int m = t * 128 + row;
-            const int f = (C::FACES > 1) ? m / ppf : 0;
-            const int mr = m - f * ppf;
-            const int yl = mr / C::W, xx = mr - yl * C::W;
-            float* hrow = sH + (size_t)(f * C::HS_FACE + (rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE + j0;
-            float v[8];
-            tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * C::NC + j0, v);
-            if (m < M1) {
-              *reinterpret_cast<float4*>(hrow) =
-                  make_float4(__saturatef(fmaf(v[0], sc1, bq[0])), __saturatef(fmaf(v[1], sc1, bq[1])),
-                              __saturatef(fmaf(v[2], sc1, bq[2])), __saturatef(fmaf(v[3], sc1, bq[3])));
-              *reinterpret_cast<float4*>(hrow + 4) =
-                  make_float4(__saturatef(fmaf(v[4], sc1, bq[4])), __saturatef(fmaf(v[5], sc1, bq[5])),
-                              __saturatef(fmaf(v[6], sc1, bq[6])), __saturatef(fmaf(v[7], sc1, bq[7])));
+            tmem_wait_ld();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = e0 + u * SUBS;
+              if (e < n_e) {
+                const int t = e / KPG, kq = grp * KPG + (e - t * KPG), j0 = kq * 8;
+                if (kq != cur_k) {
+                  cur_k = kq;
+                  const float4 b0 = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0);
+                  const float4 b1 = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0 + 4);
+                  bq[0] = b0.x; bq[1] = b0.y; bq[2] = b0.z; bq[3] = b0.w; bq[4] = b1.x; bq[5] = b1.y; bq[6] = b1.z; bq[7] = b1.w;
+                }
+                const int m = t * 128 + row;
+                if (m < M1) {
+                  const int f = (C::FACES > 1) ? m / ppf : 0;
+                  const int mr = m - f * ppf;
+                  const int yl = mr / C::W, xx = mr - yl * C::W;
+                  float* hrow = sH + (size_t)(f * C::HS_FACE + (rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE + j0;
+                  *reinterpret_cast<float4*>(hrow) =
+                      make_float4(__saturatef(fmaf(__uint_as_float(vr[u][0]), sc1, bq[0])), __saturatef(fmaf(__uint_as_float(vr[u][1]), sc1, bq[1])),
+                                  __saturatef(fmaf(__uint_as_float(vr[u][2]), sc1, bq[2])), __saturatef(fmaf(__uint_as_float(vr[u][3]), sc1, bq[3])));
+                  *reinterpret_cast<float4*>(hrow + 4) =
+                      make_float4(__saturatef(fmaf(__uint_as_float(vr[u][4]), sc1, bq[4])), __saturatef(fmaf(__uint_as_float(vr[u][5]), sc1, bq[5])),
+                                  __saturatef(fmaf(__uint_as_float(vr[u][6]), sc1, bq[6])), __saturatef(fmaf(__uint_as_float(vr[u][7]), sc1, bq[7])));
+                }
+              }
             }
           }
         }
@@ -539,16 +555,13 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         const int iy0q = spq * C::RO * C::STRIDE - 1;
         const int rfq = max(iy0q, 0), rlq = min(iy0q + C::RWIN - 1, C::W - 1);
         const int iy_first = 2 * rfq - 1, nin = 2 * (rlq - rfq + 1) + 1;
-        int nvalid = 0;
-        for (int r = 0; r < nin; ++r) nvalid += (iy_first + r >= 0 && iy_first + r < kImg) ? 1 : 0;
-        mbar_expect_tx(smem_u32(&bar_in), (uint32_t)nvalid * 3 * kImg * 4);
+        const int r_lo = (iy_first < 0) ? -iy_first : 0;                     // first / last staged row inside the crop
+        const int r_hi = min(nin - 1, kImg - 1 - iy_first);
+        const uint32_t bytes = (uint32_t)(r_hi - r_lo + 1) * kImg * 4;          // contiguous in the crop and in sIn
+        mbar_expect_tx(smem_u32(&bar_in), 3 * bytes);
         for (int ci = 0; ci < 3; ++ci)
-          for (int r = 0; r < nin; ++r) {
-            const int iy = iy_first + r;
-            if (iy < 0 || iy >= kImg) continue;
-            bulk_g2s(smem_u32(sIn + (ci * C::IN_ROWS + r) * C::IN_STRIDE + 4),
-                     p.x + ((size_t)(fgq * 3 + ci) * kImg + iy) * kImg, kImg * 4, smem_u32(&bar_in));
-          }
+          bulk_g2s(smem_u32(sIn + (ci * C::IN_ROWS + r_lo) * C::IN_STRIDE),
+                   p.x + ((size_t)(fgq * 3 + ci) * kImg + iy_first + r_lo) * kImg, bytes, smem_u32(&bar_in));
       }
     };
     stage_rows(blockIdx.x);
@@ -563,8 +576,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       mbar_wait(smem_u32(&bar_x), n_x & 1, p.err);
       ++n_x;
       tc_fence_after_sync();
-      stage_rows(tile + gridDim.x);          // sIn is free again: the conversion of this tile has consumed it
       gemm1(g, 0, mt1);
+      stage_rows(tile + gridDim.x);          // sIn is free again: the conversion of this tile has consumed it
       for (int c = 0; c < C::NCHUNK; ++c, ++g) {
         if (c + 1 < C::NCHUNK) {
           mbar_wait(smem_u32(&bar_epi1), n_epi1 & 1, p.err);    // D1 drained by the workers

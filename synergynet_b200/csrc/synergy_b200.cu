@@ -38,6 +38,11 @@ struct syn_handle {
   int engine = SYN_ENGINE_TC_FUSED;            // default: fused tcgen05 engine; 0/1 remain for cross-checks
   bool committed = false;
   int64_t launches = 0;
+  // optional per-launch timing (syn_set_timing): events recorded after every kernel of a call
+  bool timing = false;
+  std::vector<cudaEvent_t> tev;
+  std::vector<const char*> tname;
+  int tn = 0;
 
   HostConv hconv[kNumConv];
   std::vector<float> h_head_w, h_head_b;       // (62,1280), (62)
@@ -114,6 +119,20 @@ struct DeviceGuard {
   }
 };
 
+// count a launch and, when timing is on, drop an event behind it
+void mark(syn_handle* h, cudaStream_t st, const char* name) {
+  h->launches++;
+  if (!h->timing) return;
+  if (h->tn >= (int)h->tev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    h->tev.push_back(e);
+    h->tname.push_back(name);
+  }
+  h->tname[h->tn] = name;
+  cudaEventRecord(h->tev[h->tn++], st);
+}
+
 int ensure_workspace(syn_handle* h, int batch) {
   if (batch <= h->ws_batch) return SYN_OK;
   SYN_CUDA(cudaDeviceSynchronize());
@@ -146,7 +165,7 @@ int launch_pointwise_simt(syn_handle* h, const float* A, const DevConv& w, const
     pointwise_gemm_kernel<256, 16, 4, 4><<<grid, 256, 0, st>>>(A, w.w, w.bias, residual, out, M, K, N, relu6);
   }
   SYN_LAUNCH_CHECK("pointwise_gemm_kernel");
-  h->launches++;
+  mark(h, st, "pointwise_gemm_kernel");
   return SYN_OK;
 }
 
@@ -160,7 +179,7 @@ int launch_pointwise_tc(syn_handle* h, const float* A, int layer, const float* r
   dim3 grid((M + 127) / 128, h->tc_nranges[layer]);
   tc_pointwise_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
   SYN_LAUNCH_CHECK("tc_pointwise_kernel");
-  h->launches++;
+  mark(h, st, "tc_pointwise_kernel");
   return SYN_OK;
 }
 
@@ -178,7 +197,7 @@ int launch_depthwise(syn_handle* h, const float* x, int layer, float* y, int bat
   depthwise3x3_kernel<<<grid, 256, 0, st>>>(x, h->dconv[layer].w, h->dconv[layer].bias, y, batch,
                                            c.cout, c.h_in, c.h_out, c.stride);
   SYN_LAUNCH_CHECK("depthwise3x3_kernel");
-  h->launches++;
+  mark(h, st, "depthwise3x3_kernel");
   return SYN_OK;
 }
 
@@ -206,7 +225,7 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
     const size_t n4 = (size_t)batch * 3 * kImg * kImg / 4;
     normalize_u8_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x_u8, h->d_x_f32, n4);
     SYN_LAUNCH_CHECK("normalize_u8_kernel");
-    h->launches++;
+    mark(h, st, "normalize_u8_kernel");
     x = h->d_x_f32;
     x_u8 = nullptr;
   }
@@ -257,16 +276,17 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
       t.ctas_per_slice = std::max(1, std::min(ntiles, h->sm_count / 10));
       tail_conv_pool_kernel<<<10 * t.ctas_per_slice, kTailThreads, kTailSmem, st>>>(t);
       SYN_LAUNCH_CHECK("tail_conv_pool_kernel");
+      mark(h, st, "tail_conv_pool_kernel");
       heads_kernel<<<dim3((batch + 7) / 8, 2), 256, 0, st>>>(pooled, h->d_head_w, h->d_head_b, params, batch);
       SYN_LAUNCH_CHECK("heads_kernel");
-      h->launches += 2;
+      mark(h, st, "heads_kernel");
       return SYN_OK;
     }
   } else {
   stem_conv3x3s2_kernel<<<batch * 60, kStemThreads, 0, st>>>(x, h->dconv[0].w, h->dconv[0].bias,
                                                             h->buf_io[cur], batch);
   SYN_LAUNCH_CHECK("stem_conv3x3s2_kernel");
-  h->launches++;
+  mark(h, st, "stem_conv3x3s2_kernel");
   if (stop_layer == 0) return dbg(0, h->buf_io[cur]);
   }
 
@@ -301,7 +321,7 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
   pool_heads_kernel<<<batch, 256, 0, st>>>(h->buf_hid, h->d_head_w, h->d_head_b, params, pool,
                                           last.h_out * last.h_out);
   SYN_LAUNCH_CHECK("pool_heads_kernel");
-  h->launches++;
+  mark(h, st, "pool_heads_kernel");
   return SYN_OK;
 }
 
@@ -319,6 +339,7 @@ int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense,
   dense_alpha_kernel<<<n_ftiles, 64, 0, st>>>(params, h->d_mean, h->d_std, h->d_ascale, h->d_alpha_img, h->d_pose, batch,
                                              whitening);
   SYN_LAUNCH_CHECK("dense_alpha_kernel");
+  mark(h, st, "dense_alpha_kernel");
   DenseArgs a;
   a.basis_img = dense ? h->d_dn_img : h->d_sp_img;
   a.meta = dense ? h->d_dn_meta : h->d_sp_meta;
@@ -329,7 +350,7 @@ int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense,
   const int items = a.n_vtiles * a.n_ftiles;
   dense_recon_tc_kernel<<<std::min(items, h->sm_count), kDnThreads, kDnSmem, st>>>(a);
   SYN_LAUNCH_CHECK("dense_recon_tc_kernel");
-  h->launches += 2;
+  mark(h, st, "dense_recon_tc_kernel");
   return SYN_OK;
 }
 
@@ -350,7 +371,7 @@ int run_reconstruct(syn_handle* h, const float* params, int batch, int dense, in
                                                h->n_pts, h->sp_pad, whitening, transform);
   }
   SYN_LAUNCH_CHECK("reconstruct_kernel");
-  h->launches++;
+  mark(h, st, "reconstruct_kernel");
   return SYN_OK;
 }
 
@@ -485,7 +506,11 @@ int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, 
   }
   if (rc != SYN_OK) return rc;
   SYN_LAUNCH_CHECK("fused_mbconv_kernel");
-  h->launches++;
+  static const char* const names[18] = {"", "fused_stem_block1", "fused_block2", "fused_block3", "fused_block4",
+                                        "fused_block5", "fused_block6", "fused_block7", "fused_block8", "fused_block9",
+                                        "fused_block10", "fused_block11", "fused_block12", "fused_block13", "fused_block14",
+                                        "fused_block15", "fused_block16", "fused_block17"};
+  mark(h, st, names[block]);
   return SYN_OK;
 }
 
@@ -609,6 +634,7 @@ void syn_destroy(syn_handle_t* h) {
     if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
   }
+  for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_compute) cudaStreamDestroy(h->s_compute);
   delete h;
@@ -857,12 +883,14 @@ int syn_get_engine(const syn_handle_t* h) { return h ? h->engine : -1; }
 
 #define SYN_CHECK_READY(h, name)                                                         \
   if ((h) == nullptr) return fail(SYN_ERR_INVALID, name ": null handle");                \
-  if (!(h)->committed) return fail(SYN_ERR_STATE, name ": weights not committed (syn_commit)")
+  if (!(h)->committed) return fail(SYN_ERR_STATE, name ": weights not committed (syn_commit)"); \
+  (h)->tn = 0
 
 int syn_forward(syn_handle_t* h, const float* x, int batch, float* params, float* pool, void* stream) {
   SYN_CHECK_READY(h, "syn_forward");
   if (x == nullptr || params == nullptr || batch <= 0) return fail(SYN_ERR_INVALID, "syn_forward: bad argument");
   DeviceGuard g(h->device);
+  if (h->timing) { mark(h, (cudaStream_t)stream, "start"); h->launches--; }
   return run_backbone(h, x, batch, params, pool, -1, nullptr, (cudaStream_t)stream);
 }
 
@@ -871,6 +899,7 @@ int syn_reconstruct(syn_handle_t* h, const float* params, int batch, int dense, 
   SYN_CHECK_READY(h, "syn_reconstruct");
   if (params == nullptr || out == nullptr || batch <= 0) return fail(SYN_ERR_INVALID, "syn_reconstruct: bad argument");
   DeviceGuard g(h->device);
+  if (h->timing) { mark(h, (cudaStream_t)stream, "start"); h->launches--; }
   return run_reconstruct(h, params, batch, dense, whitening, transform, out, (cudaStream_t)stream);
 }
 
@@ -882,6 +911,7 @@ int syn_forward_landmarks(syn_handle_t* h, const float* x, int batch, float* par
   int rc = ensure_workspace(h, batch);
   if (rc != SYN_OK) return rc;
   float* p = params ? params : h->d_params_tmp;
+  if (h->timing) { mark(h, (cudaStream_t)stream, "start"); h->launches--; }
   rc = run_backbone(h, x, batch, p, nullptr, -1, nullptr, (cudaStream_t)stream);
   if (rc != SYN_OK) return rc;
   return run_reconstruct(h, p, batch, 0, 1, 1, lmk, (cudaStream_t)stream);
@@ -987,6 +1017,26 @@ int syn_forward_landmarks_host_u8(syn_handle_t* h, const uint8_t* x_host, int ba
 }
 
 int64_t syn_launch_count(const syn_handle_t* h) { return h ? h->launches : -1; }
+
+int syn_set_timing(syn_handle_t* h, int on) {
+  if (h == nullptr) return fail(SYN_ERR_INVALID, "syn_set_timing: null handle");
+  h->timing = on != 0;
+  h->tn = 0;
+  return SYN_OK;
+}
+
+int syn_get_timings(syn_handle_t* h, float* ms_out, const char** names_out, int max_entries, int* n_out) {
+  if (h == nullptr || ms_out == nullptr || n_out == nullptr) return fail(SYN_ERR_INVALID, "syn_get_timings: null argument");
+  DeviceGuard g(h->device);
+  SYN_CUDA(cudaDeviceSynchronize());
+  int n = 0;
+  for (int i = 1; i < h->tn && n < max_entries; ++i, ++n) {
+    SYN_CUDA(cudaEventElapsedTime(&ms_out[n], h->tev[i - 1], h->tev[i]));
+    if (names_out != nullptr) names_out[n] = h->tname[i];
+  }
+  *n_out = n;
+  return SYN_OK;
+}
 
 int syn_poll_error(syn_handle_t* h, int* flag_out) {
   if (h == nullptr || flag_out == nullptr) return fail(SYN_ERR_INVALID, "syn_poll_error: null handle");

@@ -91,6 +91,17 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.syn_launch_count(self._h))
 
+    def set_timing(self, on: bool) -> None:
+        _lib.check(self._lib.syn_set_timing(self._h, int(on)))
+
+    def timings(self):
+        """[(kernel label, ms)] of the last device-buffer call (needs set_timing(True) before it)."""
+        ms = (C.c_float * 64)()
+        names = (C.c_char_p * 64)()
+        n = C.c_int(0)
+        _lib.check(self._lib.syn_get_timings(self._h, ms, names, 64, C.byref(n)))
+        return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
     def poll_error(self) -> int:
         """Device sync + sticky in-kernel timeout flag (0 = clean)."""
         flag = C.c_int(0)

@@ -243,6 +243,19 @@ def test_get_all_outputs_matches_reference_api(model, gold, engine_kind):
         model.get_all_outputs(gold['scene'])
 
 
+def test_per_launch_timing_api(model):
+    eng = model._engine(torch.device('cuda', 0))
+    model.set_engine(_lib.ENGINE_TC_FUSED)
+    x = synthetic.make_inputs(16, 0).cuda()
+    eng.set_timing(True)
+    eng.forward_landmarks(x)
+    t = eng.timings()
+    eng.set_timing(False)
+    names = [n for n, _ in t]
+    assert names[0] == 'fused_stem_block1' and 'tail_conv_pool_kernel' in names and names[-1] == 'dense_recon_tc_kernel'
+    assert len(t) == 21 and all(ms > 0 for _, ms in t)
+
+
 def test_reload_of_weights_is_picked_up(model, sd, gold):
     x = _x(gold)[:2].cuda()
     before = model.forward_test(x)
