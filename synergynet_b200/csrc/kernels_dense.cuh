@@ -29,7 +29,8 @@ constexpr int kDnBTile = 2 * kDnBPlane;                   // 16 KB per face tile
 constexpr int kDnPoseTile = kDnFaces * 12 * 4;            // 3 KB
 constexpr int kDnBSlot = kDnBTile + kDnPoseTile;
 constexpr int kDnMetaTile = 128 * 6 * 4;                  // per vertex tile: u[3][128], 1/rowscale[3][128]
-constexpr int kDnSmem = kDnATile + 2 * kDnMetaTile + 2 * kDnBSlot + 1024;
+constexpr int kDnBSlots = 4;                              // alpha/pose ring: loads run 3 items ahead of the MMAs
+constexpr int kDnSmem = kDnATile + 2 * kDnMetaTile + kDnBSlots * kDnBSlot + 1024;
 constexpr int kDnEpiWarps = 16;                          // 4 per TMEM lane quarter: 16 faces each
 constexpr int kDnThreads = (kDnEpiWarps + 1) * 32;
 
@@ -89,12 +90,12 @@ struct DenseArgs {
 __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const DenseArgs p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_a, bar_bfull[2], bar_dfull[2], bar_dfree[2];
+  __shared__ __align__(8) uint64_t bar_a, bar_bfull[kDnBSlots], bar_dfull[2], bar_dfree[2];
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   float* sMeta = reinterpret_cast<float*>(smem + kDnATile);          // 2 slots (vertex-tile load parity)
-  uint8_t* sB = smem + kDnATile + 2 * kDnMetaTile;                   // 2 slots of alpha + pose
+  uint8_t* sB = smem + kDnATile + 2 * kDnMetaTile;                   // kDnBSlots slots of alpha + pose
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int items = p.n_vtiles * p.n_ftiles;
@@ -103,8 +104,8 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
 
   if (tid == 0) {
     mbar_init(smem_u32(&bar_a), 1);
+    for (int i = 0; i < kDnBSlots; ++i) mbar_init(smem_u32(&bar_bfull[i]), 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bar_bfull[i]), 1);
       mbar_init(smem_u32(&bar_dfull[i]), 1);
       mbar_init(smem_u32(&bar_dfree[i]), kDnEpiWarps * 32);
     }
@@ -135,10 +136,11 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
         ux = m[0 * 128 + lane_v]; uy = m[1 * 128 + lane_v]; uz = m[2 * 128 + lane_v];
         ox = m[3 * 128 + lane_v]; oy = m[4 * 128 + lane_v]; oz = m[5 * 128 + lane_v];
       }
-      mbar_wait(smem_u32(&bar_bfull[s]), use_par, p.err);          // pose tile visible to this thread
+      const int sb = i % kDnBSlots;
+      mbar_wait(smem_u32(&bar_bfull[sb]), (uint32_t)(i / kDnBSlots) & 1, p.err);   // pose tile visible to this thread
       mbar_wait(smem_u32(&bar_dfull[s]), use_par, p.err);
       tc_fence_after_sync();
-      const float* pose = reinterpret_cast<const float*>(sB + s * kDnBSlot + kDnBTile) + fq * FPT * 12;
+      const float* pose = reinterpret_cast<const float*>(sB + sb * kDnBSlot + kDnBTile) + fq * FPT * 12;
       const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + s * 192 + fq * FPT;
       float sx[FPT], sy[FPT], sz[FPT];
       tmem_ld16(trow, sx);
@@ -181,7 +183,8 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
     };
     int cur_vt = -1;
     uint32_t n_a = 0;
-    if (it0 < it1) load_b(it0, 0);
+    for (int k = 0; k < kDnBSlots - 1; ++k)
+      if (it0 + k < it1) load_b(it0 + k, k);
     for (int it = it0, i = 0; it < it1; ++it, ++i) {
       const int vt = it / p.n_ftiles;
       const int s = i & 1;
@@ -197,10 +200,11 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
         mbar_wait(smem_u32(&bar_a), n_a & 1, p.err);
         ++n_a;
       }
-      mbar_wait(smem_u32(&bar_bfull[s]), (uint32_t)(i >> 1) & 1, p.err);
+      const int sb = i % kDnBSlots;
+      mbar_wait(smem_u32(&bar_bfull[sb]), (uint32_t)(i / kDnBSlots) & 1, p.err);
       if (i >= 2) dfree_wait(i - 2);                               // TMEM buffer s drained
       tc_fence_after_sync();
-      const uint32_t b_hi = smem_u32(sB + s * kDnBSlot);
+      const uint32_t b_hi = smem_u32(sB + sb * kDnBSlot);
 #pragma unroll
       for (int plane = 0; plane < 3; ++plane) {
 #pragma unroll
@@ -214,10 +218,10 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
         }
       }
       umma_commit(smem_u32(&bar_dfull[s]));
-      // prefetch the next item's alpha/pose into the other slot, last used by item i-1 (MMA + epilogue)
-      if (it + 1 < it1) {
+      // prefetch alpha/pose three items ahead into the slot last used by item i-1 (MMA + epilogue done)
+      if (it + kDnBSlots - 1 < it1) {
         if (i >= 1) dfree_wait(i - 1);
-        load_b(it + 1, s ^ 1);
+        load_b(it + kDnBSlots - 1, (i + kDnBSlots - 1) % kDnBSlots);
       }
     }
   }

@@ -31,11 +31,11 @@ constexpr int round_up_c(int a, int b) { return ceil_div_c(a, b) * b; }
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 template <int CIN_, int CHID_, int NC_, int COUT_, int W_, int STRIDE_, int RO_, int FACES_, bool RES_, bool STEM_,
-          bool WSTREAM_>
+          int WSTREAM_>
 struct FusedCfg {
   static constexpr bool STEM = STEM_;            // GEMM1 = im2col(3x3 s2 stem conv), CIN = 27 taps
   static constexpr bool RES = RES_;
-  static constexpr bool WSTREAM = WSTREAM_;      // weights streamed per chunk instead of resident
+  static constexpr bool WSTREAM = WSTREAM_ > 0;  // weights streamed per chunk (ring of WSTREAM_ slots) instead of resident
   static constexpr int CIN = CIN_;               // channels of the NHWC input (STEM: 27)
   static constexpr int CIN_P = round_up_c(CIN_, 16);
   static constexpr int CHID = CHID_, NC = NC_, NCHUNK = CHID_ / NC_;
@@ -62,7 +62,7 @@ struct FusedCfg {
   static constexpr int CH_W1 = 0, CH_W3 = 2 * W1_PLANE, CH_DW = CH_W3 + 2 * W3_PLANE;
   static constexpr int CHUNK_BYTES = round_up_c(CH_DW + DW_ROWS * NC_ * 4, 128);
   static constexpr int W_BYTES = B3_BYTES + NCHUNK * CHUNK_BYTES;
-  static constexpr int WSTAGES = WSTREAM_ ? 2 : NCHUNK;                  // chunk slots held in smem
+  static constexpr int WSTAGES = WSTREAM_ > 0 ? WSTREAM_ : NCHUNK;       // chunk slots held in smem
   // ---- shared memory carve-up --------------------------------------------------------------------
   static constexpr int X_PLANE = MT1 * 128 * CIN_P * 2;
   static constexpr int A2_PLANE = MT2 * 128 * NC_ * 2;
@@ -83,7 +83,7 @@ struct FusedCfg {
   static_assert(D2_COL + MT2 * COUT_P <= 512, "TMEM columns");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
   static_assert(N2 % 16 == 0 && N2 <= 256, "MMA N");
-  static_assert(!WSTREAM_ || NCHUNK >= 2, "streaming needs at least two chunks");
+  static_assert(WSTREAM_ == 0 || (WSTREAM_ >= 2 && WSTREAM_ <= 4 && NCHUNK >= WSTREAM_), "weight ring");
 };
 
 struct FusedArgs {
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
   constexpr int SUBS = WPG / 4;                        // sub-groups of 128 threads (one TMEM lane each)
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_wfull[2], bar_x, bar_d1, bar_epi1, bar_a2, bar_g2, bar_d2free, bar_in;
+  __shared__ __align__(8) uint64_t bar_w, bar_wfull[4], bar_x, bar_d1, bar_epi1, bar_a2, bar_g2, bar_d2free, bar_in;
   __shared__ uint32_t tmem_base_s;
 
   // keep the pointer in the shared address space (no integer round trip): a generic pointer here
@@ -127,8 +127,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
 
   if (tid == 0) {
     mbar_init(smem_u32(&bar_w), 1);
-    mbar_init(smem_u32(&bar_wfull[0]), 1);
-    mbar_init(smem_u32(&bar_wfull[1]), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bar_wfull[i]), 1);
     mbar_init(smem_u32(&bar_x), NWT);
     mbar_init(smem_u32(&bar_d1), 1);
     mbar_init(smem_u32(&bar_epi1), NWT);
@@ -273,8 +272,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       const int mt2 = (M2 + 127) >> 7;
 
       for (int c = 0; c < C::NCHUNK; ++c, ++g) {
-        const int slot = C::WSTREAM ? (int)(g & 1) : c;
-        if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (g >> 1) & 1, p.err);
+        const int slot = C::WSTREAM ? (int)(g % C::WSTAGES) : c;
+        if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (g / C::WSTAGES) & 1, p.err);
         const float* dwc = reinterpret_cast<const float*>(sWch + slot * C::CHUNK_BYTES + C::CH_DW);
         // ---- EPI1: D1 -> relu6(s1*D1 + b1) -> hidden window --------------------------------------
         mbar_wait(smem_u32(&bar_d1), n_d1 & 1, p.err);
@@ -484,8 +483,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     // =============================== MMA issuer / weight loader ====================================
     const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const uint32_t total_chunks = (uint32_t)my_tiles * C::NCHUNK;
-    auto load_chunk = [&](uint32_t gi) {                     // streaming: chunk gi -> slot gi & 1
-      const uint32_t slot = gi & 1, c = gi % C::NCHUNK;
+    auto load_chunk = [&](uint32_t gi) {                     // streaming: chunk gi -> slot gi % WSTAGES
+      const uint32_t slot = gi % C::WSTAGES, c = gi % C::NCHUNK;
       mbar_expect_tx(smem_u32(&bar_wfull[slot]), C::CHUNK_BYTES);
       bulk_g2s(smem_u32(sWch + slot * C::CHUNK_BYTES), p.wimg + C::B3_BYTES + (size_t)c * C::CHUNK_BYTES, C::CHUNK_BYTES,
                smem_u32(&bar_wfull[slot]));
@@ -493,8 +492,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     if constexpr (C::WSTREAM) {
       mbar_expect_tx(smem_u32(&bar_w), C::B3_BYTES);
       bulk_g2s(smem_u32(smem + C::S_B3), p.wimg, C::B3_BYTES, smem_u32(&bar_w));
-      if (total_chunks > 0) load_chunk(0);
-      if (total_chunks > 1) load_chunk(1);
+      for (uint32_t k = 0; k < (uint32_t)C::WSTAGES; ++k)
+        if (total_chunks > k) load_chunk(k);
     } else {
       mbar_expect_tx(smem_u32(&bar_w), C::W_BYTES);
       bulk_g2s(smem_u32(smem + C::S_B3), p.wimg, C::W_BYTES, smem_u32(&bar_w));
@@ -507,41 +506,43 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     uint32_t g = 0;                                          // chunk counter of the current GEMM2
     int ntile_local = 0;
 
+    // descriptor halves that never change (SBO = 128 everywhere); per MMA only `lo` moves by (bytes >> 4)
+    const uint32_t d_hi = smem_desc_hi(128);
+    const uint32_t xa_lo = smem_desc_lo(smem_u32(sX), 2048), a2_lo = smem_desc_lo(smem_u32(sA2), 2048);
+    const uint32_t w_lo1 = smem_desc_lo(smem_u32(sWch) + C::CH_W1, LBO_W1), w_lo3 = smem_desc_lo(smem_u32(sWch) + C::CH_W3, LBO_W3);
     auto gemm1 = [&](uint32_t gi, int c, int mt1) {
-      const int slot = C::WSTREAM ? (int)(gi & 1) : c;
-      if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (gi >> 1) & 1, p.err);
-      const uint32_t wbase = smem_u32(sWch + slot * C::CHUNK_BYTES) + C::CH_W1;
+      const int slot = C::WSTREAM ? (int)(gi % C::WSTAGES) : c;
+      if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (gi / C::WSTAGES) & 1, p.err);
+      const uint32_t wb = w_lo1 + ((slot * C::CHUNK_BYTES) >> 4);
       for (int t = 0; t < mt1; ++t) {
-        uint32_t acc = 0;
+        const uint32_t ab = xa_lo + ((t * (128 * C::CIN_P * 2)) >> 4);
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a_base = smem_u32(sX) + (pass == 2 ? C::X_PLANE : 0) + t * (128 * C::CIN_P * 2);
-          const uint32_t b_base = wbase + (pass == 1 ? C::W1_PLANE : 0);
 #pragma unroll
-          for (int ks = 0; ks < C::CIN_P / 16; ++ks) {
-            umma_f16(tmem + t * C::NC, make_smem_desc(a_base + ks * 4096, 2048, 128),
-                     make_smem_desc(b_base + ks * 2 * LBO_W1, LBO_W1, 128), idesc1, acc);
-            acc = 1;
-          }
+          for (int ks = 0; ks < C::CIN_P / 16; ++ks)
+            umma_f16(tmem + t * C::NC, desc64(d_hi, ab + (((pass == 2 ? C::X_PLANE : 0) + ks * 4096) >> 4)),
+                     desc64(d_hi, wb + (((pass == 1 ? C::W1_PLANE : 0) + ks * 2 * LBO_W1) >> 4)), idesc1,
+                     (pass > 0 || ks > 0) ? 1u : 0u);
         }
       }
       umma_commit(smem_u32(&bar_d1));
     };
     auto gemm2 = [&](uint32_t gi, int c, int mt2) {
-      const int slot = C::WSTREAM ? (int)(gi & 1) : c;
-      const uint32_t wbase = smem_u32(sWch + slot * C::CHUNK_BYTES) + C::CH_W3;
+      const int slot = C::WSTREAM ? (int)(gi % C::WSTAGES) : c;
+      const uint32_t wb = w_lo3 + ((slot * C::CHUNK_BYTES) >> 4);
+      const uint32_t acc0 = (c > 0) ? 1u : 0u;
       for (int t = 0; t < mt2; ++t) {
+        const uint32_t ab = a2_lo + ((t * (128 * C::NC * 2)) >> 4);
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a_base = smem_u32(sA2) + (pass == 2 ? C::A2_PLANE : 0) + t * (128 * C::NC * 2);
-          const uint32_t b_base = wbase + (pass == 1 ? C::W3_PLANE : 0);
 #pragma unroll
           for (int ks = 0; ks < C::NC / 16; ++ks)
 #pragma unroll
             for (int hh = 0; hh < C::NSPLIT; ++hh)
-              umma_f16(tmem + C::D2_COL + t * C::COUT_P + hh * C::N2, make_smem_desc(a_base + ks * 4096, 2048, 128),
-                       make_smem_desc(b_base + ks * 2 * LBO_W3 + hh * (C::N2 / 8) * 128, LBO_W3, 128), idesc2,
-                       (c > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+              umma_f16(tmem + C::D2_COL + t * C::COUT_P + hh * C::N2,
+                       desc64(d_hi, ab + (((pass == 2 ? C::A2_PLANE : 0) + ks * 4096) >> 4)),
+                       desc64(d_hi, wb + (((pass == 1 ? C::W3_PLANE : 0) + ks * 2 * LBO_W3 + hh * (C::N2 / 8) * 128) >> 4)),
+                       idesc2, (pass > 0 || ks > 0) ? 1u : acc0);
         }
       }
       umma_commit(smem_u32(&bar_g2));
@@ -594,9 +595,9 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         tc_fence_after_sync();
         gemm2(g, c, mt2);
         if constexpr (C::WSTREAM) {
-          // slot g&1 may be refilled once GEMM2(g) has read W3c (the workers are already past it)
+          // the slot of chunk g may be refilled once GEMM2(g) has read W3c (the workers are already past it)
           mbar_wait(smem_u32(&bar_g2), n_g2i & 1, p.err);
-          if (g + 2 < total_chunks) load_chunk(g + 2);
+          if (g + C::WSTAGES < total_chunks) load_chunk(g + C::WSTAGES);
         }
         ++n_g2i;
       }
@@ -614,18 +615,18 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
 }
 
 // ---- the instantiations used by the backbone (SURVEY.md section 8(a) shape table) -------------------
-//                          CIN CHID NC COUT  W  S  RO FACES RES    STEM   WSTREAM
-using FusedStemB1 = FusedCfg<27, 32, 32, 16, 60, 1, 6, 1, false, true, false>;    // features[0] + features[1]
-using FusedB2 = FusedCfg<16, 96, 32, 24, 60, 2, 5, 1, false, false, false>;       // features[2]
-using FusedB3 = FusedCfg<24, 144, 16, 24, 30, 1, 15, 1, true, false, false>;      // features[3]
-using FusedB4 = FusedCfg<24, 144, 48, 32, 30, 2, 5, 1, false, false, false>;      // features[4]
-using FusedB56 = FusedCfg<32, 192, 32, 32, 15, 1, 15, 1, true, false, false>;     // features[5], [6]
-using FusedB7 = FusedCfg<32, 192, 32, 64, 15, 2, 8, 1, false, false, false>;      // features[7]
-using FusedB8 = FusedCfg<64, 384, 64, 64, 8, 1, 8, 2, true, false, true>;         // features[8..10]
-using FusedB11 = FusedCfg<64, 384, 64, 96, 8, 1, 8, 2, false, false, true>;       // features[11]
-using FusedB12 = FusedCfg<96, 576, 32, 96, 8, 1, 8, 2, true, false, true>;        // features[12], [13]
-using FusedB14 = FusedCfg<96, 576, 32, 160, 8, 2, 4, 2, false, false, true>;      // features[14]
-using FusedB15 = FusedCfg<160, 960, 32, 160, 4, 1, 4, 8, true, false, true>;      // features[15], [16]
-using FusedB17 = FusedCfg<160, 960, 16, 320, 4, 1, 4, 8, false, false, true>;     // features[17]
+//                          CIN CHID NC COUT  W  S  RO FACES RES    STEM   weight ring slots (0 = resident)
+using FusedStemB1 = FusedCfg<27, 32, 32, 16, 60, 1, 6, 1, false, true, 0>;    // features[0] + features[1]
+using FusedB2 = FusedCfg<16, 96, 32, 24, 60, 2, 5, 1, false, false, 0>;       // features[2]
+using FusedB3 = FusedCfg<24, 144, 16, 24, 30, 1, 15, 1, true, false, 0>;      // features[3]
+using FusedB4 = FusedCfg<24, 144, 48, 32, 30, 2, 5, 1, false, false, 0>;      // features[4]
+using FusedB56 = FusedCfg<32, 192, 32, 32, 15, 1, 15, 1, true, false, 0>;     // features[5], [6]
+using FusedB7 = FusedCfg<32, 192, 32, 64, 15, 2, 8, 1, false, false, 0>;      // features[7]
+using FusedB8 = FusedCfg<64, 384, 64, 64, 8, 1, 8, 2, true, false, 3>;         // features[8..10]
+using FusedB11 = FusedCfg<64, 384, 64, 96, 8, 1, 8, 2, false, false, 2>;       // features[11]
+using FusedB12 = FusedCfg<96, 576, 32, 96, 8, 1, 8, 2, true, false, 3>;        // features[12], [13]
+using FusedB14 = FusedCfg<96, 576, 32, 160, 8, 2, 4, 2, false, false, 3>;      // features[14]
+using FusedB15 = FusedCfg<160, 960, 32, 160, 4, 1, 4, 8, true, false, 2>;      // features[15], [16]
+using FusedB17 = FusedCfg<160, 960, 16, 320, 4, 1, 4, 8, false, false, 3>;     // features[17]
 
 }  // namespace syn

@@ -30,6 +30,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+// The two 32-bit halves separately: the MMA issuer keeps `hi` and a base `lo` in registers and only
+// adds (byte offset >> 4) to `lo` per instruction instead of rebuilding the 64-bit descriptor.
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
 // ---- instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, 16-bit x 16-bit -> f32 -------
 __host__ __device__ constexpr uint32_t make_idesc_16b(int M, int N, uint32_t ab_format) {
   return (1u << 4)                     // c_format  = F32
