@@ -11,7 +11,8 @@
 //                          96 KB basis tile (3 planes x hi/lo) stays in smem while the CTA walks over
 //                          the face tiles
 //     warp 16 lane 0: loader + MMA issuer (3 planes x 3 passes x 4 K-steps, N = 64), 2 TMEM buffers
-//     warps 0-15:     epilogue (lane = vertex; four warps per lane quarter split the 64 faces)
+//     warps 0-15:     epilogue in two groups of 8 warps, one per TMEM buffer (lane = vertex; the two
+//                     warps of a lane quarter split the 64 faces)
 // Split-16x3 precision scheme of kernels_tc.cuh; basis rows are pre-scaled per vertex row and alpha
 // per coefficient (both powers of two, folded back exactly in the epilogue / the basis image).
 #pragma once
@@ -86,7 +87,7 @@ struct DenseArgs {
 //   bar_bfull   alpha + pose tile landed                                    loader -> issuer, epilogue
 //   bar_dfull   MMAs of the item complete                                   tcgen05.commit -> epilogue
 //   bar_dfree   epilogue done with the item (TMEM buffer, B slot, and -- at a vertex-tile change --
-//               every epilogue thread has passed its bar_a wait)            512 arrivals -> issuer
+//               the meta rows of its basis tile have been read)              256 arrivals -> issuer
 __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const DenseArgs p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
     for (int i = 0; i < kDnBSlots; ++i) mbar_init(smem_u32(&bar_bfull[i]), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar_dfull[i]), 1);
-      mbar_init(smem_u32(&bar_dfree[i]), kDnEpiWarps * 32);
+      mbar_init(smem_u32(&bar_dfree[i]), kDnEpiWarps * 16);     // one group of 8 warps per TMEM buffer
     }
     fence_mbar_init();
   }
@@ -119,54 +120,59 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
 
   if (warp < kDnEpiWarps) {
     // ------------------------------ epilogue ------------------------------------------------------
-    constexpr int FPT = kDnFaces / (kDnEpiWarps / 4);              // faces per thread (16)
-    const int lane_v = tid & 127, fq = tid >> 7;                   // vertex row of the tile, face group
+    // Two groups of 8 warps: group g owns TMEM buffer g and every item with (i & 1) == g, so that the MMAs
+    // of item i+1 (other buffer, other group) and their completion latency overlap this group's work.
+    // Inside a group: warp & 3 = TMEM lane quarter, (warp >> 2) & 1 = which 32 of the 64 faces.
+    const int grp = warp >> 3, half = (warp >> 2) & 1;
+    const int lane_v = tid & 127;
+    const int vt0 = it0 / p.n_ftiles;
     int cur_vt = -1;
-    uint32_t n_a = 0;
     float ux = 0.f, uy = 0.f, uz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
-    for (int it = it0, i = 0; it < it1; ++it, ++i) {
+    for (int it = it0 + grp, i = grp; it < it1; it += 2, i += 2) {
       const int vt = it / p.n_ftiles, ft = it - vt * p.n_ftiles;
-      const int s = i & 1;
       const uint32_t use_par = (uint32_t)(i >> 1) & 1;
-      if (vt != cur_vt) {                                          // new basis tile: fetch its meta rows
+      const int sb = i % kDnBSlots;
+      mbar_wait(smem_u32(&bar_bfull[sb]), (uint32_t)(i / kDnBSlots) & 1, p.err);   // pose tile visible to this thread
+      mbar_wait(smem_u32(&bar_dfull[grp]), use_par, p.err);
+      tc_fence_after_sync();
+      if (vt != cur_vt) {             // new basis tile: its meta rows (landed before the MMAs of this item ran)
         cur_vt = vt;
-        mbar_wait(smem_u32(&bar_a), n_a & 1, p.err);
-        const float* m = sMeta + (n_a & 1) * (kDnMetaTile / 4);
-        ++n_a;
+        mbar_wait(smem_u32(&bar_a), (uint32_t)(vt - vt0) & 1, p.err);
+        const float* m = sMeta + ((vt - vt0) & 1) * (kDnMetaTile / 4);
         ux = m[0 * 128 + lane_v]; uy = m[1 * 128 + lane_v]; uz = m[2 * 128 + lane_v];
         ox = m[3 * 128 + lane_v]; oy = m[4 * 128 + lane_v]; oz = m[5 * 128 + lane_v];
       }
-      const int sb = i % kDnBSlots;
-      mbar_wait(smem_u32(&bar_bfull[sb]), (uint32_t)(i / kDnBSlots) & 1, p.err);   // pose tile visible to this thread
-      mbar_wait(smem_u32(&bar_dfull[s]), use_par, p.err);
-      tc_fence_after_sync();
-      const float* pose = reinterpret_cast<const float*>(sB + sb * kDnBSlot + kDnBTile) + fq * FPT * 12;
-      const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + s * 192 + fq * FPT;
-      float sx[FPT], sy[FPT], sz[FPT];
-      tmem_ld16(trow, sx);
-      tmem_ld16(trow + 64, sy);
-      tmem_ld16(trow + 128, sz);
       const int v = vt * 128 + lane_v;
-      const int b0 = ft * kDnFaces + fq * FPT;
-      if (v < p.nver) {
 #pragma unroll
-        for (int f = 0; f < FPT; ++f) {
-          if (b0 + f < p.batch) {
-            const float4 r0 = *reinterpret_cast<const float4*>(pose + f * 12);
-            const float4 r1 = *reinterpret_cast<const float4*>(pose + f * 12 + 4);
-            const float4 r2 = *reinterpret_cast<const float4*>(pose + f * 12 + 8);
-            const float X = fmaf(sx[f], ox, ux), Y = fmaf(sy[f], oy, uy), Z = fmaf(sz[f], oz, uz);
-            float vx = fmaf(r0.x, X, fmaf(r0.y, Y, r0.z * Z)) + r0.w;
-            float vy = fmaf(r1.x, X, fmaf(r1.y, Y, r1.z * Z)) + r1.w;
-            float vz = fmaf(r2.x, X, fmaf(r2.y, Y, r2.z * Z)) + r2.w;
-            if (p.transform) vy = (float)(kImg + 1) - vy;          // model_building.py:129,137
-            float* o = p.out + (size_t)(b0 + f) * 3 * p.nver + v;
-            __stcs(o, vx); __stcs(o + p.nver, vy); __stcs(o + 2 * (size_t)p.nver, vz);   // write-once stream
+      for (int rnd = 0; rnd < 2; ++rnd) {                            // 2 x 16 faces per thread
+        const int fofs = half * 32 + rnd * 16;
+        const float* pose = reinterpret_cast<const float*>(sB + sb * kDnBSlot + kDnBTile) + fofs * 12;
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + grp * 192 + fofs;
+        float sx[16], sy[16], sz[16];
+        tmem_ld16(trow, sx);
+        tmem_ld16(trow + 64, sy);
+        tmem_ld16(trow + 128, sz);
+        const int b0 = ft * kDnFaces + fofs;
+        if (v < p.nver) {
+#pragma unroll
+          for (int f = 0; f < 16; ++f) {
+            if (b0 + f < p.batch) {
+              const float4 r0 = *reinterpret_cast<const float4*>(pose + f * 12);
+              const float4 r1 = *reinterpret_cast<const float4*>(pose + f * 12 + 4);
+              const float4 r2 = *reinterpret_cast<const float4*>(pose + f * 12 + 8);
+              const float X = fmaf(sx[f], ox, ux), Y = fmaf(sy[f], oy, uy), Z = fmaf(sz[f], oz, uz);
+              float vx = fmaf(r0.x, X, fmaf(r0.y, Y, r0.z * Z)) + r0.w;
+              float vy = fmaf(r1.x, X, fmaf(r1.y, Y, r1.z * Z)) + r1.w;
+              float vz = fmaf(r2.x, X, fmaf(r2.y, Y, r2.z * Z)) + r2.w;
+              if (p.transform) vy = (float)(kImg + 1) - vy;          // model_building.py:129,137
+              float* o = p.out + (size_t)(b0 + f) * 3 * p.nver + v;
+              __stcs(o, vx); __stcs(o + p.nver, vy); __stcs(o + 2 * (size_t)p.nver, vz);   // write-once stream
+            }
           }
         }
       }
       tc_fence_before_sync();
-      mbar_arrive(smem_u32(&bar_dfree[s]));
+      mbar_arrive(smem_u32(&bar_dfree[grp]));
     }
   } else if (tid == kDnEpiWarps * 32) {
     // ------------------------------ loader + MMA issuer -------------------------------------------
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
       mbar_wait(smem_u32(&bar_dfree[j & 1]), (uint32_t)(j >> 1) & 1, p.err);
     };
     int cur_vt = -1;
-    uint32_t n_a = 0;
+    const int vt0 = it0 / p.n_ftiles;
     for (int k = 0; k < kDnBSlots - 1; ++k)
       if (it0 + k < it1) load_b(it0 + k, k);
     for (int it = it0, i = 0; it < it1; ++it, ++i) {
@@ -195,10 +201,9 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
         cur_vt = vt;
         mbar_expect_tx(smem_u32(&bar_a), kDnATile + kDnMetaTile);
         bulk_g2s(smem_u32(sA), p.basis_img + (size_t)vt * kDnATile, kDnATile, smem_u32(&bar_a));
-        bulk_g2s(smem_u32(sMeta + (n_a & 1) * (kDnMetaTile / 4)), p.meta + (size_t)vt * 6 * 128, kDnMetaTile,
+        bulk_g2s(smem_u32(sMeta + ((vt - vt0) & 1) * (kDnMetaTile / 4)), p.meta + (size_t)vt * 6 * 128, kDnMetaTile,
                  smem_u32(&bar_a));
-        mbar_wait(smem_u32(&bar_a), n_a & 1, p.err);
-        ++n_a;
+        mbar_wait(smem_u32(&bar_a), (uint32_t)(vt - vt0) & 1, p.err);
       }
       const int sb = i % kDnBSlots;
       mbar_wait(smem_u32(&bar_bfull[sb]), (uint32_t)(i / kDnBSlots) & 1, p.err);

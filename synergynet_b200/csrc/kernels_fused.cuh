@@ -270,6 +270,17 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       const int mt1 = (M1 + 127) >> 7;
       const int M2 = nfaces * C::M2F;
       const int mt2 = (M2 + 127) >> 7;
+      // float offset of this thread's pixel of every M-tile inside the hidden window (-1: no such pixel);
+      // identical for every chunk of the tile, so the divisions are done once
+      int hoff[C::MT1];
+#pragma unroll
+      for (int t = 0; t < C::MT1; ++t) {
+        const int m = t * 128 + row;
+        const int f = (C::FACES > 1) ? m / ppf : 0;
+        const int mr = m - f * ppf;
+        const int yl = mr / C::W, xx = mr - yl * C::W;
+        hoff[t] = (m < M1) ? (f * C::HS_FACE + (rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE : -1;
+      }
 
       for (int c = 0; c < C::NCHUNK; ++c, ++g) {
         const int slot = C::WSTREAM ? (int)(g % C::WSTAGES) : c;
@@ -325,12 +336,11 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                   const float4 b1 = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0 + 4);
                   bq[0] = b0.x; bq[1] = b0.y; bq[2] = b0.z; bq[3] = b0.w; bq[4] = b1.x; bq[5] = b1.y; bq[6] = b1.z; bq[7] = b1.w;
                 }
-                const int m = t * 128 + row;
-                if (m < M1) {
-                  const int f = (C::FACES > 1) ? m / ppf : 0;
-                  const int mr = m - f * ppf;
-                  const int yl = mr / C::W, xx = mr - yl * C::W;
-                  float* hrow = sH + (size_t)(f * C::HS_FACE + (rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE + j0;
+                int ho = hoff[0];
+#pragma unroll
+                for (int tt = 1; tt < C::MT1; ++tt) ho = (t == tt) ? hoff[tt] : ho;      // register select, no local array
+                if (ho >= 0) {
+                  float* hrow = sH + ho + j0;
                   *reinterpret_cast<float4*>(hrow) =
                       make_float4(__saturatef(fmaf(__uint_as_float(vr[u][0]), sc1, bq[0])), __saturatef(fmaf(__uint_as_float(vr[u][1]), sc1, bq[1])),
                                   __saturatef(fmaf(__uint_as_float(vr[u][2]), sc1, bq[2])), __saturatef(fmaf(__uint_as_float(vr[u][3]), sc1, bq[3])));
