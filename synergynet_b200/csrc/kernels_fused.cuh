@@ -52,8 +52,12 @@ struct FusedCfg {
   static constexpr int M2_MAX = FACES_ * M2F;
   static constexpr int MT2 = ceil_div_c(M2_MAX, 128);
   static constexpr int HS_COLS = W_ + 2, HS_FACE = RWIN * HS_COLS, HS_PIX = FACES_ * HS_FACE, HS_STRIDE = NC_ + 4;
-  static constexpr int D2_COL = round_up_c(MT1 * NC_, 32);
+  // TMEM columns: two D1 buffers (GEMM1 of chunk c+1/c+2 runs while chunk c is drained), then D2
+  static constexpr int D1_STRIDE = round_up_c(MT1 * NC_, 32);
+  static constexpr int D2_COL = 2 * D1_STRIDE;
   static constexpr int TM_COLS = pow2_cols(D2_COL + MT2 * COUT_P);
+  // how many chunks GEMM1 may run ahead of the workers: 2 (both D1 buffers) unless the weight ring is too short
+  static constexpr int LOOK = (WSTREAM_ == 2) ? 1 : 2;
   // ---- weight image: [b3 | s3] then NCHUNK x { W1c hi, W1c lo, W3c hi, W3c lo, DW rows } -----------
   static constexpr int B3_BYTES = round_up_c(2 * COUT_P * 4, 128);       // [2][COUT_P] fp32: b3, s3
   static constexpr int W1_PLANE = NC_ * CIN_P * 2;                       // bytes, one plane of one chunk
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
   constexpr int SUBS = WPG / 4;                        // sub-groups of 128 threads (one TMEM lane each)
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_wfull[4], bar_x, bar_d1, bar_epi1, bar_a2, bar_g2, bar_d2free, bar_in;
+  __shared__ __align__(8) uint64_t bar_w, bar_wfull[4], bar_x, bar_d1[2], bar_epi1[2], bar_a2, bar_g2, bar_d2free, bar_in;
   __shared__ uint32_t tmem_base_s;
 
   // keep the pointer in the shared address space (no integer round trip): a generic pointer here
@@ -129,8 +133,10 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     mbar_init(smem_u32(&bar_w), 1);
     for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bar_wfull[i]), 1);
     mbar_init(smem_u32(&bar_x), NWT);
-    mbar_init(smem_u32(&bar_d1), 1);
-    mbar_init(smem_u32(&bar_epi1), NWT);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_d1[i]), 1);
+      mbar_init(smem_u32(&bar_epi1[i]), NWT);
+    }
     mbar_init(smem_u32(&bar_a2), NWT);
     mbar_init(smem_u32(&bar_g2), 1);
     mbar_init(smem_u32(&bar_d2free), NWT);
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     for (int i = tid; i < C::HS_PIX * C::HS_STRIDE / 4; i += NWT)
       reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     mbar_wait(smem_u32(&bar_w), 0, p.err);                // b3/s3 (and, if resident, all chunks) landed
-    uint32_t n_d1 = 0, n_g2 = 0, g = 0, n_in = 0;                   // completed-phase counters; g = chunk counter
+    uint32_t n_g2 = 0, g = 0, n_in = 0;                   // completed-phase counters; g = chunk counter
     asm volatile("bar.sync 5, %0;" ::"n"(NWT) : "memory");
 
     // Geometry of a tile + "prep": stage / convert its input into the GEMM1 A operand and publish it.
@@ -287,8 +293,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (g / C::WSTAGES) & 1, p.err);
         const float* dwc = reinterpret_cast<const float*>(sWch + slot * C::CHUNK_BYTES + C::CH_DW);
         // ---- EPI1: D1 -> relu6(s1*D1 + b1) -> hidden window --------------------------------------
-        mbar_wait(smem_u32(&bar_d1), n_d1 & 1, p.err);
-        ++n_d1;
+        const int db = (int)(g & 1);                       // D1 buffer of this chunk; its (g >> 1)-th use
+        mbar_wait(smem_u32(&bar_d1[db]), (g >> 1) & 1, p.err);
         tc_fence_after_sync();
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(TPG) : "memory");   // the group is done reading ITS Hs columns (DW c-1)
         if (c == 0) {
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
               const int e = e0 + u * SUBS;
               if (e < n_e) {                                // warp-uniform
                 const int t = e / KPG, kq = grp * KPG + (e - t * KPG);
-                tmem_ld8_async(tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * C::NC + kq * 8, vr[u]);
+                tmem_ld8_async(tmem + ((uint32_t)((warp & 3) * 32) << 16) + db * C::D1_STRIDE + t * C::NC + kq * 8, vr[u]);
               }
             }
             tmem_wait_ld();
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           }
         }
         tc_fence_before_sync();
-        mbar_arrive(smem_u32(&bar_epi1));
+        mbar_arrive(smem_u32(&bar_epi1[db]));
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(TPG) : "memory");   // the group's channel columns of the window are complete
         // ---- DW: 3x3 depthwise on the window -> A2 operand ----------------------------------------
         if (c > 0) {                                        // A2 is free once GEMM2(c-1) has completed
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     const uint32_t idesc1 = make_idesc_f16(128, C::NC);
     const uint32_t idesc2 = make_idesc_f16(128, C::N2);
     constexpr uint32_t LBO_W1 = (C::NC / 8) * 128, LBO_W3 = (C::COUT_P / 8) * 128;
-    uint32_t n_x = 0, n_epi1 = 0, n_a2 = 0, n_free = 0, n_g2i = 0;
+    uint32_t n_x = 0, n_a2 = 0, n_free = 0, n_g2i = 0;
     uint32_t g = 0;                                          // chunk counter of the current GEMM2
     int ntile_local = 0;
 
@@ -522,6 +528,11 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     const uint32_t w_lo1 = smem_desc_lo(smem_u32(sWch) + C::CH_W1, LBO_W1), w_lo3 = smem_desc_lo(smem_u32(sWch) + C::CH_W3, LBO_W3);
     auto gemm1 = [&](uint32_t gi, int c, int mt1) {
       const int slot = C::WSTREAM ? (int)(gi % C::WSTAGES) : c;
+      const int db = (int)(gi & 1);
+      if (gi >= 2) {                       // the buffer's previous chunk (gi - 2) must have been drained by the workers
+        mbar_wait(smem_u32(&bar_epi1[db]), ((gi - 2) >> 1) & 1, p.err);
+        tc_fence_after_sync();
+      }
       if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (gi / C::WSTAGES) & 1, p.err);
       const uint32_t wb = w_lo1 + ((slot * C::CHUNK_BYTES) >> 4);
       for (int t = 0; t < mt1; ++t) {
@@ -530,12 +541,12 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
           for (int ks = 0; ks < C::CIN_P / 16; ++ks)
-            umma_f16(tmem + t * C::NC, desc64(d_hi, ab + (((pass == 2 ? C::X_PLANE : 0) + ks * 4096) >> 4)),
+            umma_f16(tmem + db * C::D1_STRIDE + t * C::NC, desc64(d_hi, ab + (((pass == 2 ? C::X_PLANE : 0) + ks * 4096) >> 4)),
                      desc64(d_hi, wb + (((pass == 1 ? C::W1_PLANE : 0) + ks * 2 * LBO_W1) >> 4)), idesc1,
                      (pass > 0 || ks > 0) ? 1u : 0u);
         }
       }
-      umma_commit(smem_u32(&bar_d1));
+      umma_commit(smem_u32(&bar_d1[db]));
     };
     auto gemm2 = [&](uint32_t gi, int c, int mt2) {
       const int slot = C::WSTREAM ? (int)(gi % C::WSTAGES) : c;
@@ -588,14 +599,10 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       ++n_x;
       tc_fence_after_sync();
       gemm1(g, 0, mt1);
+      if (C::LOOK >= 2 && C::NCHUNK > 1) gemm1(g + 1, 1, mt1);
       stage_rows(tile + gridDim.x);          // sIn is free again: the conversion of this tile has consumed it
       for (int c = 0; c < C::NCHUNK; ++c, ++g) {
-        if (c + 1 < C::NCHUNK) {
-          mbar_wait(smem_u32(&bar_epi1), n_epi1 & 1, p.err);    // D1 drained by the workers
-          ++n_epi1;
-          tc_fence_after_sync();
-          gemm1(g + 1, c + 1, mt1);
-        }
+        if (C::LOOK == 1 && c + 1 < C::NCHUNK) gemm1(g + 1, c + 1, mt1);     // waits until chunk g-1 is drained
         mbar_wait(smem_u32(&bar_a2), n_a2 & 1, p.err);
         ++n_a2;
         if (c == 0 && ntile_local > 0) {                         // D2 of the previous tile drained
@@ -610,10 +617,9 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           if (g + C::WSTAGES < total_chunks) load_chunk(g + C::WSTAGES);
         }
         ++n_g2i;
+        // chunk g was drained before the workers arrived on bar_a2, so its D1 buffer can take chunk g+2 now
+        if (C::LOOK >= 2 && c + 2 < C::NCHUNK) gemm1(g + 2, c + 2, mt1);
       }
-      // the last chunk's EPI1 arrival is not consumed above: keep the phase counter in step
-      mbar_wait(smem_u32(&bar_epi1), n_epi1 & 1, p.err);
-      ++n_epi1;
     }
   }
   tc_fence_before_sync();

@@ -82,30 +82,21 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes or ~hint_ns
-// elapse, so a waiting warp does not burn issue slots polling (an un-hinted spin loop was measured at 25 %
-// of all issued instructions in the fused kernel).
-__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(hint_ns)
-      : "memory");
-  return ok != 0;
-}
+// Slow path: plain try_wait polling (a suspend-time hint was tried and measured ~6 % slower end to end:
+// wake-up latency matters more than the issue slots the polling warps take).  The sticky flag (a global
+// load) and the wall clock are only looked at every 256 polls.
 __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* err_flag) {
   const uint64_t t0 = globaltimer_ns();
-  while (!mbar_try_wait_hint(bar, parity, 1000000u)) {       // parked for up to ~1 ms per iteration
-    if (err_flag != nullptr && *reinterpret_cast<volatile int*>(err_flag) != 0) return false;
-    if (globaltimer_ns() - t0 > 2000000000ull) {
-      if (err_flag != nullptr) atomicExch(err_flag, 1);
-      return false;
+  for (uint32_t it = 1;; ++it) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((it & 255u) == 0) {
+      if (err_flag != nullptr && *reinterpret_cast<volatile int*>(err_flag) != 0) return false;
+      if (globaltimer_ns() - t0 > 2000000000ull) {
+        if (err_flag != nullptr) atomicExch(err_flag, 1);
+        return false;
+      }
     }
   }
-  return true;
 }
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err_flag) {
   if (mbar_try_wait(bar, parity)) return true;
