@@ -10,7 +10,7 @@ import os
 import re
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, 'libsynergy_b200.so')
+LIB_PATH = os.environ.get('SYN_LIB_PATH') or os.path.join(_PKG, 'libsynergy_b200.so')   # override: A/B runs of two builds
 HEADER_PATH = os.path.join(_PKG, '..', 'include', 'synergy_b200.h')
 
 SYN_OK = 0

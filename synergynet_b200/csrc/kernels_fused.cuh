@@ -27,6 +27,18 @@
 namespace syn {
 
 constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
+#ifndef SYN_EB_STEM
+#define SYN_EB_STEM 1
+#endif
+#ifndef SYN_EB_WIDE
+#define SYN_EB_WIDE 1
+#endif
+#ifndef SYN_EB_MID
+#define SYN_EB_MID 1
+#endif
+#ifndef SYN_EB_SMALL
+#define SYN_EB_SMALL 1
+#endif
 constexpr int round_up_c(int a, int b) { return ceil_div_c(a, b) * b; }
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
@@ -52,12 +64,10 @@ struct FusedCfg {
   static constexpr int M2_MAX = FACES_ * M2F;
   static constexpr int MT2 = ceil_div_c(M2_MAX, 128);
   static constexpr int HS_COLS = W_ + 2, HS_FACE = RWIN * HS_COLS, HS_PIX = FACES_ * HS_FACE, HS_STRIDE = NC_ + 4;
-  // TMEM columns: two D1 buffers (GEMM1 of chunk c+1/c+2 runs while chunk c is drained), then D2
-  static constexpr int D1_STRIDE = round_up_c(MT1 * NC_, 32);
-  static constexpr int D2_COL = 2 * D1_STRIDE;
+  static constexpr int D2_COL = round_up_c(MT1 * NC_, 32);
+  // EPI1 TMEM loads kept in flight per wait (measured per map size, scripts/ab_variants.sh)
+  static constexpr int EPI1_BATCH = STEM_ ? SYN_EB_STEM : W_ >= 30 ? SYN_EB_WIDE : W_ >= 15 ? SYN_EB_MID : SYN_EB_SMALL;
   static constexpr int TM_COLS = pow2_cols(D2_COL + MT2 * COUT_P);
-  // how many chunks GEMM1 may run ahead of the workers: 2 (both D1 buffers) unless the weight ring is too short
-  static constexpr int LOOK = (WSTREAM_ == 2) ? 1 : 2;
   // ---- weight image: [b3 | s3] then NCHUNK x { W1c hi, W1c lo, W3c hi, W3c lo, DW rows } -----------
   static constexpr int B3_BYTES = round_up_c(2 * COUT_P * 4, 128);       // [2][COUT_P] fp32: b3, s3
   static constexpr int W1_PLANE = NC_ * CIN_P * 2;                       // bytes, one plane of one chunk
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
   constexpr int SUBS = WPG / 4;                        // sub-groups of 128 threads (one TMEM lane each)
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_wfull[4], bar_x, bar_d1[2], bar_epi1[2], bar_a2, bar_g2, bar_d2free, bar_in;
+  __shared__ __align__(8) uint64_t bar_w, bar_wfull[4], bar_x, bar_d1, bar_epi1, bar_a2, bar_g2, bar_d2free, bar_in;
   __shared__ uint32_t tmem_base_s;
 
   // keep the pointer in the shared address space (no integer round trip): a generic pointer here
@@ -133,10 +143,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     mbar_init(smem_u32(&bar_w), 1);
     for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bar_wfull[i]), 1);
     mbar_init(smem_u32(&bar_x), NWT);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bar_d1[i]), 1);
-      mbar_init(smem_u32(&bar_epi1[i]), NWT);
-    }
+    mbar_init(smem_u32(&bar_d1), 1);
+    mbar_init(smem_u32(&bar_epi1), NWT);
     mbar_init(smem_u32(&bar_a2), NWT);
     mbar_init(smem_u32(&bar_g2), 1);
     mbar_init(smem_u32(&bar_d2free), NWT);
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     for (int i = tid; i < C::HS_PIX * C::HS_STRIDE / 4; i += NWT)
       reinterpret_cast<float4*>(sH)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     mbar_wait(smem_u32(&bar_w), 0, p.err);                // b3/s3 (and, if resident, all chunks) landed
-    uint32_t n_g2 = 0, g = 0, n_in = 0;                   // completed-phase counters; g = chunk counter
+    uint32_t n_d1 = 0, n_g2 = 0, g = 0, n_in = 0;                   // completed-phase counters; g = chunk counter
     asm volatile("bar.sync 5, %0;" ::"n"(NWT) : "memory");
 
     // Geometry of a tile + "prep": stage / convert its input into the GEMM1 A operand and publish it.
@@ -276,25 +284,14 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       const int mt1 = (M1 + 127) >> 7;
       const int M2 = nfaces * C::M2F;
       const int mt2 = (M2 + 127) >> 7;
-      // float offset of this thread's pixel of every M-tile inside the hidden window (-1: no such pixel);
-      // identical for every chunk of the tile, so the divisions are done once
-      int hoff[C::MT1];
-#pragma unroll
-      for (int t = 0; t < C::MT1; ++t) {
-        const int m = t * 128 + row;
-        const int f = (C::FACES > 1) ? m / ppf : 0;
-        const int mr = m - f * ppf;
-        const int yl = mr / C::W, xx = mr - yl * C::W;
-        hoff[t] = (m < M1) ? (f * C::HS_FACE + (rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE : -1;
-      }
 
       for (int c = 0; c < C::NCHUNK; ++c, ++g) {
         const int slot = C::WSTREAM ? (int)(g % C::WSTAGES) : c;
         if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (g / C::WSTAGES) & 1, p.err);
         const float* dwc = reinterpret_cast<const float*>(sWch + slot * C::CHUNK_BYTES + C::CH_DW);
         // ---- EPI1: D1 -> relu6(s1*D1 + b1) -> hidden window --------------------------------------
-        const int db = (int)(g & 1);                       // D1 buffer of this chunk; its (g >> 1)-th use
-        mbar_wait(smem_u32(&bar_d1[db]), (g >> 1) & 1, p.err);
+        mbar_wait(smem_u32(&bar_d1), n_d1 & 1, p.err);
+        ++n_d1;
         tc_fence_after_sync();
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(TPG) : "memory");   // the group is done reading ITS Hs columns (DW c-1)
         if (c == 0) {
@@ -320,19 +317,20 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           int cur_k = -1;
           float bq[8];
           const int n_e = mt1 * KPG;
-          for (int e0 = gsub; e0 < n_e; e0 += 4 * SUBS) {
-            uint32_t vr[4][8];
+          constexpr int EB = C::EPI1_BATCH;
+          for (int e0 = gsub; e0 < n_e; e0 += EB * SUBS) {
+            uint32_t vr[EB][8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {                   // up to four TMEM loads in flight, one wait
+            for (int u = 0; u < EB; ++u) {                  // up to EB TMEM loads in flight, one wait
               const int e = e0 + u * SUBS;
               if (e < n_e) {                                // warp-uniform
                 const int t = e / KPG, kq = grp * KPG + (e - t * KPG);
-                tmem_ld8_async(tmem + ((uint32_t)((warp & 3) * 32) << 16) + db * C::D1_STRIDE + t * C::NC + kq * 8, vr[u]);
+                tmem_ld8_async(tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * C::NC + kq * 8, vr[u]);
               }
             }
             tmem_wait_ld();
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < EB; ++u) {
               const int e = e0 + u * SUBS;
               if (e < n_e) {
                 const int t = e / KPG, kq = grp * KPG + (e - t * KPG), j0 = kq * 8;
@@ -342,11 +340,12 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                   const float4 b1 = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0 + 4);
                   bq[0] = b0.x; bq[1] = b0.y; bq[2] = b0.z; bq[3] = b0.w; bq[4] = b1.x; bq[5] = b1.y; bq[6] = b1.z; bq[7] = b1.w;
                 }
-                int ho = hoff[0];
-#pragma unroll
-                for (int tt = 1; tt < C::MT1; ++tt) ho = (t == tt) ? hoff[tt] : ho;      // register select, no local array
-                if (ho >= 0) {
-                  float* hrow = sH + ho + j0;
+                const int m = t * 128 + row;
+                if (m < M1) {
+                  const int f = (C::FACES > 1) ? m / ppf : 0;
+                  const int mr = m - f * ppf;
+                  const int yl = mr / C::W, xx = mr - yl * C::W;
+                  float* hrow = sH + (size_t)(f * C::HS_FACE + (rf - iy0 + yl) * C::HS_COLS + xx + 1) * C::HS_STRIDE + j0;
                   *reinterpret_cast<float4*>(hrow) =
                       make_float4(__saturatef(fmaf(__uint_as_float(vr[u][0]), sc1, bq[0])), __saturatef(fmaf(__uint_as_float(vr[u][1]), sc1, bq[1])),
                                   __saturatef(fmaf(__uint_as_float(vr[u][2]), sc1, bq[2])), __saturatef(fmaf(__uint_as_float(vr[u][3]), sc1, bq[3])));
@@ -359,7 +358,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           }
         }
         tc_fence_before_sync();
-        mbar_arrive(smem_u32(&bar_epi1[db]));
+        mbar_arrive(smem_u32(&bar_epi1));
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(TPG) : "memory");   // the group's channel columns of the window are complete
         // ---- DW: 3x3 depthwise on the window -> A2 operand ----------------------------------------
         if (c > 0) {                                        // A2 is free once GEMM2(c-1) has completed
@@ -380,6 +379,12 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           constexpr int NR = C::STRIDE + 3;                                // window rows of a row pair
           const int per_kg = nfaces * PER_FACE;
           const int l8 = tid & 7, lx = l8 % GX, ly = l8 / GX;
+          // Stride 2: the window pixels of neighbouring lanes lie 2 * HS_STRIDE floats apart, an even number
+          // of 16-byte bank groups, so lanes l and l+4 of a quarter-warp would collide on every window load.
+          // Lanes 4-7 therefore take the two channel quads of their octet in the opposite order (q0, q1 are
+          // the float offsets of the first / second quad); only the final operand store swaps them back.
+          const bool swz = (C::STRIDE == 2) && (l8 & 4);
+          const int q0 = swz ? 4 : 0, q1 = 4 - q0;
           const int kg_end = (grp + 1) * KPG;                              // this group's channel octets
           int kg = grp * KPG, it = gtid >> 3;
           while (it >= per_kg && kg < kg_end) { it -= per_kg; ++kg; }
@@ -393,8 +398,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
               const bool two = (oy + 1 < C::RO);                           // second output row exists
               float acc0[8], acc1[8];
               {
-                const float4 a = *reinterpret_cast<const float4*>(wbase + 9 * C::NC);
-                const float4 e = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + 4);
+                const float4 a = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q0);
+                const float4 e = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q1);
                 acc0[0] = a.x; acc0[1] = a.y; acc0[2] = a.z; acc0[3] = a.w; acc0[4] = e.x; acc0[5] = e.y; acc0[6] = e.z; acc0[7] = e.w;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc1[j] = acc0[j];
@@ -404,8 +409,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                 float w[3][8];
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
-                  const float4 a = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC);
-                  const float4 e = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + 4);
+                  const float4 a = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q0);
+                  const float4 e = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q1);
                   w[dy][0] = a.x; w[dy][1] = a.y; w[dy][2] = a.z; w[dy][3] = a.w;
                   w[dy][4] = e.x; w[dy][5] = e.y; w[dy][6] = e.z; w[dy][7] = e.w;
                 }
@@ -413,8 +418,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                 for (int wr = 0; wr < NR; ++wr) {
                   if (wr >= 3 && !two) continue;                           // rows only the (absent) second pixel needs
                   const float* hp = h0 + (wr * C::HS_COLS + dx) * C::HS_STRIDE;
-                  const float4 a = *reinterpret_cast<const float4*>(hp);
-                  const float4 e = *reinterpret_cast<const float4*>(hp + 4);
+                  const float4 a = *reinterpret_cast<const float4*>(hp + q0);
+                  const float4 e = *reinterpret_cast<const float4*>(hp + q1);
                   const float d[8] = {a.x, a.y, a.z, a.w, e.x, e.y, e.z, e.w};
                   if (wr < 3) {
 #pragma unroll
@@ -434,8 +439,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                 for (int j = 0; j < 4; ++j)
                   split2_f16<false>(__saturatef(acc0[2 * j]) * kOut, __saturatef(acc0[2 * j + 1]) * kOut, h[j], l[j]);
                 uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16;
-                *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = make_uint4(l[0], l[1], l[2], l[3]);
+                *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
               }
               if (two) {
                 const int m3 = m2 + C::WO;
@@ -444,8 +449,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                 for (int j = 0; j < 4; ++j)
                   split2_f16<false>(__saturatef(acc1[2 * j]) * kOut, __saturatef(acc1[2 * j + 1]) * kOut, h[j], l[j]);
                 uint8_t* dst = sA2 + (m3 >> 7) * (128 * C::NC * 2) + ((m3 & 127) >> 3) * 128 + kg * 2048 + (m3 & 7) * 16;
-                *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = make_uint4(l[0], l[1], l[2], l[3]);
+                *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
               }
             }
             it += TPG / 8;
@@ -518,7 +523,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     const uint32_t idesc1 = make_idesc_f16(128, C::NC);
     const uint32_t idesc2 = make_idesc_f16(128, C::N2);
     constexpr uint32_t LBO_W1 = (C::NC / 8) * 128, LBO_W3 = (C::COUT_P / 8) * 128;
-    uint32_t n_x = 0, n_a2 = 0, n_free = 0, n_g2i = 0;
+    uint32_t n_x = 0, n_epi1 = 0, n_a2 = 0, n_free = 0, n_g2i = 0;
     uint32_t g = 0;                                          // chunk counter of the current GEMM2
     int ntile_local = 0;
 
@@ -528,11 +533,6 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     const uint32_t w_lo1 = smem_desc_lo(smem_u32(sWch) + C::CH_W1, LBO_W1), w_lo3 = smem_desc_lo(smem_u32(sWch) + C::CH_W3, LBO_W3);
     auto gemm1 = [&](uint32_t gi, int c, int mt1) {
       const int slot = C::WSTREAM ? (int)(gi % C::WSTAGES) : c;
-      const int db = (int)(gi & 1);
-      if (gi >= 2) {                       // the buffer's previous chunk (gi - 2) must have been drained by the workers
-        mbar_wait(smem_u32(&bar_epi1[db]), ((gi - 2) >> 1) & 1, p.err);
-        tc_fence_after_sync();
-      }
       if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (gi / C::WSTAGES) & 1, p.err);
       const uint32_t wb = w_lo1 + ((slot * C::CHUNK_BYTES) >> 4);
       for (int t = 0; t < mt1; ++t) {
@@ -541,12 +541,12 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
           for (int ks = 0; ks < C::CIN_P / 16; ++ks)
-            umma_f16(tmem + db * C::D1_STRIDE + t * C::NC, desc64(d_hi, ab + (((pass == 2 ? C::X_PLANE : 0) + ks * 4096) >> 4)),
+            umma_f16(tmem + t * C::NC, desc64(d_hi, ab + (((pass == 2 ? C::X_PLANE : 0) + ks * 4096) >> 4)),
                      desc64(d_hi, wb + (((pass == 1 ? C::W1_PLANE : 0) + ks * 2 * LBO_W1) >> 4)), idesc1,
                      (pass > 0 || ks > 0) ? 1u : 0u);
         }
       }
-      umma_commit(smem_u32(&bar_d1[db]));
+      umma_commit(smem_u32(&bar_d1));
     };
     auto gemm2 = [&](uint32_t gi, int c, int mt2) {
       const int slot = C::WSTREAM ? (int)(gi % C::WSTAGES) : c;
@@ -599,10 +599,14 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       ++n_x;
       tc_fence_after_sync();
       gemm1(g, 0, mt1);
-      if (C::LOOK >= 2 && C::NCHUNK > 1) gemm1(g + 1, 1, mt1);
       stage_rows(tile + gridDim.x);          // sIn is free again: the conversion of this tile has consumed it
       for (int c = 0; c < C::NCHUNK; ++c, ++g) {
-        if (C::LOOK == 1 && c + 1 < C::NCHUNK) gemm1(g + 1, c + 1, mt1);     // waits until chunk g-1 is drained
+        if (c + 1 < C::NCHUNK) {
+          mbar_wait(smem_u32(&bar_epi1), n_epi1 & 1, p.err);    // D1 drained by the workers
+          ++n_epi1;
+          tc_fence_after_sync();
+          gemm1(g + 1, c + 1, mt1);
+        }
         mbar_wait(smem_u32(&bar_a2), n_a2 & 1, p.err);
         ++n_a2;
         if (c == 0 && ntile_local > 0) {                         // D2 of the previous tile drained
@@ -617,9 +621,10 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           if (g + C::WSTAGES < total_chunks) load_chunk(g + C::WSTAGES);
         }
         ++n_g2i;
-        // chunk g was drained before the workers arrived on bar_a2, so its D1 buffer can take chunk g+2 now
-        if (C::LOOK >= 2 && c + 2 < C::NCHUNK) gemm1(g + 2, c + 2, mt1);
       }
+      // the last chunk's EPI1 arrival is not consumed above: keep the phase counter in step
+      mbar_wait(smem_u32(&bar_epi1), n_epi1 & 1, p.err);
+      ++n_epi1;
     }
   }
   tc_fence_before_sync();

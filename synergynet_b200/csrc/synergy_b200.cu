@@ -940,12 +940,23 @@ int syn_forward_landmarks_u8(syn_handle_t* h, const uint8_t* x_u8, int batch, fl
   return run_reconstruct(h, p, batch, 0, 1, 1, lmk, (cudaStream_t)stream);
 }
 
-// Shared host pipeline: chunks of <= 256 faces, H2D on s_copy overlapped with compute on s_compute.
+// Faces per pipeline chunk: large enough that the 8x8 / 4x4 blocks still fill the 148 SMs, small enough
+// that the first copy does not sit exposed.  SYN_HOST_CHUNK overrides it for measurements.
+static int host_chunk_faces() {
+  static const int v = [] {
+    const char* e = getenv("SYN_HOST_CHUNK");
+    const int c = e ? atoi(e) : 0;
+    return c > 0 ? c : 512;
+  }();
+  return v;
+}
+
+// Shared host pipeline: chunks of host_chunk_faces() faces, H2D on s_copy overlapped with compute on s_compute.
 static int forward_landmarks_host_impl(syn_handle_t* h, const void* x_host, int is_u8, int batch,
                                        float* params_host, float* lmk_host) {
   if (h->n_pts <= 0) return fail(SYN_ERR_STATE, "forward_landmarks_host: sparse basis not set");
   DeviceGuard g(h->device);
-  const int chunk = std::min(batch, 256);
+  const int chunk = std::min(batch, host_chunk_faces());
   const size_t x_face = (size_t)3 * kImg * kImg;
   const size_t elt = is_u8 ? 1 : sizeof(float);
   const size_t lmk_face = (size_t)3 * h->n_pts;
