@@ -500,8 +500,12 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       tc_fence_before_sync();
       mbar_arrive(smem_u32(&bar_d2free));
     }
-  } else if (tid == NWT) {
+  } else if (warp == NWW) {
     // =============================== MMA issuer / weight loader ====================================
+    // The whole warp runs this control flow convergently and every batch of tcgen05.mma / bulk copies sits
+    // under one elect.sync: the compiler then knows a single thread issues them (no per-instruction
+    // uniformisation loop, descriptors straight from uniform registers).  Measured with tools/umma_timing:
+    // ~170 cycles per MMA from a `tid == X` branch against 32 + N/4 (the operand-read floor) this way.
     const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const uint32_t total_chunks = (uint32_t)my_tiles * C::NCHUNK;
     auto load_chunk = [&](uint32_t gi) {                     // streaming: chunk gi -> slot gi % WSTAGES
@@ -510,15 +514,18 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       bulk_g2s(smem_u32(sWch + slot * C::CHUNK_BYTES), p.wimg + C::B3_BYTES + (size_t)c * C::CHUNK_BYTES, C::CHUNK_BYTES,
                smem_u32(&bar_wfull[slot]));
     };
-    if constexpr (C::WSTREAM) {
-      mbar_expect_tx(smem_u32(&bar_w), C::B3_BYTES);
-      bulk_g2s(smem_u32(smem + C::S_B3), p.wimg, C::B3_BYTES, smem_u32(&bar_w));
-      for (uint32_t k = 0; k < (uint32_t)C::WSTAGES; ++k)
-        if (total_chunks > k) load_chunk(k);
-    } else {
-      mbar_expect_tx(smem_u32(&bar_w), C::W_BYTES);
-      bulk_g2s(smem_u32(smem + C::S_B3), p.wimg, C::W_BYTES, smem_u32(&bar_w));
+    if (elect_one()) {
+      if constexpr (C::WSTREAM) {
+        mbar_expect_tx(smem_u32(&bar_w), C::B3_BYTES);
+        bulk_g2s(smem_u32(smem + C::S_B3), p.wimg, C::B3_BYTES, smem_u32(&bar_w));
+        for (uint32_t k = 0; k < (uint32_t)C::WSTAGES; ++k)
+          if (total_chunks > k) load_chunk(k);
+      } else {
+        mbar_expect_tx(smem_u32(&bar_w), C::W_BYTES);
+        bulk_g2s(smem_u32(smem + C::S_B3), p.wimg, C::W_BYTES, smem_u32(&bar_w));
+      }
     }
+    __syncwarp();
     mbar_wait(smem_u32(&bar_w), 0, p.err);
     const uint32_t idesc1 = make_idesc_f16(128, C::NC);
     const uint32_t idesc2 = make_idesc_f16(128, C::N2);
@@ -535,6 +542,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       const int slot = C::WSTREAM ? (int)(gi % C::WSTAGES) : c;
       if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (gi / C::WSTAGES) & 1, p.err);
       const uint32_t wb = w_lo1 + ((slot * C::CHUNK_BYTES) >> 4);
+      if (elect_one()) {
       for (int t = 0; t < mt1; ++t) {
         const uint32_t ab = xa_lo + ((t * (128 * C::CIN_P * 2)) >> 4);
 #pragma unroll
@@ -547,11 +555,14 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         }
       }
       umma_commit(smem_u32(&bar_d1));
+      }
+      __syncwarp();
     };
     auto gemm2 = [&](uint32_t gi, int c, int mt2) {
       const int slot = C::WSTREAM ? (int)(gi % C::WSTAGES) : c;
       const uint32_t wb = w_lo3 + ((slot * C::CHUNK_BYTES) >> 4);
       const uint32_t acc0 = (c > 0) ? 1u : 0u;
+      if (elect_one()) {
       for (int t = 0; t < mt2; ++t) {
         const uint32_t ab = a2_lo + ((t * (128 * C::NC * 2)) >> 4);
 #pragma unroll
@@ -567,12 +578,15 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         }
       }
       umma_commit(smem_u32(&bar_g2));
+      }
+      __syncwarp();
     };
 
     // stem, fp32 crops: bulk-copy (TMA) the crop rows of a tile into sIn, one tile ahead of the workers
     auto stage_rows = [&](int tile) {
       if constexpr (C::STEM) {
         if (p.x_u8 != nullptr || tile >= ntiles) return;
+        if (!elect_one()) return;
         const int fgq = tile / C::STRIPS, spq = tile - fgq * C::STRIPS;
         const int iy0q = spq * C::RO * C::STRIDE - 1;
         const int rfq = max(iy0q, 0), rlq = min(iy0q + C::RWIN - 1, C::W - 1);
@@ -618,7 +632,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         if constexpr (C::WSTREAM) {
           // the slot of chunk g may be refilled once GEMM2(g) has read W3c (the workers are already past it)
           mbar_wait(smem_u32(&bar_g2), n_g2i & 1, p.err);
-          if (g + C::WSTAGES < total_chunks) load_chunk(g + C::WSTAGES);
+          if (g + C::WSTAGES < total_chunks && elect_one()) load_chunk(g + C::WSTAGES);
+          __syncwarp();
         }
         ++n_g2i;
       }

@@ -105,6 +105,14 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
 
 // ---- proxies / fences ----------------------------------------------------------------------------
 // generic-proxy st.shared -> visible to the async proxy (tcgen05.mma / bulk copies)
+// One lane of a converged warp (elect.sync, full mask).  Code under `if (elect_one())` is known to the
+// compiler to run on a single thread, which is what lets tcgen05.mma take uniform-register operands directly.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
