@@ -107,7 +107,22 @@ struct FusedArgs {
   float* y;              // NHWC (B,WO,WO,COUT)
   int batch;
   int* err;
+#ifdef SYN_FUSED_TRACE
+  int trace_id;          // backbone block of this launch (1..17)
+#endif
 };
+
+// Phase trace (debug builds only, -DSYN_FUSED_TRACE): clock64 stamps of CTA 0's second tile, one row of 8
+// events per (block, role, chunk); read back with syn_debug_read_trace.  role 0 = worker thread 0, 1 = issuer.
+#ifdef SYN_FUSED_TRACE
+__device__ long long g_fused_trace[18 * 2 * 64 * 8];
+#define SYN_TRACE(role, chunk, ev)                                                                        \
+  do {                                                                                                    \
+    if (trace_on) g_fused_trace[((p.trace_id * 2 + (role)) * 64 + (chunk)) * 8 + (ev)] = clock64();      \
+  } while (0)
+#else
+#define SYN_TRACE(role, chunk, ev) do { } while (0)
+#endif
 
 // NWW = worker warps (multiple of 4: TMEM lane quarter = warp % 4); the issuer is warp NWW.
 template <class C, int NWW>
@@ -280,6 +295,10 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       const int iy0 = oy0 * C::STRIDE - 1;
       const int rf = max(iy0, 0), rl = min(iy0 + C::RWIN - 1, C::W - 1);
       const int ppf = (rl - rf + 1) * C::W;               // valid input pixels per face
+#ifdef SYN_FUSED_TRACE
+      const bool trace_on = blockIdx.x == 0 && tile == (int)gridDim.x && tid == 0;
+#endif
+      SYN_TRACE(0, 63, 0);
       const int M1 = nfaces * ppf;
       const int mt1 = (M1 + 127) >> 7;
       const int M2 = nfaces * C::M2F;
@@ -289,11 +308,14 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         const int slot = C::WSTREAM ? (int)(g % C::WSTAGES) : c;
         if constexpr (C::WSTREAM) mbar_wait(smem_u32(&bar_wfull[slot]), (g / C::WSTAGES) & 1, p.err);
         const float* dwc = reinterpret_cast<const float*>(sWch + slot * C::CHUNK_BYTES + C::CH_DW);
+        SYN_TRACE(0, c, 0);
         // ---- EPI1: D1 -> relu6(s1*D1 + b1) -> hidden window --------------------------------------
         mbar_wait(smem_u32(&bar_d1), n_d1 & 1, p.err);
         ++n_d1;
         tc_fence_after_sync();
+        SYN_TRACE(0, c, 1);
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(TPG) : "memory");   // the group is done reading ITS Hs columns (DW c-1)
+        SYN_TRACE(0, c, 2);
         if (c == 0) {
           // ---- strip mode: window rows outside the image must read as zero (may hold a previous tile);
           //      every group clears its own channel columns
@@ -357,6 +379,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
             }
           }
         }
+        SYN_TRACE(0, c, 3);
         tc_fence_before_sync();
         mbar_arrive(smem_u32(&bar_epi1));
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(TPG) : "memory");   // the group's channel columns of the window are complete
@@ -365,6 +388,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           mbar_wait(smem_u32(&bar_g2), n_g2 & 1, p.err);
           ++n_g2;
         }
+        SYN_TRACE(0, c, 4);
         {
           // Item = (8 hidden channels, two vertically adjacent output rows, 8 lanes along x): the 3x3
           // windows of the two rows share (S=1: 2 of 4, S=2: 1 of 5) input rows and all nine tap vectors,
@@ -374,9 +398,14 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           constexpr int NKG = C::NC / 8;
           constexpr int GX = (C::WO >= 8) ? 8 : 4, GY = 8 / GX;            // quarter-warp footprint
           constexpr int XG = (C::WO + GX - 1) / GX;                        // x groups per output row
-          constexpr int RP = (C::RO + 1) / 2, RPG = (RP + GY - 1) / GY;    // row pairs, groups of them
+          // small maps (8x8, 4x4) have fewer row-pair items than worker threads: one output row per item
+          // there, so that every thread has work and the per-chunk dependency chain is half as long
+          // (measured: pays when at most a quarter of the threads would have a row-pair item, blocks 7/14/17;
+          // with half of them busy the extra window loads of single rows cost more than the idle warps)
+          constexpr int RPI = (4 * C::FACES * ((C::RO + 1) / 2) * ((C::WO + GX - 1) / GX) * GX * NKG <= NWT) ? 1 : 2;
+          constexpr int RP = (C::RO + RPI - 1) / RPI, RPG = (RP + GY - 1) / GY;   // row pairs (rows), groups of them
           constexpr int PER_FACE = XG * RPG;
-          constexpr int NR = C::STRIDE + 3;                                // window rows of a row pair
+          constexpr int NR = (RPI - 1) * C::STRIDE + 3;                    // window rows of an item
           const int per_kg = nfaces * PER_FACE;
           const int l8 = tid & 7, lx = l8 % GX, ly = l8 / GX;
           // Stride 2: the window pixels of neighbouring lanes lie 2 * HS_STRIDE floats apart, an even number
@@ -391,11 +420,13 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           while (kg < kg_end) {
             const int f = it / PER_FACE, r2 = it - f * PER_FACE;
             const int rpg = r2 / XG, xg = r2 - rpg * XG;
-            const int ox = xg * GX + lx, oy = 2 * (rpg * GY + ly);
+            // single rows with GY == 2: the two rows of a quarter-warp lie RPG rows apart (an even number),
+            // which keeps the two half-rows of lanes on disjoint bank groups
+            const int ox = xg * GX + lx, oy = (RPI == 2) ? 2 * (rpg * GY + ly) : rpg + RPG * ly;
             if (ox < C::WO && oy < C::RO) {
               const float* wbase = dwc + kg * 8;
               const float* h0 = sH + (size_t)(f * C::HS_FACE + (oy * C::STRIDE) * C::HS_COLS + ox * C::STRIDE) * C::HS_STRIDE + kg * 8;
-              const bool two = (oy + 1 < C::RO);                           // second output row exists
+              const bool two = (RPI == 2) && (oy + 1 < C::RO);             // second output row exists
               float acc0[8], acc1[8];
               {
                 const float4 a = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q0);
@@ -425,7 +456,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
 #pragma unroll
                     for (int j = 0; j < 8; ++j) acc0[j] = fmaf(d[j], w[wr][j], acc0[j]);
                   }
-                  if (wr >= C::STRIDE) {
+                  if (RPI == 2 && wr >= C::STRIDE) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) acc1[j] = fmaf(d[j], w[wr - C::STRIDE][j], acc1[j]);
                   }
@@ -457,15 +488,19 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
             while (it >= per_kg && kg < kg_end) { it -= per_kg; ++kg; }
           }
         }
+        SYN_TRACE(0, c, 5);
         fence_proxy_async_smem();
         mbar_arrive(smem_u32(&bar_a2));
       }
+      SYN_TRACE(0, 63, 1);
 
       if (tile + (int)gridDim.x < ntiles) prep(tile + gridDim.x);   // Xs is free: every GEMM1 of this tile is done
       // ---- EPI2: s3*D2 + b3 (+ skip) -> global NHWC --------------------------------------------------
+      SYN_TRACE(0, 63, 2);
       mbar_wait(smem_u32(&bar_g2), n_g2 & 1, p.err);
       ++n_g2;
       tc_fence_after_sync();
+      SYN_TRACE(0, 63, 3);
       {
         constexpr int JW = (C::COUT_P % 32 == 0 && C::MT2 * (C::COUT_P / 32) >= 2 * NWG) ? 32
                            : (C::MT2 * (C::COUT_P / 16) >= 2 * NWG) ? 16 : 8;
@@ -497,6 +532,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           }
         }
       }
+      SYN_TRACE(0, 63, 4);
       tc_fence_before_sync();
       mbar_arrive(smem_u32(&bar_d2free));
     }
@@ -609,17 +645,26 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       const int rf = max(iy0, 0), rl = min(iy0 + C::RWIN - 1, C::W - 1);
       const int mt1 = (nfaces * (rl - rf + 1) * C::W + 127) >> 7;
       const int mt2 = (nfaces * C::M2F + 127) >> 7;
+#ifdef SYN_FUSED_TRACE
+      const bool trace_on = blockIdx.x == 0 && tile == (int)gridDim.x && tid == NWT;
+#endif
+      SYN_TRACE(1, 63, 0);
       mbar_wait(smem_u32(&bar_x), n_x & 1, p.err);
       ++n_x;
       tc_fence_after_sync();
+      SYN_TRACE(1, 63, 1);
       gemm1(g, 0, mt1);
+      SYN_TRACE(1, 63, 2);
       stage_rows(tile + gridDim.x);          // sIn is free again: the conversion of this tile has consumed it
       for (int c = 0; c < C::NCHUNK; ++c, ++g) {
+        SYN_TRACE(1, c, 0);
         if (c + 1 < C::NCHUNK) {
           mbar_wait(smem_u32(&bar_epi1), n_epi1 & 1, p.err);    // D1 drained by the workers
           ++n_epi1;
           tc_fence_after_sync();
+          SYN_TRACE(1, c, 1);
           gemm1(g + 1, c + 1, mt1);
+          SYN_TRACE(1, c, 2);
         }
         mbar_wait(smem_u32(&bar_a2), n_a2 & 1, p.err);
         ++n_a2;
@@ -628,12 +673,15 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           ++n_free;
         }
         tc_fence_after_sync();
+        SYN_TRACE(1, c, 3);
         gemm2(g, c, mt2);
+        SYN_TRACE(1, c, 4);
         if constexpr (C::WSTREAM) {
           // the slot of chunk g may be refilled once GEMM2(g) has read W3c (the workers are already past it)
           mbar_wait(smem_u32(&bar_g2), n_g2i & 1, p.err);
           if (g + C::WSTAGES < total_chunks && elect_one()) load_chunk(g + C::WSTAGES);
           __syncwarp();
+          SYN_TRACE(1, c, 5);
         }
         ++n_g2i;
       }

@@ -496,6 +496,9 @@ int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, 
   FusedArgs a;
   a.x_u8 = x_u8;
   a.x = x; a.wimg = h->d_fused + h->fused_off[block]; a.y = y; a.batch = batch; a.err = h->d_err;
+#ifdef SYN_FUSED_TRACE
+  a.trace_id = block;
+#endif
   const int ntiles = (batch + C::FACES - 1) / C::FACES * C::STRIPS;
   const int grid = std::min(ntiles, h->sm_count);
   int rc;
@@ -1060,6 +1063,15 @@ int syn_poll_error(syn_handle_t* h, int* flag_out) {
   }
   return SYN_OK;
 }
+
+#ifdef SYN_FUSED_TRACE
+// Debug builds only: copy the phase trace of the fused kernels (kernels_fused.cuh) to the host.
+int syn_debug_read_trace(long long* out, int n) {
+  SYN_CUDA(cudaDeviceSynchronize());
+  SYN_CUDA(cudaMemcpyFromSymbol(out, g_fused_trace, std::min<size_t>((size_t)n, 18 * 2 * 64 * 8) * sizeof(long long)));
+  return SYN_OK;
+}
+#endif
 
 int syn_debug_forward_until(syn_handle_t* h, const float* x, int batch, int layer, float* out, void* stream) {
   SYN_CHECK_READY(h, "syn_debug_forward_until");
