@@ -67,7 +67,10 @@ struct FusedCfg {
   static constexpr int D2_COL = round_up_c(MT1 * NC_, 32);
   // EPI1 TMEM loads kept in flight per wait (measured per map size, scripts/ab_variants.sh)
   static constexpr int EPI1_BATCH = STEM_ ? SYN_EB_STEM : W_ >= 30 ? SYN_EB_WIDE : W_ >= 15 ? SYN_EB_MID : SYN_EB_SMALL;
-  static constexpr int TM_COLS = pow2_cols(D2_COL + MT2 * COUT_P);
+  // GEMM1's A operand (the block input as fp16 hi/lo) lives in TMEM, not in shared memory: per M tile
+  // CIN_P/2 columns of hi K-pairs, then CIN_P/2 columns of lo K-pairs
+  static constexpr int XA_COL = D2_COL + MT2 * COUT_P;
+  static constexpr int TM_COLS = pow2_cols(XA_COL + MT1 * CIN_P);
   // ---- weight image: [b3 | s3] then NCHUNK x { W1c hi, W1c lo, W3c hi, W3c lo, DW rows } -----------
   static constexpr int B3_BYTES = round_up_c(2 * COUT_P * 4, 128);       // [2][COUT_P] fp32: b3, s3
   static constexpr int W1_PLANE = NC_ * CIN_P * 2;                       // bytes, one plane of one chunk
@@ -78,12 +81,11 @@ struct FusedCfg {
   static constexpr int W_BYTES = B3_BYTES + NCHUNK * CHUNK_BYTES;
   static constexpr int WSTAGES = WSTREAM_ > 0 ? WSTREAM_ : NCHUNK;       // chunk slots held in smem
   // ---- shared memory carve-up --------------------------------------------------------------------
-  static constexpr int X_PLANE = MT1 * 128 * CIN_P * 2;
   static constexpr int A2_PLANE = MT2 * 128 * NC_ * 2;
   static constexpr int S_B3 = 0;
   static constexpr int S_WCH = S_B3 + B3_BYTES;
   static constexpr int S_X = S_WCH + WSTAGES * CHUNK_BYTES;
-  static constexpr int S_A2 = S_X + 2 * X_PLANE;
+  static constexpr int S_A2 = S_X;
   static constexpr int S_H = S_A2 + 2 * A2_PLANE;
   // stem only: staged input rows [3][IN_ROWS][120] fp32, exactly as they lie in the NCHW crop (one bulk
   // copy per channel); the left zero-pad column is a predicate in the im2col gather
@@ -94,7 +96,7 @@ struct FusedCfg {
   static_assert(CHID_ % NC_ == 0 && NC_ % 16 == 0, "hidden chunking");
   static_assert(WO % RO_ == 0, "strips must tile the output");
   static_assert(FACES_ == 1 || RO_ == WO, "multi-face tiles hold whole faces");
-  static_assert(D2_COL + MT2 * COUT_P <= 512, "TMEM columns");
+  static_assert(XA_COL + MT1 * CIN_P <= 512, "TMEM columns");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
   static_assert(N2 % 16 == 0 && N2 <= 256, "MMA N");
   static_assert(WSTREAM_ == 0 || (WSTREAM_ >= 2 && WSTREAM_ <= 4 && NCHUNK >= WSTREAM_), "weight ring");
@@ -179,7 +181,6 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
   const uint32_t tmem = tmem_base_s;
 
   uint8_t* sWch = smem + C::S_WCH;
-  uint8_t* sX = smem + C::S_X;
   uint8_t* sA2 = smem + C::S_A2;
   float* sH = reinterpret_cast<float*>(smem + C::S_H);
   const float* sB3 = reinterpret_cast<const float*>(smem + C::S_B3);
@@ -242,8 +243,6 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           const int m = t * 128 + row;
           const int f = (C::FACES > 1) ? m / ppf : 0;
           const int mr = m - f * ppf;                     // pixel inside the face's valid rows
-          uint8_t* xh = sX + t * (128 * C::CIN_P * 2) + (row >> 3) * 128 + (row & 7) * 16;
-          uint8_t* xl = xh + C::X_PLANE;
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -277,11 +276,14 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           uint32_t h[4], l[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) split2_f16(v[2 * j] * kActScale, v[2 * j + 1] * kActScale, h[j], l[j]);
-          *reinterpret_cast<uint4*>(xh + kg * 2048) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(xl + kg * 2048) = make_uint4(l[0], l[1], l[2], l[3]);
+          // TMEM lane = GEMM row of this thread; 8 K values = 4 columns of fp16 pairs
+          const uint32_t xa = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::XA_COL + t * C::CIN_P + kg * 4;
+          tmem_st4(xa, h[0], h[1], h[2], h[3]);
+          tmem_st4(xa + C::CIN_P / 2, l[0], l[1], l[2], l[3]);
         }
       }
-      fence_proxy_async_smem();
+      tmem_wait_st();
+      tc_fence_before_sync();
       mbar_arrive(smem_u32(&bar_x));
 
     };
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
 
     // descriptor halves that never change (SBO = 128 everywhere); per MMA only `lo` moves by (bytes >> 4)
     const uint32_t d_hi = smem_desc_hi(128);
-    const uint32_t xa_lo = smem_desc_lo(smem_u32(sX), 2048), a2_lo = smem_desc_lo(smem_u32(sA2), 2048);
+    const uint32_t a2_lo = smem_desc_lo(smem_u32(sA2), 2048);
     const uint32_t w_lo1 = smem_desc_lo(smem_u32(sWch) + C::CH_W1, LBO_W1), w_lo3 = smem_desc_lo(smem_u32(sWch) + C::CH_W3, LBO_W3);
     auto gemm1 = [&](uint32_t gi, int c, int mt1) {
       const int slot = C::WSTREAM ? (int)(gi % C::WSTAGES) : c;
@@ -580,14 +582,14 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       const uint32_t wb = w_lo1 + ((slot * C::CHUNK_BYTES) >> 4);
       if (elect_one()) {
       for (int t = 0; t < mt1; ++t) {
-        const uint32_t ab = xa_lo + ((t * (128 * C::CIN_P * 2)) >> 4);
+        const uint32_t xa = tmem + C::XA_COL + t * C::CIN_P;     // A from TMEM: N/2 cycles per MMA, no smem read of X
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
           for (int ks = 0; ks < C::CIN_P / 16; ++ks)
-            umma_f16(tmem + t * C::NC, desc64(d_hi, ab + (((pass == 2 ? C::X_PLANE : 0) + ks * 4096) >> 4)),
-                     desc64(d_hi, wb + (((pass == 1 ? C::W1_PLANE : 0) + ks * 2 * LBO_W1) >> 4)), idesc1,
-                     (pass > 0 || ks > 0) ? 1u : 0u);
+            umma_f16_ts(tmem + t * C::NC, xa + (pass == 2 ? C::CIN_P / 2 : 0) + ks * 8,
+                        desc64(d_hi, wb + (((pass == 1 ? C::W1_PLANE : 0) + ks * 2 * LBO_W1) >> 4)), idesc1,
+                        (pass > 0 || ks > 0) ? 1u : 0u);
         }
       }
       umma_commit(smem_u32(&bar_d1));
