@@ -27,6 +27,22 @@
 namespace syn {
 
 constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
+// hidden-channel chunk widths that are worth re-measuring when the kernel changes (scripts/ab_variants.sh)
+#ifndef SYN_NC_B56
+#define SYN_NC_B56 64
+#endif
+#ifndef SYN_NC_B7
+#define SYN_NC_B7 64
+#endif
+#ifndef SYN_NC_B12
+#define SYN_NC_B12 64
+#endif
+#ifndef SYN_NC_B14
+#define SYN_NC_B14 64
+#endif
+#ifndef SYN_NC_B17
+#define SYN_NC_B17 32
+#endif
 #ifndef SYN_EB_STEM
 #define SYN_EB_STEM 1
 #endif
@@ -706,13 +722,13 @@ using FusedStemB1 = FusedCfg<27, 32, 32, 16, 60, 1, 6, 1, false, true, 0>;    //
 using FusedB2 = FusedCfg<16, 96, 32, 24, 60, 2, 5, 1, false, false, 0>;       // features[2]
 using FusedB3 = FusedCfg<24, 144, 16, 24, 30, 1, 15, 1, true, false, 0>;      // features[3]
 using FusedB4 = FusedCfg<24, 144, 48, 32, 30, 2, 5, 1, false, false, 0>;      // features[4]
-using FusedB56 = FusedCfg<32, 192, 32, 32, 15, 1, 15, 1, true, false, 0>;     // features[5], [6]
-using FusedB7 = FusedCfg<32, 192, 32, 64, 15, 2, 8, 1, false, false, 0>;      // features[7]
+using FusedB56 = FusedCfg<32, 192, SYN_NC_B56, 32, 15, 1, 15, 1, true, false, 0>;     // features[5], [6]
+using FusedB7 = FusedCfg<32, 192, SYN_NC_B7, 64, 15, 2, 8, 1, false, false, 0>;      // features[7]
 using FusedB8 = FusedCfg<64, 384, 64, 64, 8, 1, 8, 2, true, false, 3>;         // features[8..10]
 using FusedB11 = FusedCfg<64, 384, 64, 96, 8, 1, 8, 2, false, false, 2>;       // features[11]
-using FusedB12 = FusedCfg<96, 576, 32, 96, 8, 1, 8, 2, true, false, 3>;        // features[12], [13]
-using FusedB14 = FusedCfg<96, 576, 32, 160, 8, 2, 4, 2, false, false, 3>;      // features[14]
+using FusedB12 = FusedCfg<96, 576, SYN_NC_B12, 96, 8, 1, 8, 2, true, false, SYN_NC_B12 == 32 ? 3 : 2>;        // features[12], [13]
+using FusedB14 = FusedCfg<96, 576, SYN_NC_B14, 160, 8, 2, 4, 2, false, false, SYN_NC_B14 == 32 ? 3 : 2>;      // features[14]
 using FusedB15 = FusedCfg<160, 960, 32, 160, 4, 1, 4, 8, true, false, 2>;      // features[15], [16]
-using FusedB17 = FusedCfg<160, 960, 16, 320, 4, 1, 4, 8, false, false, 3>;     // features[17]
+using FusedB17 = FusedCfg<160, 960, SYN_NC_B17, 320, 4, 1, 4, 8, false, false, SYN_NC_B17 == 16 ? 3 : 2>;     // features[17]
 
 }  // namespace syn
