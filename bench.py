@@ -320,7 +320,7 @@ def run_b200(args):
             'config': {'workload': 'configs[1]: batch=1024 synthetic 120x120 crops, MobileNetV2 + 3DMM params + '
                                    '68-landmark reconstruction' + (' + all-gather of landmarks' if world > 1 else ''),
                        'batch_per_gpu': B, 'global_batch': world * B,
-                       'engine': {0: 'simt_fp32', 1: 'tcgen05_bf16x3', 2: 'tcgen05_bf16x3_fused'}.get(eng.engine, eng.engine),
+                       'engine': {0: 'simt_fp32', 1: 'tcgen05_f16x3_unfused', 2: 'tcgen05_f16x3_fused'}.get(eng.engine, eng.engine),
                        'parallelism': f'dp{world}',
                        'l2': f'{n_rot} rotating device-resident input batches of {B * X_BYTES_PER_FACE / 1e6:.0f} MB '
                              '(> 126 MB L2) + >1 GB of activations written per step'},
