@@ -251,51 +251,66 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
         }
         asm volatile("bar.sync 5, %0;" ::"n"(NWT) : "memory");
       }
-      // ---- X tile -> fp16 hi/lo canonical operand ------------------------------------------------
+      // ---- X tile -> fp16 hi/lo K pairs in TMEM ---------------------------------------------------
       {
         constexpr int KG = C::CIN_P / 8;
-        for (int e = wg; e < mt1 * KG; e += NWG) {
-          const int t = e / KG, kg = e - t * KG;
-          const int m = t * 128 + row;
-          const int f = (C::FACES > 1) ? m / ppf : 0;
-          const int mr = m - f * ppf;                     // pixel inside the face's valid rows
-          float v[8];
+        constexpr int PB = 1;     // items whose global loads are issued before the first use (4 measured no faster)
+        for (int e0 = wg; e0 < mt1 * KG; e0 += PB * NWG) {
+          float v[PB][8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = 0.f;
-          if (m < M1) {
-            if constexpr (C::STEM) {
-              // im2col of the 3x3 stride-2 pad-1 stem conv from the staged rows: k = (ci*3+ky)*3+kx;
-              // the kg switch makes every tap offset a compile-time constant
-              const int yl = mr / C::W, xx = mr - yl * C::W;
-              const float* base = sIn + (2 * yl) * C::IN_STRIDE + 2 * xx - 1;   // column 2xx-1+kx; -1 is the zero pad
+          for (int u = 0; u < PB; ++u) {
+            const int e = e0 + u * NWG;
 #pragma unroll
-              for (int kgc = 0; kgc < KG; ++kgc)
-                if (kg == kgc) {
+            for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+            if (e < mt1 * KG) {
+              const int t = e / KG, kg = e - t * KG;
+              const int m = t * 128 + row;
+              const int f = (C::FACES > 1) ? m / ppf : 0;
+              const int mr = m - f * ppf;                     // pixel inside the face's valid rows
+              if (m < M1) {
+                if constexpr (C::STEM) {
+                  // im2col of the 3x3 stride-2 pad-1 stem conv from the staged rows: k = (ci*3+ky)*3+kx;
+                  // the kg switch makes every tap offset a compile-time constant
+                  const int yl = mr / C::W, xx = mr - yl * C::W;
+                  const float* base = sIn + (2 * yl) * C::IN_STRIDE + 2 * xx - 1;   // column 2xx-1+kx; -1 is the zero pad
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const int k = kgc * 8 + j;
-                    if (k < 27) {
-                      const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
-                      if (kx > 0 || xx > 0) v[j] = base[(ci * C::IN_ROWS + ky) * C::IN_STRIDE + kx];
+                  for (int kgc = 0; kgc < KG; ++kgc)
+                    if (kg == kgc) {
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) {
+                        const int k = kgc * 8 + j;
+                        if (k < 27) {
+                          const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+                          if (kx > 0 || xx > 0) v[u][j] = base[(ci * C::IN_ROWS + ky) * C::IN_STRIDE + kx];
+                        }
+                      }
                     }
+                } else {
+                  if (kg * 8 < C::CIN) {
+                    const float* src = p.x + ((size_t)((f0 + f) * C::W + rf) * C::W + mr) * C::CIN + kg * 8;
+                    const float4 a = *reinterpret_cast<const float4*>(src);
+                    const float4 e4 = *reinterpret_cast<const float4*>(src + 4);
+                    v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+                    v[u][4] = e4.x; v[u][5] = e4.y; v[u][6] = e4.z; v[u][7] = e4.w;
                   }
                 }
-            } else {
-              if (kg * 8 < C::CIN) {
-                const float* src = p.x + ((size_t)((f0 + f) * C::W + rf) * C::W + mr) * C::CIN + kg * 8;
-                const float4 a = *reinterpret_cast<const float4*>(src);
-                const float4 e4 = *reinterpret_cast<const float4*>(src + 4);
-                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = e4.x; v[5] = e4.y; v[6] = e4.z; v[7] = e4.w;
               }
             }
           }
-          uint32_t h[4], l[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) split2_f16(v[2 * j] * kActScale, v[2 * j + 1] * kActScale, h[j], l[j]);
-          // TMEM lane = GEMM row of this thread; 8 K values = 4 columns of fp16 pairs
-          const uint32_t xa = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::XA_COL + t * C::CIN_P + kg * 4;
-          tmem_st4(xa, h[0], h[1], h[2], h[3]);
-          tmem_st4(xa + C::CIN_P / 2, l[0], l[1], l[2], l[3]);
+          for (int u = 0; u < PB; ++u) {
+            const int e = e0 + u * NWG;
+            if (e < mt1 * KG) {                               // warp-uniform: tcgen05.st is .sync.aligned
+              const int t = e / KG, kg = e - t * KG;
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) split2_f16(v[u][2 * j] * kActScale, v[u][2 * j + 1] * kActScale, h[j], l[j]);
+              // TMEM lane = GEMM row of this thread; 8 K values = 4 columns of fp16 pairs
+              const uint32_t xa = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::XA_COL + t * C::CIN_P + kg * 4;
+              tmem_st4(xa, h[0], h[1], h[2], h[3]);
+              tmem_st4(xa + C::CIN_P / 2, l[0], l[1], l[2], l[3]);
+            }
+          }
         }
       }
       tmem_wait_st();
@@ -407,6 +422,94 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           ++n_g2;
         }
         SYN_TRACE(0, c, 4);
+        if constexpr (C::STRIDE == 1 && C::WO >= 15 && C::WO <= 30) {
+          // Stride-1 30^2 and 15^2 maps (on the 60^2 map of block 1 the units do not divide evenly between
+          // the channel groups and the row-pair items below are faster): the window loads of the depthwise conv are what the
+          // shared-memory pipe spends its time on, so an item is register-blocked over a 2 x 2 output patch
+          // of ONE channel quad -- 16 window + 10 tap LDS.128 per 16 outputs instead of 24 + 20.
+          // A unit of 16 threads = 8 lanes along x (column pairs) x the two quads of a channel octet.
+          // Lanes 4-7 are MIRRORED: they walk the four window columns right to left, use the taps with kx
+          // reversed and own the patch columns in the opposite order.  Neighbouring lanes are 2 pixels =
+          // an even number of 16-byte bank groups apart, and the mirror image shifts lanes 4-7 onto the odd
+          // groups: every window load (quarter-warp) and every 8-byte operand store (half-warp) is
+          // bank-conflict free.
+          constexpr int CPR = (C::WO + 1) / 2, XG2 = (CPR + 7) / 8, RP2 = (C::RO + 1) / 2;
+          constexpr int UPK = RP2 * XG2;                                   // units per (face, channel octet)
+          const int l8 = tid & 7, qh = (tid >> 3) & 1;
+          const bool mir = (l8 & 4) != 0;
+          const int units = KPG * nfaces * UPK;
+          for (int u = gtid >> 4; u < units; u += TPG / 16) {
+            const int kgl = u / (nfaces * UPK), r1 = u - kgl * (nfaces * UPK);
+            const int f = r1 / UPK, r2 = r1 - f * UPK;
+            const int rp = r2 / XG2, xg = r2 - rp * XG2;
+            const int kg = grp * KPG + kgl, j0 = kg * 8 + qh * 4;
+            const int ox = 2 * (xg * 8 + l8), oy = 2 * rp;
+            if (ox >= C::WO) continue;
+            const bool two = (oy + 1 < C::RO), wide = (ox + 1 < C::WO);
+            const float* wq = dwc + j0;
+            float w[3][3][4];                                              // [ky][local kx][channel]
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kl = 0; kl < 3; ++kl) {
+                const float4 t4 = *reinterpret_cast<const float4*>(wq + (ky * 3 + (mir ? 2 - kl : kl)) * C::NC);
+                w[ky][kl][0] = t4.x; w[ky][kl][1] = t4.y; w[ky][kl][2] = t4.z; w[ky][kl][3] = t4.w;
+              }
+            float acc[2][2][4];                                            // [output row][local column][channel]
+            {
+              const float4 b4 = *reinterpret_cast<const float4*>(wq + 9 * C::NC);
+#pragma unroll
+              for (int ro = 0; ro < 2; ++ro)
+#pragma unroll
+                for (int a = 0; a < 2; ++a) { acc[ro][a][0] = b4.x; acc[ro][a][1] = b4.y; acc[ro][a][2] = b4.z; acc[ro][a][3] = b4.w; }
+            }
+            // window columns ox-1 .. ox+2 are Hs columns ox .. ox+3; local column ic is Hs column ox+ic (ox+3-ic mirrored)
+            const float* hb = sH + (size_t)(f * C::HS_FACE + oy * C::HS_COLS + ox + (mir ? 3 : 0)) * C::HS_STRIDE + j0;
+            const int cstep = mir ? -C::HS_STRIDE : C::HS_STRIDE;
+#pragma unroll
+            for (int ic = 0; ic < 4; ++ic) {
+              float d[4][4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                if (r == 3 && !two) continue;                              // row only the absent second output row needs
+                const float4 t4 = *reinterpret_cast<const float4*>(hb + r * (C::HS_COLS * C::HS_STRIDE) + ic * cstep);
+                d[r][0] = t4.x; d[r][1] = t4.y; d[r][2] = t4.z; d[r][3] = t4.w;
+              }
+#pragma unroll
+              for (int a = 0; a < 2; ++a) {
+                const int kl = ic - a;
+                if (kl < 0 || kl > 2) continue;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) acc[0][a][j] = fmaf(d[ky][j], w[ky][kl][j], acc[0][a][j]);
+                  if (two) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[1][a][j] = fmaf(d[ky + 1][j], w[ky][kl][j], acc[1][a][j]);
+                  }
+                }
+              }
+            }
+            constexpr float kOut = 6.0f * kActScale;
+#pragma unroll
+            for (int ro = 0; ro < 2; ++ro) {
+              if (ro == 1 && !two) continue;
+#pragma unroll
+              for (int a = 0; a < 2; ++a) {
+                const int col = ox + (mir ? 1 - a : a);
+                if (col >= C::WO) continue;                                // odd width: the last pair has one column
+                const int m2 = f * C::M2F + (oy + ro) * C::WO + col;
+                uint32_t h0, l0, h1, l1;
+                split2_f16<false>(__saturatef(acc[ro][a][0]) * kOut, __saturatef(acc[ro][a][1]) * kOut, h0, l0);
+                split2_f16<false>(__saturatef(acc[ro][a][2]) * kOut, __saturatef(acc[ro][a][3]) * kOut, h1, l1);
+                uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16 + qh * 8;
+                *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(dst + C::A2_PLANE) = make_uint2(l0, l1);
+              }
+            }
+            (void)wide;
+          }
+        } else
         {
           // Item = (8 hidden channels, two vertically adjacent output rows, 8 lanes along x): the 3x3
           // windows of the two rows share (S=1: 2 of 4, S=2: 1 of 5) input rows and all nine tap vectors,
