@@ -36,6 +36,9 @@ def main():
         t0 = w[63, 0]
         print(f'== block {b}: tile start 0, chunks done {w[63, 1] - t0}, EPI2 wait..start {w[63, 2] - t0}..{w[63, 3] - t0}, '
               f'EPI2 end {w[63, 4] - t0}; issuer: wait X {i[63, 0] - t0}..{i[63, 1] - t0}, GEMM1(0) issued {i[63, 2] - t0}')
+        q = w[62]
+        if q[0]:
+            print(f'   prep(next tile): start {q[0] - t0}, staged {q[1] - t0}, all workers {q[2] - t0}, converted {q[3] - t0}, published {q[4] - t0}; first batch: loads issued {q[5] - t0}, first item stored {q[6] - t0}, batch done {q[7] - t0}')
         print('  c | worker: start  waitD1   bar   EPI1  bar+G2     DW | issuer: start waitEPI1  G1iss  waitA2  G2iss  waitG2')
         for c in range(63):
             if w[c, 0] == 0:

@@ -28,6 +28,24 @@ namespace syn {
 
 constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 // hidden-channel chunk widths that are worth re-measuring when the kernel changes (scripts/ab_variants.sh)
+#ifndef SYN_RO_STEM
+#define SYN_RO_STEM 6
+#endif
+#ifndef SYN_RO_B2
+#define SYN_RO_B2 6
+#endif
+#ifndef SYN_PREP_BATCH
+#define SYN_PREP_BATCH 4
+#endif
+#ifndef SYN_NC_B4
+#define SYN_NC_B4 16
+#endif
+#ifndef SYN_RO_B4
+#define SYN_RO_B4 15
+#endif
+#ifndef SYN_DW2_MAXW
+#define SYN_DW2_MAXW 30
+#endif
 #ifndef SYN_NC_B56
 #define SYN_NC_B56 64
 #endif
@@ -223,6 +241,10 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       const int ppf = (rl - rf + 1) * C::W;
       const int M1 = nfaces * ppf;
       const int mt1 = (M1 + 127) >> 7;
+#ifdef SYN_FUSED_TRACE
+      const bool trace_on = blockIdx.x == 0 && tile == 2 * (int)gridDim.x && tid == 0;   // prep of the tile after the traced one
+#endif
+      SYN_TRACE(0, 62, 0);
       // ---- stem: the crop rows this strip needs, zero outside the image ------------------------------
       if constexpr (C::STEM) {
         const int iy_first = 2 * rf - 1, nin = 2 * (rl - rf + 1) + 1;
@@ -249,58 +271,72 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                     make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        SYN_TRACE(0, 62, 1);
         asm volatile("bar.sync 5, %0;" ::"n"(NWT) : "memory");
       }
+      SYN_TRACE(0, 62, 2);
       // ---- X tile -> fp16 hi/lo K pairs in TMEM ---------------------------------------------------
+      // The conversion sits between the last depthwise and EPI2 of the current tile, so its global-load
+      // latency is exposed once per batch of loads: all loads of a batch are issued unconditionally (from a
+      // clamped, always valid address) before the first use, and masked afterwards -- a predicated load per
+      // item would put a branch between the loads and serialise one DRAM latency per item.
       {
         constexpr int KG = C::CIN_P / 8;
-        constexpr int PB = 1;     // items whose global loads are issued before the first use (4 measured no faster)
-        for (int e0 = wg; e0 < mt1 * KG; e0 += PB * NWG) {
+        constexpr int ITERS = (C::MT1 * KG + NWG - 1) / NWG;             // items per thread
+        constexpr int PB = C::STEM ? 1 : (ITERS < SYN_PREP_BATCH ? ITERS : SYN_PREP_BATCH);
+        const int n_items = mt1 * KG;
+        for (int e0 = wg; e0 < n_items; e0 += PB * NWG) {
           float v[PB][8];
+          if constexpr (C::STEM) {
+            const int t = e0 / KG, kg = e0 - t * KG;
+            const int mr = t * 128 + row;                     // FACES == 1
 #pragma unroll
-          for (int u = 0; u < PB; ++u) {
-            const int e = e0 + u * NWG;
+            for (int j = 0; j < 8; ++j) v[0][j] = 0.f;
+            if (mr < M1) {
+              // im2col of the 3x3 stride-2 pad-1 stem conv from the staged rows: k = (ci*3+ky)*3+kx;
+              // the kg switch makes every tap offset a compile-time constant
+              const int yl = mr / C::W, xx = mr - yl * C::W;
+              const float* base = sIn + (2 * yl) * C::IN_STRIDE + 2 * xx - 1;   // column 2xx-1+kx; -1 is the zero pad
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
-            if (e < mt1 * KG) {
-              const int t = e / KG, kg = e - t * KG;
-              const int m = t * 128 + row;
-              const int f = (C::FACES > 1) ? m / ppf : 0;
-              const int mr = m - f * ppf;                     // pixel inside the face's valid rows
-              if (m < M1) {
-                if constexpr (C::STEM) {
-                  // im2col of the 3x3 stride-2 pad-1 stem conv from the staged rows: k = (ci*3+ky)*3+kx;
-                  // the kg switch makes every tap offset a compile-time constant
-                  const int yl = mr / C::W, xx = mr - yl * C::W;
-                  const float* base = sIn + (2 * yl) * C::IN_STRIDE + 2 * xx - 1;   // column 2xx-1+kx; -1 is the zero pad
+              for (int kgc = 0; kgc < KG; ++kgc)
+                if (kg == kgc) {
 #pragma unroll
-                  for (int kgc = 0; kgc < KG; ++kgc)
-                    if (kg == kgc) {
-#pragma unroll
-                      for (int j = 0; j < 8; ++j) {
-                        const int k = kgc * 8 + j;
-                        if (k < 27) {
-                          const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
-                          if (kx > 0 || xx > 0) v[u][j] = base[(ci * C::IN_ROWS + ky) * C::IN_STRIDE + kx];
-                        }
-                      }
+                  for (int j = 0; j < 8; ++j) {
+                    const int k = kgc * 8 + j;
+                    if (k < 27) {
+                      const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+                      if (kx > 0 || xx > 0) v[0][j] = base[(ci * C::IN_ROWS + ky) * C::IN_STRIDE + kx];
                     }
-                } else {
-                  if (kg * 8 < C::CIN) {
-                    const float* src = p.x + ((size_t)((f0 + f) * C::W + rf) * C::W + mr) * C::CIN + kg * 8;
-                    const float4 a = *reinterpret_cast<const float4*>(src);
-                    const float4 e4 = *reinterpret_cast<const float4*>(src + 4);
-                    v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
-                    v[u][4] = e4.x; v[u][5] = e4.y; v[u][6] = e4.z; v[u][7] = e4.w;
                   }
                 }
-              }
+            }
+          } else {
+            float4 qa[PB], qb[PB];
+            bool ok[PB];
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+              const int e = min(e0 + u * NWG, n_items - 1);
+              const int t = e / KG, kg = e - t * KG;
+              const int m = t * 128 + row;
+              ok[u] = (e0 + u * NWG < n_items) && (m < M1) && (kg * 8 < C::CIN);
+              const int mc = min(m, M1 - 1), kgc = min(kg, (C::CIN - 1) / 8);
+              const int f = (C::FACES > 1) ? mc / ppf : 0;
+              const int mr = mc - f * ppf;                    // pixel inside the face's valid rows
+              const float* src = p.x + ((size_t)((f0 + f) * C::W + rf) * C::W + mr) * C::CIN + kgc * 8;
+              qa[u] = __ldg(reinterpret_cast<const float4*>(src));
+              qb[u] = __ldg(reinterpret_cast<const float4*>(src + 4));
+            }
+            if (e0 == wg) SYN_TRACE(0, 62, 5);
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+              v[u][0] = ok[u] ? qa[u].x : 0.f; v[u][1] = ok[u] ? qa[u].y : 0.f; v[u][2] = ok[u] ? qa[u].z : 0.f; v[u][3] = ok[u] ? qa[u].w : 0.f;
+              v[u][4] = ok[u] ? qb[u].x : 0.f; v[u][5] = ok[u] ? qb[u].y : 0.f; v[u][6] = ok[u] ? qb[u].z : 0.f; v[u][7] = ok[u] ? qb[u].w : 0.f;
             }
           }
 #pragma unroll
           for (int u = 0; u < PB; ++u) {
             const int e = e0 + u * NWG;
-            if (e < mt1 * KG) {                               // warp-uniform: tcgen05.st is .sync.aligned
+            if (e < n_items) {                                // warp-uniform: tcgen05.st is .sync.aligned
               const int t = e / KG, kg = e - t * KG;
               uint32_t h[4], l[4];
 #pragma unroll
@@ -309,16 +345,37 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
               const uint32_t xa = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::XA_COL + t * C::CIN_P + kg * 4;
               tmem_st4(xa, h[0], h[1], h[2], h[3]);
               tmem_st4(xa + C::CIN_P / 2, l[0], l[1], l[2], l[3]);
+              if (e == wg) SYN_TRACE(0, 62, 6);
             }
           }
+          if (e0 == wg) SYN_TRACE(0, 62, 7);
         }
       }
+      SYN_TRACE(0, 62, 3);
       tmem_wait_st();
       tc_fence_before_sync();
       mbar_arrive(smem_u32(&bar_x));
+      SYN_TRACE(0, 62, 4);
 
     };
+    // L2 prefetch of a tile's input (one contiguous NHWC range) a whole tile ahead of its conversion: the
+    // loads in prep() then hit L2 with warm TLB entries instead of paying ~2000 cycles per batch
+    auto prefetch_x = [&](int tile) {
+      if constexpr (!C::STEM) {
+        if (tile >= ntiles) return;
+        const int fg = tile / C::STRIPS, sp = tile - fg * C::STRIPS;
+        const int f0 = fg * C::FACES;
+        const int nfaces = min(C::FACES, p.batch - f0);
+        const int iy0 = sp * C::RO * C::STRIDE - 1;
+        const int rf = max(iy0, 0), rl = min(iy0 + C::RWIN - 1, C::W - 1);
+        const char* base = reinterpret_cast<const char*>(p.x + ((size_t)(f0 * C::W + rf) * C::W) * C::CIN);
+        const int bytes = (C::FACES > 1 ? nfaces * C::W * C::W : (rl - rf + 1) * C::W) * C::CIN * 4;
+        for (int o = tid * 128; o < bytes; o += NWT * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+      }
+    };
     if ((int)blockIdx.x < ntiles) prep(blockIdx.x);
+    prefetch_x(blockIdx.x + gridDim.x);
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int fg = tile / C::STRIPS, sp = tile - fg * C::STRIPS;
@@ -422,7 +479,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           ++n_g2;
         }
         SYN_TRACE(0, c, 4);
-        if constexpr (C::STRIDE == 1 && C::WO >= 15 && C::WO <= 30) {
+        if constexpr (C::STRIDE == 1 && C::WO >= 15 && C::WO <= SYN_DW2_MAXW) {
           // Stride-1 30^2 and 15^2 maps (on the 60^2 map of block 1 the units do not divide evenly between
           // the channel groups and the row-pair items below are faster): the window loads of the depthwise conv are what the
           // shared-memory pipe spends its time on, so an item is register-blocked over a 2 x 2 output patch
@@ -615,7 +672,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       }
       SYN_TRACE(0, 63, 1);
 
-      if (tile + (int)gridDim.x < ntiles) prep(tile + gridDim.x);   // Xs is free: every GEMM1 of this tile is done
+      if (tile + (int)gridDim.x < ntiles) prep(tile + gridDim.x);   // XA is free: every GEMM1 of this tile is done
+      prefetch_x(tile + 2 * (int)gridDim.x);
       // ---- EPI2: s3*D2 + b3 (+ skip) -> global NHWC --------------------------------------------------
       SYN_TRACE(0, 63, 2);
       mbar_wait(smem_u32(&bar_g2), n_g2 & 1, p.err);
@@ -821,10 +879,10 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
 
 // ---- the instantiations used by the backbone (SURVEY.md section 8(a) shape table) -------------------
 //                          CIN CHID NC COUT  W  S  RO FACES RES    STEM   weight ring slots (0 = resident)
-using FusedStemB1 = FusedCfg<27, 32, 32, 16, 60, 1, 6, 1, false, true, 0>;    // features[0] + features[1]
-using FusedB2 = FusedCfg<16, 96, 32, 24, 60, 2, 5, 1, false, false, 0>;       // features[2]
+using FusedStemB1 = FusedCfg<27, 32, 32, 16, 60, 1, SYN_RO_STEM, 1, false, true, 0>;    // features[0] + features[1]
+using FusedB2 = FusedCfg<16, 96, 32, 24, 60, 2, SYN_RO_B2, 1, false, false, 0>;       // features[2]
 using FusedB3 = FusedCfg<24, 144, 16, 24, 30, 1, 15, 1, true, false, 0>;      // features[3]
-using FusedB4 = FusedCfg<24, 144, 48, 32, 30, 2, 5, 1, false, false, 0>;      // features[4]
+using FusedB4 = FusedCfg<24, 144, SYN_NC_B4, 32, 30, 2, SYN_RO_B4, 1, false, false, 0>;      // features[4]
 using FusedB56 = FusedCfg<32, 192, SYN_NC_B56, 32, 15, 1, 15, 1, true, false, 0>;     // features[5], [6]
 using FusedB7 = FusedCfg<32, 192, SYN_NC_B7, 64, 15, 2, 8, 1, false, false, 0>;      // features[7]
 using FusedB8 = FusedCfg<64, 384, 64, 64, 8, 1, 8, 2, true, false, 3>;         // features[8..10]
