@@ -142,6 +142,8 @@ struct FusedArgs {
   const uint8_t* wimg;   // packed weight image (FusedCfg::W_BYTES)
   float* y;              // NHWC (B,WO,WO,COUT)
   int batch;
+  int split;             // two-face configs: face groups >= split hold ONE face (tail wave, see fused_tile_plan)
+  int face_groups;       // number of face groups (tiles = face_groups * STRIPS)
   int* err;
 #ifdef SYN_FUSED_TRACE
   int trace_id;          // backbone block of this launch (1..17)
@@ -187,8 +189,19 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
   const int row = tid & 127, wg = tid >> 7;   // GEMM row / TMEM lane of this worker, and its 128-thread slice
   const int grp = warp / WPG;                  // channel group (workers only)
   const int gtid = tid - grp * TPG, gsub = gtid >> 7;
-  const int face_groups = (p.batch + C::FACES - 1) / C::FACES;
-  const int ntiles = face_groups * C::STRIPS;
+  const int ntiles = p.face_groups * C::STRIPS;
+  // faces of a face group.  Two-face tiles (8x8 maps): 512 groups over 148 SMs would leave the last wave
+  // 46 % full, so the host turns the groups of that wave into single-face groups (twice as many CTAs busy,
+  // each done sooner); small batches become single-face groups altogether.
+  auto group_faces = [&](int fg, int& f0, int& nfaces) {
+    if constexpr (C::FACES == 2) {
+      if (fg < p.split) { f0 = 2 * fg; nfaces = 2; }
+      else { f0 = 2 * p.split + (fg - p.split); nfaces = 1; }
+    } else {
+      f0 = fg * C::FACES;
+      nfaces = min(C::FACES, p.batch - f0);
+    }
+  };
 
   if (tid == 0) {
     mbar_init(smem_u32(&bar_w), 1);
@@ -234,8 +247,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     // and the global-load latency of the conversion is hidden -- while the workers drain D2.
     auto prep = [&](int tile) {
       const int fg = tile / C::STRIPS, sp = tile - fg * C::STRIPS;
-      const int f0 = fg * C::FACES;
-      const int nfaces = min(C::FACES, p.batch - f0);
+      int f0, nfaces;
+      group_faces(fg, f0, nfaces);
       const int iy0 = sp * C::RO * C::STRIDE - 1;
       const int rf = max(iy0, 0), rl = min(iy0 + C::RWIN - 1, C::W - 1);
       const int ppf = (rl - rf + 1) * C::W;
@@ -364,8 +377,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       if constexpr (!C::STEM) {
         if (tile >= ntiles) return;
         const int fg = tile / C::STRIPS, sp = tile - fg * C::STRIPS;
-        const int f0 = fg * C::FACES;
-        const int nfaces = min(C::FACES, p.batch - f0);
+        int f0, nfaces;
+        group_faces(fg, f0, nfaces);
         const int iy0 = sp * C::RO * C::STRIDE - 1;
         const int rf = max(iy0, 0), rl = min(iy0 + C::RWIN - 1, C::W - 1);
         const char* base = reinterpret_cast<const char*>(p.x + ((size_t)(f0 * C::W + rf) * C::W) * C::CIN);
@@ -379,8 +392,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int fg = tile / C::STRIPS, sp = tile - fg * C::STRIPS;
-      const int f0 = fg * C::FACES;
-      const int nfaces = min(C::FACES, p.batch - f0);
+      int f0, nfaces;
+      group_faces(fg, f0, nfaces);
       const int oy0 = sp * C::RO;
       const int iy0 = oy0 * C::STRIDE - 1;
       const int rf = max(iy0, 0), rl = min(iy0 + C::RWIN - 1, C::W - 1);
@@ -819,7 +832,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ntile_local) {
       const int fg = tile / C::STRIPS, sp = tile - fg * C::STRIPS;
-      const int nfaces = min(C::FACES, p.batch - fg * C::FACES);
+      int f0_unused, nfaces;
+      group_faces(fg, f0_unused, nfaces);
       const int iy0 = sp * C::RO * C::STRIDE - 1;
       const int rf = max(iy0, 0), rl = min(iy0 + C::RWIN - 1, C::W - 1);
       const int mt1 = (nfaces * (rl - rf + 1) * C::W + 127) >> 7;
@@ -874,6 +888,20 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
   if (warp == NWW) {
     __syncwarp();
     tmem_dealloc<C::TM_COLS>(tmem);
+  }
+}
+
+// Face groups of a launch: {split, face_groups}.  FACES == 2: full two-face groups fill whole waves of `sms`
+// CTAs; the remainder becomes single-face groups when those still fit in one wave.
+template <class C>
+inline void fused_tile_plan(int batch, int sms, int& split, int& face_groups) {
+  if constexpr (C::FACES == 2) {
+    const int full = batch / 2, odd = batch & 1, rem = full % sms;
+    split = (2 * rem + odd <= sms) ? full - rem : full;
+    face_groups = split + (batch - 2 * split);              // every face past the two-face groups is its own group
+  } else {
+    split = 0;
+    face_groups = (batch + C::FACES - 1) / C::FACES;
   }
 }
 

@@ -499,7 +499,8 @@ int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, 
 #ifdef SYN_FUSED_TRACE
   a.trace_id = block;
 #endif
-  const int ntiles = (batch + C::FACES - 1) / C::FACES * C::STRIPS;
+  fused_tile_plan<C>(batch, h->sm_count, a.split, a.face_groups);
+  const int ntiles = a.face_groups * C::STRIPS;
   const int grid = std::min(ntiles, h->sm_count);
   int rc;
   switch (fused_worker_warps()) {
