@@ -5,21 +5,22 @@
 // (mobilenetv2_backbone.py:127 + features[1]).
 //
 // Work item (tile) = RO output rows of one face (large maps) or FACES whole faces (8x8 / 4x4 maps).
-// Per tile, for each chunk of NC hidden channels:
-//   GEMM1  D1[t] (128 x NC, TMEM)  = Xs[t] (128 input pixels x CIN_P, fp16 hi/lo) * W1c^T   (tensor)
+// Per tile the block input is converted once to fp16 hi/lo and stored in TMEM (XA, tcgen05.st); then, for
+// each chunk of NC hidden channels:
+//   GEMM1  D1[t] (128 x NC, TMEM)  = XA[t] (TMEM, TS mode) * W1c^T (smem)                      (tensor)
 //   EPI1   Hs[pixel][NC] (fp32, smem, zero halo) = relu6(s1 * D1 + b1) / 6  (one FFMA.SAT)   (CUDA)
 //   DW     A2[out pixel][NC] (fp16 hi/lo, smem)  = split(relu6(dw3x3(6 Hs) + bdw))          (CUDA)
 //   GEMM2  D2[t] (128 x COUT_P, TMEM) += A2[t] * W3c^T                                      (tensor)
 // and finally EPI2: out = s3 * D2 + b3 (+ x).  GEMM1 of chunk c+1 and GEMM2 of chunk c run on the
-// tensor pipe while the 128 worker threads do EPI1/DW, so the CUDA-core work is the critical path.
-// CTAs are persistent (grid = #SMs).  Weights (fp16 hi/lo, split-16x3 scheme of kernels_tc.cuh) are
-// either resident in shared memory for the whole kernel (early blocks, <= 83 KB) or streamed chunk by
-// chunk through a 2-stage bulk-copy (TMA) ring (late blocks).
+// tensor pipe while the worker warps do EPI1/DW; the depthwise phase (shared-memory loads) is the
+// critical path.  CTAs are persistent (grid = #SMs).  Weights (fp16 hi/lo, split-16x3 scheme of
+// kernels_tc.cuh) are either resident in shared memory for the whole kernel (early blocks, <= 83 KB) or
+// streamed chunk by chunk through a 2-3-slot bulk-copy (TMA) ring (late blocks).
 //
-// Roles: warps 0..NWW-1 = workers (thread = GEMM row / pixel; NWW/4 groups share the column chunks),
-// warp NWW lane 0 = MMA issuer + weight loader.
-// Operand tiles use the canonical K-major no-swizzle layout of tc_common.cuh (SBO 128 B,
-// LBO = rows/8 * 128 B).
+// Roles: warps 0..NWW-1 = workers (thread = GEMM row / pixel / TMEM lane; channel groups own the column
+// octets of a chunk), warp NWW = MMA issuer + weight loader (converged warp, issue under elect.sync).
+// smem operand tiles use the canonical K-major no-swizzle layout of tc_common.cuh (SBO 128 B,
+// LBO = rows/8 * 128 B).  DESIGN.md section 5 lists the measurements behind each of these choices.
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -27,7 +28,8 @@
 namespace syn {
 
 constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
-// hidden-channel chunk widths that are worth re-measuring when the kernel changes (scripts/ab_variants.sh)
+// tile shapes / chunk widths / batching depths worth re-measuring when the kernel changes: build variants
+// with -D... and compare them on one box with scripts/ab_variants.sh
 #ifndef SYN_RO_STEM
 #define SYN_RO_STEM 6
 #endif
