@@ -45,6 +45,9 @@ constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 #ifndef SYN_RO_B4
 #define SYN_RO_B4 15
 #endif
+#ifndef SYN_DW2_SMALL
+#define SYN_DW2_SMALL 1
+#endif
 #ifndef SYN_DW2_MAXW
 #define SYN_DW2_MAXW 30
 #endif
@@ -494,10 +497,10 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           ++n_g2;
         }
         SYN_TRACE(0, c, 4);
-        if constexpr (C::STRIDE == 1 && C::WO >= 15 && C::WO <= SYN_DW2_MAXW) {
-          // Stride-1 30^2 and 15^2 maps (on the 60^2 map of block 1 the units do not divide evenly between
-          // the channel groups and the row-pair items below are faster): the window loads of the depthwise conv are what the
-          // shared-memory pipe spends its time on, so an item is register-blocked over a 2 x 2 output patch
+        if constexpr (C::STRIDE == 1 && ((C::WO >= 15 && C::WO <= SYN_DW2_MAXW) || (SYN_DW2_SMALL && C::WO == 8))) {
+          // Stride-1 30^2, 15^2 and 8^2 maps (on the 60^2 map of block 1 the units do not divide evenly between
+          // the channel groups and the row-pair items below are faster): the window loads of the depthwise
+          // conv are what the shared-memory pipe spends its time on, so an item is register-blocked over a 2 x 2 output patch
           // of ONE channel quad -- 16 window + 10 tap LDS.128 per 16 outputs instead of 24 + 20.
           // A unit of 16 threads = 8 lanes along x (column pairs) x the two quads of a channel octet.
           // Lanes 4-7 are MIRRORED: they walk the four window columns right to left, use the taps with kx
@@ -505,18 +508,23 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           // an even number of 16-byte bank groups apart, and the mirror image shifts lanes 4-7 onto the odd
           // groups: every window load (quarter-warp) and every 8-byte operand store (half-warp) is
           // bank-conflict free.
-          constexpr int CPR = (C::WO + 1) / 2, XG2 = (CPR + 7) / 8, RP2 = (C::RO + 1) / 2;
-          constexpr int UPK = RP2 * XG2;                                   // units per (face, channel octet)
+          // 8x8 maps (SYN_DW2_SMALL; measured -2.2 % of the step with scripts/quick_variant_check.py): the 8 lanes
+          // are 4 column pairs x 2 row pairs; the second row pair lies 2 window rows = 4 bank groups further
+          // and is the mirrored half.
+          constexpr int XL = (C::WO >= 15) ? 8 : 4, YL = 8 / XL;           // lanes of a unit along x / along row pairs
+          constexpr int CPR = (C::WO + 1) / 2, XG2 = (CPR + XL - 1) / XL, RP2 = (C::RO + 1) / 2;
+          constexpr int RPU = (RP2 + YL - 1) / YL, UPK = RPU * XG2;        // units per (face, channel octet)
           const int l8 = tid & 7, qh = (tid >> 3) & 1;
+          const int lx = l8 % XL, ly = l8 / XL;
           const bool mir = (l8 & 4) != 0;
           const int units = KPG * nfaces * UPK;
           for (int u = gtid >> 4; u < units; u += TPG / 16) {
             const int kgl = u / (nfaces * UPK), r1 = u - kgl * (nfaces * UPK);
             const int f = r1 / UPK, r2 = r1 - f * UPK;
-            const int rp = r2 / XG2, xg = r2 - rp * XG2;
+            const int rpu = r2 / XG2, xg = r2 - rpu * XG2;
             const int kg = grp * KPG + kgl, j0 = kg * 8 + qh * 4;
-            const int ox = 2 * (xg * 8 + l8), oy = 2 * rp;
-            if (ox >= C::WO) continue;
+            const int ox = 2 * (xg * XL + lx), oy = 2 * (rpu * YL + ly);
+            if (ox >= C::WO || oy >= C::RO) continue;
             const bool two = (oy + 1 < C::RO), wide = (ox + 1 < C::WO);
             const float* wq = dwc + j0;
             float w[3][3][4];                                              // [ky][local kx][channel]
