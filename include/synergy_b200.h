@@ -43,10 +43,14 @@ enum {
 /* Compute engines for the 1x1 convolutions / basis products (syn_set_engine). */
 enum {
   SYN_ENGINE_SIMT_FP32 = 0,   /* CUDA-core fp32 FMA everywhere (bring-up / cross-check path)     */
-  SYN_ENGINE_TC_BF16X3 = 1,   /* tcgen05.mma, operands split in bf16 hi+lo, 3 MMAs per product,  */
-                              /* fp32 accumulation in TMEM: meets the 1e-4 parity bar            */
-  SYN_ENGINE_TC_FUSED = 2     /* engine 1 + stem/block1 and blocks 2..7 each fused into one      */
-                              /* kernel (expand -> depthwise -> project, hidden tensor on chip)  */
+  SYN_ENGINE_TC_SPLIT3 = 1,   /* tcgen05.mma, operands split in fp16 hi+lo with exact power-of-two  */
+                              /* pre-scaling, 3 MMAs per product (hi*hi + hi*lo + lo*hi), fp32      */
+                              /* accumulation in TMEM: meets the 1e-4 parity bar (a bf16 split, the  */
+                              /* first version, measured 1.7e-4 and was dropped); convs unfused      */
+  SYN_ENGINE_TC_BF16X3 = 1,   /* old name of SYN_ENGINE_TC_SPLIT3                                    */
+  SYN_ENGINE_TC_FUSED = 2     /* default: the same arithmetic with the stem + all 17 inverted-       */
+                              /* residual blocks each fused into one kernel (expand -> depthwise ->  */
+                              /* project, hidden tensor on chip), last conv fused with the pooling   */
 };
 
 typedef struct syn_handle syn_handle_t;

@@ -150,7 +150,8 @@ class _SynergyBase(nn.Module):
         return self.I2P._engine(device)
 
     def set_engine(self, kind: int) -> None:
-        """0 = fp32 CUDA-core engine, 1 = tcgen05 bf16x3 engine (include/synergy_b200.h)."""
+        """0 = fp32 CUDA-core engine, 1 = tcgen05 split-fp16 engine (unfused), 2 = fused tcgen05 engine (default);
+        see include/synergy_b200.h."""
         for eng in self.I2P._rt._engines.values():
             eng.set_engine(int(kind))
         self.I2P._rt.engine_kind = int(kind)
