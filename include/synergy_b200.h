@@ -147,6 +147,13 @@ int syn_poll_error(syn_handle_t* h, int* flag_out);
 int syn_debug_forward_until(syn_handle_t* h, const float* x_dev, int batch, int layer,
                             float* out_dev, void* stream);
 
+/* Host-only: the face-group plan the fused engine uses for a launch over `batch` faces on a GPU with
+ * `sms` SMs and `faces_per_tile` (1, 2 or 8) faces per full tile.  Groups [0, *split) hold
+ * faces_per_tile faces each; for two-face tiles the groups [*split, *face_groups) hold ONE face each
+ * (the partial last wave is split so that more SMs share it), otherwise the last group may be
+ * partial.  Lets the host logic be tested without a GPU. */
+int syn_debug_tile_plan(int batch, int sms, int faces_per_tile, int* split, int* face_groups);
+
 #ifdef __cplusplus
 }
 #endif

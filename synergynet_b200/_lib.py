@@ -58,6 +58,7 @@ SIGNATURES = {
     'syn_get_timings': (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_char_p), _I, C.POINTER(C.c_int)]),
     'syn_poll_error': (_I, [_P, C.POINTER(C.c_int)]),
     'syn_debug_forward_until': (_I, [_P, _F, _I, _I, _F, _P]),
+    'syn_debug_tile_plan': (_I, [_I, _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }
 
 

@@ -1074,6 +1074,18 @@ int syn_debug_read_trace(long long* out, int n) {
 }
 #endif
 
+int syn_debug_tile_plan(int batch, int sms, int faces_per_tile, int* split, int* face_groups) {
+  if (batch <= 0 || sms <= 0 || split == nullptr || face_groups == nullptr)
+    return fail(SYN_ERR_INVALID, "syn_debug_tile_plan: bad argument");
+  switch (faces_per_tile) {     // one representative configuration per tile size
+    case 1: fused_tile_plan<FusedB3>(batch, sms, *split, *face_groups); break;
+    case 2: fused_tile_plan<FusedB8>(batch, sms, *split, *face_groups); break;
+    case 8: fused_tile_plan<FusedB15>(batch, sms, *split, *face_groups); break;
+    default: return fail(SYN_ERR_INVALID, "syn_debug_tile_plan: faces_per_tile must be 1, 2 or 8");
+  }
+  return SYN_OK;
+}
+
 int syn_debug_forward_until(syn_handle_t* h, const float* x, int batch, int layer, float* out, void* stream) {
   SYN_CHECK_READY(h, "syn_debug_forward_until");
   if (x == nullptr || out == nullptr || batch <= 0 || layer < 0 || layer >= kNumConv)
