@@ -145,3 +145,22 @@ def test_product_package_never_imports_oracle():
         if fn.endswith('.py'):
             src = open(os.path.join(root, fn)).read()
             assert 'import oracle' not in src and 'from oracle' not in src, fn
+
+
+def test_shared_memory_lane_mappings_are_conflict_free():
+    """Executable form of the layout claims in DESIGN.md section 5 (scripts/bank_check.py restates the kernel's
+    lane -> address mappings): with the shipped choices every quarter-/half-warp access is conflict-free, and
+    the rejected alternatives are exactly the 2-way conflicts ncu showed before the fixes."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        'bank_check', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'scripts', 'bank_check.py'))
+    bc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bc)
+    for name, (nc, w, s, ro) in bc.CONFIGS.items():
+        assert bc.epi1_stores(nc) == 1, name
+        assert bc.dw_octet_loads(nc, w, s, swap=(s == 2)) == 1, name            # quad swap only on stride 2
+        assert bc.dw_octet_loads(nc, w, s, swap=(s != 2)) == 2, name
+        if s == 1 and w in (8, 15, 30):                                         # register-blocked path
+            assert bc.dw_quad_loads(nc, w, mirrored=True) == 1 and bc.dw_quad_loads(nc, w, mirrored=False) == 2, name
+            assert bc.a2_quad_stores(w, mirrored=True) == 1 and bc.a2_quad_stores(w, mirrored=False) == 2, name
