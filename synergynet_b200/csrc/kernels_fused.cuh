@@ -45,6 +45,9 @@ constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 #ifndef SYN_RO_B4
 #define SYN_RO_B4 15
 #endif
+#ifndef SYN_EPI2_STAGED
+#define SYN_EPI2_STAGED 0
+#endif
 #ifndef SYN_DW2_SMALL
 #define SYN_DW2_SMALL 1
 #endif
@@ -703,7 +706,49 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
       ++n_g2;
       tc_fence_after_sync();
       SYN_TRACE(0, 63, 3);
-      {
+      if constexpr (SYN_EPI2_STAGED && NWG == 4) {
+        // EXPERIMENTAL (-DSYN_EPI2_STAGED=1, compiled and reviewed but not yet run on a GPU): EPI2 through a
+        // shared-memory transpose.  With lane = pixel every 16-byte global store / skip load of a warp touches
+        // 32 different lines; here the four 128-thread slices take four adjacent 8-channel column blocks of
+        // one M tile, stage a [128 px][32 ch] block (16 KB in the A2 region, free after the last GEMM2; the
+        // 16-byte chunk index is XORed with the row so that both directions are conflict-free) and write it
+        // back with lanes along the channels: 128 contiguous bytes per pixel.
+        float* stage = reinterpret_cast<float*>(sA2);
+        constexpr int JB = (C::COUT_P + 31) / 32;
+        for (int t = 0; t < mt2; ++t) {
+          for (int jb = 0; jb < JB; ++jb) {
+            const int j0 = jb * 32 + wg * 8;
+            if (j0 < C::COUT_P) {                                 // warp-uniform (tcgen05.ld is .sync.aligned)
+              float v[8];
+              tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::D2_COL + t * C::COUT_P + j0, v);
+              const float4 b0 = *reinterpret_cast<const float4*>(sB3 + j0), b1 = *reinterpret_cast<const float4*>(sB3 + j0 + 4);
+              const float4 s0 = *reinterpret_cast<const float4*>(sB3 + C::COUT_P + j0);
+              const float4 s1 = *reinterpret_cast<const float4*>(sB3 + C::COUT_P + j0 + 4);
+              float* srow = stage + row * 32;
+              *reinterpret_cast<float4*>(srow + (((2 * wg) ^ (row & 7)) << 2)) =
+                  make_float4(fmaf(v[0], s0.x, b0.x), fmaf(v[1], s0.y, b0.y), fmaf(v[2], s0.z, b0.z), fmaf(v[3], s0.w, b0.w));
+              *reinterpret_cast<float4*>(srow + (((2 * wg + 1) ^ (row & 7)) << 2)) =
+                  make_float4(fmaf(v[4], s1.x, b1.x), fmaf(v[5], s1.y, b1.y), fmaf(v[6], s1.z, b1.z), fmaf(v[7], s1.w, b1.w));
+            }
+            asm volatile("bar.sync 5, %0;" ::"n"(NWT) : "memory");
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {                         // 128 px x 8 chunks of 16 B over 512 threads
+              const int idx = tid + k * NWT, px = idx >> 3, c4 = idx & 7;
+              const int m2 = t * 128 + px, j = jb * 32 + c4 * 4;
+              if (m2 < M2 && j < C::COUT) {
+                float4 o = *reinterpret_cast<const float4*>(stage + px * 32 + ((c4 ^ (px & 7)) << 2));
+                const size_t pix = (size_t)(f0 * C::WO + oy0) * C::WO + m2;   // tiles are contiguous in NHWC memory
+                if constexpr (C::RES) {                           // stride 1, CIN == COUT: same pixel of the block input
+                  const float4 r = __ldg(reinterpret_cast<const float4*>(p.x + pix * C::CIN + j));
+                  o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+                *reinterpret_cast<float4*>(p.y + pix * C::COUT + j) = o;
+              }
+            }
+            asm volatile("bar.sync 5, %0;" ::"n"(NWT) : "memory");   // the stage (and, after the last item, A2) may be rewritten
+          }
+        }
+      } else {
         constexpr int JW = (C::COUT_P % 32 == 0 && C::MT2 * (C::COUT_P / 32) >= 2 * NWG) ? 32
                            : (C::MT2 * (C::COUT_P / 16) >= 2 * NWG) ? 16 : 8;
         constexpr int JC = C::COUT_P / JW;
