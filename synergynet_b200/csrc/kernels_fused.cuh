@@ -45,6 +45,9 @@ constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 #ifndef SYN_RO_B4
 #define SYN_RO_B4 15
 #endif
+#ifndef SYN_DW_SPLIT_LAST
+#define SYN_DW_SPLIT_LAST 0
+#endif
 #ifndef SYN_EPI2_STAGED
 #define SYN_EPI2_STAGED 0
 #endif
@@ -618,78 +621,161 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           // the float offsets of the first / second quad); only the final operand store swaps them back.
           const bool swz = (C::STRIDE == 2) && (l8 & 4);
           const int q0 = swz ? 4 : 0, q1 = 4 - q0;
-          const int kg_end = (grp + 1) * KPG;                              // this group's channel octets
-          int kg = grp * KPG, it = gtid >> 3;
-          while (it >= per_kg && kg < kg_end) { it -= per_kg; ++kg; }
-          while (kg < kg_end) {
-            const int f = it / PER_FACE, r2 = it - f * PER_FACE;
-            const int rpg = r2 / XG, xg = r2 - rpg * XG;
-            // single rows with GY == 2: the two rows of a quarter-warp lie RPG rows apart (an even number),
-            // which keeps the two half-rows of lanes on disjoint bank groups
-            const int ox = xg * GX + lx, oy = (RPI == 2) ? 2 * (rpg * GY + ly) : rpg + RPG * ly;
-            if (ox < C::WO && oy < C::RO) {
-              const float* wbase = dwc + kg * 8;
-              const float* h0 = sH + (size_t)(f * C::HS_FACE + (oy * C::STRIDE) * C::HS_COLS + ox * C::STRIDE) * C::HS_STRIDE + kg * 8;
-              const bool two = (RPI == 2) && (oy + 1 < C::RO);             // second output row exists
-              float acc0[8], acc1[8];
-              {
-                const float4 a = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q0);
-                const float4 e = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q1);
-                acc0[0] = a.x; acc0[1] = a.y; acc0[2] = a.z; acc0[3] = a.w; acc0[4] = e.x; acc0[5] = e.y; acc0[6] = e.z; acc0[7] = e.w;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc1[j] = acc0[j];
-              }
-#pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
-                float w[3][8];
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                  const float4 a = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q0);
-                  const float4 e = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q1);
-                  w[dy][0] = a.x; w[dy][1] = a.y; w[dy][2] = a.z; w[dy][3] = a.w;
-                  w[dy][4] = e.x; w[dy][5] = e.y; w[dy][6] = e.z; w[dy][7] = e.w;
+          if constexpr (SYN_DW_SPLIT_LAST && RPI == 2 && GY == 1) {
+            // EXPERIMENTAL (-DSYN_DW_SPLIT_LAST=1, compiled, never run on a GPU): when the row-pair items do not
+            // fill the last round of the group's item slots (stem: 24 item groups on 16 slots), the pair items
+            // of that round are split into single-row items so that every slot has work: 1.6 rounds instead of 2.
+            auto item = [&](int kg, int it, int rowsel, bool single) {
+              const int f = it / PER_FACE, r2 = it - f * PER_FACE;
+              const int rpg = r2 / XG, xg = r2 - rpg * XG;
+              // single rows with GY == 2: the two rows of a quarter-warp lie RPG rows apart (an even number),
+              // which keeps the two half-rows of lanes on disjoint bank groups
+              const int ox = xg * GX + lx, oy = 2 * (rpg * GY + ly) + rowsel;
+              if (ox < C::WO && oy < C::RO) {
+                const float* wbase = dwc + kg * 8;
+                const float* h0 = sH + (size_t)(f * C::HS_FACE + (oy * C::STRIDE) * C::HS_COLS + ox * C::STRIDE) * C::HS_STRIDE + kg * 8;
+                const bool two = !single && (oy + 1 < C::RO);                // second output row exists and is ours
+                float acc0[8], acc1[8];
+                {
+                  const float4 a = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q0);
+                  const float4 e = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q1);
+                  acc0[0] = a.x; acc0[1] = a.y; acc0[2] = a.z; acc0[3] = a.w; acc0[4] = e.x; acc0[5] = e.y; acc0[6] = e.z; acc0[7] = e.w;
+  #pragma unroll
+                  for (int j = 0; j < 8; ++j) acc1[j] = acc0[j];
                 }
-#pragma unroll
-                for (int wr = 0; wr < NR; ++wr) {
-                  if (wr >= 3 && !two) continue;                           // rows only the (absent) second pixel needs
-                  const float* hp = h0 + (wr * C::HS_COLS + dx) * C::HS_STRIDE;
-                  const float4 a = *reinterpret_cast<const float4*>(hp + q0);
-                  const float4 e = *reinterpret_cast<const float4*>(hp + q1);
-                  const float d[8] = {a.x, a.y, a.z, a.w, e.x, e.y, e.z, e.w};
-                  if (wr < 3) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc0[j] = fmaf(d[j], w[wr][j], acc0[j]);
+  #pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                  float w[3][8];
+  #pragma unroll
+                  for (int dy = 0; dy < 3; ++dy) {
+                    const float4 a = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q0);
+                    const float4 e = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q1);
+                    w[dy][0] = a.x; w[dy][1] = a.y; w[dy][2] = a.z; w[dy][3] = a.w;
+                    w[dy][4] = e.x; w[dy][5] = e.y; w[dy][6] = e.z; w[dy][7] = e.w;
                   }
-                  if (RPI == 2 && wr >= C::STRIDE) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc1[j] = fmaf(d[j], w[wr - C::STRIDE][j], acc1[j]);
+  #pragma unroll
+                  for (int wr = 0; wr < NR; ++wr) {
+                    if (wr >= 3 && !two) continue;                           // rows only the (absent) second pixel needs
+                    const float* hp = h0 + (wr * C::HS_COLS + dx) * C::HS_STRIDE;
+                    const float4 a = *reinterpret_cast<const float4*>(hp + q0);
+                    const float4 e = *reinterpret_cast<const float4*>(hp + q1);
+                    const float d[8] = {a.x, a.y, a.z, a.w, e.x, e.y, e.z, e.w};
+                    if (wr < 3) {
+  #pragma unroll
+                      for (int j = 0; j < 8; ++j) acc0[j] = fmaf(d[j], w[wr][j], acc0[j]);
+                    }
+                    if (RPI == 2 && wr >= C::STRIDE) {
+  #pragma unroll
+                      for (int j = 0; j < 8; ++j) acc1[j] = fmaf(d[j], w[wr - C::STRIDE][j], acc1[j]);
+                    }
                   }
                 }
+                constexpr float kOut = 6.0f * kActScale;                   // relu6(x) * kActScale = sat(x/6) * 384
+                const int m2 = f * C::M2F + oy * C::WO + ox;
+                {
+                  uint32_t h[4], l[4];
+  #pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    split2_f16<false>(__saturatef(acc0[2 * j]) * kOut, __saturatef(acc0[2 * j + 1]) * kOut, h[j], l[j]);
+                  uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16;
+                  *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
+                  *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
+                }
+                if (two) {
+                  const int m3 = m2 + C::WO;
+                  uint32_t h[4], l[4];
+  #pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    split2_f16<false>(__saturatef(acc1[2 * j]) * kOut, __saturatef(acc1[2 * j + 1]) * kOut, h[j], l[j]);
+                  uint8_t* dst = sA2 + (m3 >> 7) * (128 * C::NC * 2) + ((m3 & 127) >> 3) * 128 + kg * 2048 + (m3 & 7) * 16;
+                  *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
+                  *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
+                }
               }
-              constexpr float kOut = 6.0f * kActScale;                   // relu6(x) * kActScale = sat(x/6) * 384
-              const int m2 = f * C::M2F + oy * C::WO + ox;
-              {
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  split2_f16<false>(__saturatef(acc0[2 * j]) * kOut, __saturatef(acc0[2 * j + 1]) * kOut, h[j], l[j]);
-                uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16;
-                *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
-              }
-              if (two) {
-                const int m3 = m2 + C::WO;
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  split2_f16<false>(__saturatef(acc1[2 * j]) * kOut, __saturatef(acc1[2 * j + 1]) * kOut, h[j], l[j]);
-                uint8_t* dst = sA2 + (m3 >> 7) * (128 * C::NC * 2) + ((m3 & 127) >> 3) * 128 + kg * 2048 + (m3 & 7) * 16;
-                *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
-              }
+            };
+            const int T = KPG * per_kg, S = TPG / 8, slot = gtid >> 3;
+            const int L = T % S;                                           // pair items left for a partial last round
+            const bool split = (L > 0) && (2 * L <= S);
+            const int t_pairs = split ? T - L : T;
+            for (int G = slot; G < t_pairs; G += S) item(grp * KPG + G / per_kg, G % per_kg, 0, false);
+            if (split && (slot >> 1) < L) {
+              const int G = t_pairs + (slot >> 1);
+              item(grp * KPG + G / per_kg, G % per_kg, slot & 1, true);
             }
-            it += TPG / 8;
+          } else {
+            const int kg_end = (grp + 1) * KPG;                              // this group's channel octets
+            int kg = grp * KPG, it = gtid >> 3;
             while (it >= per_kg && kg < kg_end) { it -= per_kg; ++kg; }
+            while (kg < kg_end) {
+              const int f = it / PER_FACE, r2 = it - f * PER_FACE;
+              const int rpg = r2 / XG, xg = r2 - rpg * XG;
+              // single rows with GY == 2: the two rows of a quarter-warp lie RPG rows apart (an even number),
+              // which keeps the two half-rows of lanes on disjoint bank groups
+              const int ox = xg * GX + lx, oy = (RPI == 2) ? 2 * (rpg * GY + ly) : rpg + RPG * ly;
+              if (ox < C::WO && oy < C::RO) {
+                const float* wbase = dwc + kg * 8;
+                const float* h0 = sH + (size_t)(f * C::HS_FACE + (oy * C::STRIDE) * C::HS_COLS + ox * C::STRIDE) * C::HS_STRIDE + kg * 8;
+                const bool two = (RPI == 2) && (oy + 1 < C::RO);             // second output row exists
+                float acc0[8], acc1[8];
+                {
+                  const float4 a = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q0);
+                  const float4 e = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q1);
+                  acc0[0] = a.x; acc0[1] = a.y; acc0[2] = a.z; acc0[3] = a.w; acc0[4] = e.x; acc0[5] = e.y; acc0[6] = e.z; acc0[7] = e.w;
+  #pragma unroll
+                  for (int j = 0; j < 8; ++j) acc1[j] = acc0[j];
+                }
+  #pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                  float w[3][8];
+  #pragma unroll
+                  for (int dy = 0; dy < 3; ++dy) {
+                    const float4 a = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q0);
+                    const float4 e = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q1);
+                    w[dy][0] = a.x; w[dy][1] = a.y; w[dy][2] = a.z; w[dy][3] = a.w;
+                    w[dy][4] = e.x; w[dy][5] = e.y; w[dy][6] = e.z; w[dy][7] = e.w;
+                  }
+  #pragma unroll
+                  for (int wr = 0; wr < NR; ++wr) {
+                    if (wr >= 3 && !two) continue;                           // rows only the (absent) second pixel needs
+                    const float* hp = h0 + (wr * C::HS_COLS + dx) * C::HS_STRIDE;
+                    const float4 a = *reinterpret_cast<const float4*>(hp + q0);
+                    const float4 e = *reinterpret_cast<const float4*>(hp + q1);
+                    const float d[8] = {a.x, a.y, a.z, a.w, e.x, e.y, e.z, e.w};
+                    if (wr < 3) {
+  #pragma unroll
+                      for (int j = 0; j < 8; ++j) acc0[j] = fmaf(d[j], w[wr][j], acc0[j]);
+                    }
+                    if (RPI == 2 && wr >= C::STRIDE) {
+  #pragma unroll
+                      for (int j = 0; j < 8; ++j) acc1[j] = fmaf(d[j], w[wr - C::STRIDE][j], acc1[j]);
+                    }
+                  }
+                }
+                constexpr float kOut = 6.0f * kActScale;                   // relu6(x) * kActScale = sat(x/6) * 384
+                const int m2 = f * C::M2F + oy * C::WO + ox;
+                {
+                  uint32_t h[4], l[4];
+  #pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    split2_f16<false>(__saturatef(acc0[2 * j]) * kOut, __saturatef(acc0[2 * j + 1]) * kOut, h[j], l[j]);
+                  uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16;
+                  *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
+                  *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
+                }
+                if (two) {
+                  const int m3 = m2 + C::WO;
+                  uint32_t h[4], l[4];
+  #pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    split2_f16<false>(__saturatef(acc1[2 * j]) * kOut, __saturatef(acc1[2 * j + 1]) * kOut, h[j], l[j]);
+                  uint8_t* dst = sA2 + (m3 >> 7) * (128 * C::NC * 2) + ((m3 & 127) >> 3) * 128 + kg * 2048 + (m3 & 7) * 16;
+                  *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
+                  *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
+                }
+              }
+              it += TPG / 8;
+              while (it >= per_kg && kg < kg_end) { it -= per_kg; ++kg; }
+            }
           }
         }
         SYN_TRACE(0, c, 5);
