@@ -45,6 +45,9 @@ constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 #ifndef SYN_RO_B4
 #define SYN_RO_B4 15
 #endif
+#ifndef SYN_PDL
+#define SYN_PDL 0
+#endif
 #ifndef SYN_DW_SPLIT_LAST
 #define SYN_DW_SPLIT_LAST 0
 #endif
@@ -214,6 +217,9 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
     }
   };
 
+#if SYN_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's prologue may overlap this one's tail
+#endif
   if (tid == 0) {
     mbar_init(smem_u32(&bar_w), 1);
     for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bar_wfull[i]), 1);
@@ -398,6 +404,12 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
           asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
       }
     };
+#if SYN_PDL
+    // EXPERIMENTAL (-DSYN_PDL=1, never run): programmatic dependent launch.  Everything above (barriers,
+    // TMEM, the zeroed window, the weight image) does not depend on the previous kernel; its output -- this
+    // kernel's input -- is first touched below, and this kernel's first global store comes later still.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     if ((int)blockIdx.x < ntiles) prep(blockIdx.x);
     prefetch_x(blockIdx.x + gridDim.x);
 
@@ -969,6 +981,9 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                    p.x + ((size_t)(fgq * 3 + ci) * kImg + iy_first + r_lo) * kImg, bytes, smem_u32(&bar_in));
       }
     };
+#if SYN_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // the stem's crop rows are the previous step's business only in
+#endif                                                     // theory (inputs), but the rule is kept uniform
     stage_rows(blockIdx.x);
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ntile_local) {

@@ -487,7 +487,23 @@ int launch_fused_nww(syn_handle* h, const FusedArgs& a, int grid, cudaStream_t s
     SYN_CUDA(cudaFuncSetAttribute(fused_mbconv_kernel<C, NWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set[h->device & 15] = true;
   }
+#if SYN_PDL
+  // programmatic dependent launch (experimental, see kernels_fused.cuh): the kernel may start while its
+  // predecessor in the stream drains; it waits (griddepcontrol.wait) before touching the predecessor's output
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3((NWW + 1) * 32);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SYN_CUDA(cudaLaunchKernelEx(&cfg, fused_mbconv_kernel<C, NWW>, a));
+#else
   fused_mbconv_kernel<C, NWW><<<grid, (NWW + 1) * 32, C::SMEM_BYTES, st>>>(a);
+#endif
   return SYN_OK;
 }
 
