@@ -543,7 +543,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
             const int kg = grp * KPG + kgl, j0 = kg * 8 + qh * 4;
             const int ox = 2 * (xg * XL + lx), oy = 2 * (rpu * YL + ly);
             if (ox >= C::WO || oy >= C::RO) continue;
-            const bool two = (oy + 1 < C::RO), wide = (ox + 1 < C::WO);
+            const bool two = (oy + 1 < C::RO);
             const float* wq = dwc + j0;
             float w[3][3][4];                                              // [ky][local kx][channel]
 #pragma unroll
@@ -605,7 +605,6 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                 *reinterpret_cast<uint2*>(dst + C::A2_PLANE) = make_uint2(l0, l1);
               }
             }
-            (void)wide;
           }
         } else
         {
