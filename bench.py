@@ -170,9 +170,19 @@ def cpu_reference_throughput(seconds: float, batch: int = 64):
         el = time.perf_counter() - t0
         if el >= seconds and n >= 3:
             break
+    # configs[0]: the reference's own CPU-runnable case, one face per call (latency, same thread count)
+    x1 = x[:1]
+    for _ in range(3):
+        rp.reconstruct_vertex_62(rp.mobilenetv2_forward(sd, x1)[0].numpy(), basis)
+    t1 = time.perf_counter()
+    for _ in range(20):
+        rp.reconstruct_vertex_62(rp.mobilenetv2_forward(sd, x1)[0].numpy(), basis)
+    b1_ms = (time.perf_counter() - t1) / 20 * 1e3
     return {'value': n * batch / el, 'unit': 'faces/s', 'cores': best_n, 'kind': 'port',
+            'batch1_ms_per_face': b1_ms,
             'sample': f'{n} batches of {batch} faces ({el:.1f} s), forward_test + 68-landmark reconstruction, '
-                      f'torch {torch.__version__} CPU fp32, best of a thread sweep on {ncpu} logical CPUs'}, step
+                      f'torch {torch.__version__} CPU fp32, best of a thread sweep on {ncpu} logical CPUs; '
+                      f'batch1_ms_per_face = configs[0] (one face per call, 20 calls)'}, step
 
 
 def run_reference(args):
