@@ -149,9 +149,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
         const float* pose = reinterpret_cast<const float*>(sB + sb * kDnBSlot + kDnBTile) + fofs * 12;
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + grp * 192 + fofs;
         float sx[16], sy[16], sz[16];
-        tmem_ld16(trow, sx);
-        tmem_ld16(trow + 64, sy);
-        tmem_ld16(trow + 128, sz);
+        tmem_ld16x3(trow, trow + 64, trow + 128, sx, sy, sz);   // three loads in flight, one wait
         const int b0 = ft * kDnFaces + fofs;
         if (v < p.nver) {
 #pragma unroll
@@ -174,15 +172,23 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
       tc_fence_before_sync();
       mbar_arrive(smem_u32(&bar_dfree[grp]));
     }
-  } else if (tid == kDnEpiWarps * 32) {
+  } else if (warp == kDnEpiWarps) {
     // ------------------------------ loader + MMA issuer -------------------------------------------
+    // The whole warp runs this control flow convergently; bulk copies and MMA batches sit under one
+    // elect.sync each, so the descriptors come straight from uniform registers (a `tid == X` branch costs
+    // ~170 cycles per MMA, tools/umma_timing: 36 MMAs per item made the issuer the bottleneck of round 1).
     const uint32_t idesc = make_idesc_f16(128, kDnFaces);
+    const uint32_t d_hi = smem_desc_hi(128);
+    const uint32_t a_lo = smem_desc_lo(smem_u32(sA), 2048);
     auto load_b = [&](int it, int s) {
-      const int ft = it % p.n_ftiles;
-      uint8_t* dst = sB + s * kDnBSlot;
-      mbar_expect_tx(smem_u32(&bar_bfull[s]), kDnBSlot);
-      bulk_g2s(smem_u32(dst), p.alpha_img + (size_t)ft * kDnBTile, kDnBTile, smem_u32(&bar_bfull[s]));
-      bulk_g2s(smem_u32(dst + kDnBTile), p.pose + (size_t)ft * kDnFaces * 12, kDnPoseTile, smem_u32(&bar_bfull[s]));
+      if (elect_one()) {
+        const int ft = it % p.n_ftiles;
+        uint8_t* dst = sB + s * kDnBSlot;
+        mbar_expect_tx(smem_u32(&bar_bfull[s]), kDnBSlot);
+        bulk_g2s(smem_u32(dst), p.alpha_img + (size_t)ft * kDnBTile, kDnBTile, smem_u32(&bar_bfull[s]));
+        bulk_g2s(smem_u32(dst + kDnBTile), p.pose + (size_t)ft * kDnFaces * 12, kDnPoseTile, smem_u32(&bar_bfull[s]));
+      }
+      __syncwarp();
     };
     auto dfree_wait = [&](int j) {                                   // epilogue finished item j (>= 0)
       mbar_wait(smem_u32(&bar_dfree[j & 1]), (uint32_t)(j >> 1) & 1, p.err);
@@ -199,30 +205,36 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
         // epilogue thread past its bar_a wait, both implied by the epilogue having finished item i-1
         if (i >= 1) dfree_wait(i - 1);
         cur_vt = vt;
-        mbar_expect_tx(smem_u32(&bar_a), kDnATile + kDnMetaTile);
-        bulk_g2s(smem_u32(sA), p.basis_img + (size_t)vt * kDnATile, kDnATile, smem_u32(&bar_a));
-        bulk_g2s(smem_u32(sMeta + ((vt - vt0) & 1) * (kDnMetaTile / 4)), p.meta + (size_t)vt * 6 * 128, kDnMetaTile,
-                 smem_u32(&bar_a));
+        if (elect_one()) {
+          mbar_expect_tx(smem_u32(&bar_a), kDnATile + kDnMetaTile);
+          bulk_g2s(smem_u32(sA), p.basis_img + (size_t)vt * kDnATile, kDnATile, smem_u32(&bar_a));
+          bulk_g2s(smem_u32(sMeta + ((vt - vt0) & 1) * (kDnMetaTile / 4)), p.meta + (size_t)vt * 6 * 128, kDnMetaTile,
+                   smem_u32(&bar_a));
+        }
+        __syncwarp();
         mbar_wait(smem_u32(&bar_a), (uint32_t)(vt - vt0) & 1, p.err);
       }
       const int sb = i % kDnBSlots;
       mbar_wait(smem_u32(&bar_bfull[sb]), (uint32_t)(i / kDnBSlots) & 1, p.err);
       if (i >= 2) dfree_wait(i - 2);                               // TMEM buffer s drained
       tc_fence_after_sync();
-      const uint32_t b_hi = smem_u32(sB + sb * kDnBSlot);
+      const uint32_t b_lo = smem_desc_lo(smem_u32(sB + sb * kDnBSlot), 1024);
+      if (elect_one()) {
 #pragma unroll
-      for (int plane = 0; plane < 3; ++plane) {
+        for (int plane = 0; plane < 3; ++plane) {
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a_base = smem_u32(sA) + (plane * 2 + (pass == 2 ? 1 : 0)) * kDnAPlane;   // W: hi,hi,lo
-          const uint32_t b_base = b_hi + (pass == 1 ? kDnBPlane : 0);                             // alpha: hi,lo,hi
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a_off = (plane * 2 + (pass == 2 ? 1 : 0)) * kDnAPlane;   // W: hi,hi,lo
+            const uint32_t b_off = (pass == 1 ? kDnBPlane : 0);                     // alpha: hi,lo,hi
 #pragma unroll
-          for (int ks = 0; ks < kDnK / 16; ++ks)
-            umma_f16(tmem + s * 192 + plane * 64, make_smem_desc(a_base + ks * 4096, 2048, 128),
-                     make_smem_desc(b_base + ks * 2048, 1024, 128), idesc, (pass > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < kDnK / 16; ++ks)
+              umma_f16(tmem + s * 192 + plane * 64, desc64(d_hi, a_lo + ((a_off + ks * 4096) >> 4)),
+                       desc64(d_hi, b_lo + ((b_off + ks * 2048) >> 4)), idesc, (pass > 0 || ks > 0) ? 1u : 0u);
+          }
         }
+        umma_commit(smem_u32(&bar_dfull[s]));
       }
-      umma_commit(smem_u32(&bar_dfull[s]));
+      __syncwarp();
       // prefetch alpha/pose three items ahead into the slot last used by item i-1 (MMA + epilogue done)
       if (it + kDnBSlots - 1 < it1) {
         if (i >= 1) dfree_wait(i - 1);

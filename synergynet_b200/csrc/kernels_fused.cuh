@@ -30,6 +30,9 @@ namespace syn {
 constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 // tile shapes / chunk widths / batching depths worth re-measuring when the kernel changes: build variants
 // with -D... and compare them on one box with scripts/ab_variants.sh
+#ifndef SYN_OCC2
+#define SYN_OCC2 0
+#endif
 #ifndef SYN_RO_STEM
 #define SYN_RO_STEM 6
 #endif
@@ -58,7 +61,7 @@ constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 #define SYN_DW2_SMALL 1
 #endif
 #ifndef SYN_DW2_MAXW
-#define SYN_DW2_MAXW 30
+#define SYN_DW2_MAXW (SYN_OCC2 ? 60 : 30)
 #endif
 #ifndef SYN_NC_B56
 #define SYN_NC_B56 64
@@ -74,6 +77,11 @@ constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 #endif
 #ifndef SYN_NC_B17
 #define SYN_NC_B17 32
+#endif
+// SYN_OCC2: two co-resident CTAs per SM (8 worker warps each, <= 112 KB smem, <= 256 TMEM columns) for the
+// stem ... block 13, so that one CTA's EPI1 / GEMM waits / EPI2 overlap the other's depthwise phase
+#ifndef SYN_OCC2
+#define SYN_OCC2 0
 #endif
 #ifndef SYN_EB_STEM
 #define SYN_EB_STEM 1
@@ -91,8 +99,9 @@ constexpr int round_up_c(int a, int b) { return ceil_div_c(a, b) * b; }
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 template <int CIN_, int CHID_, int NC_, int COUT_, int W_, int STRIDE_, int RO_, int FACES_, bool RES_, bool STEM_,
-          int WSTREAM_>
+          int WSTREAM_, int OCC_ = 1>
 struct FusedCfg {
+  static constexpr int OCC = OCC_;               // co-resident CTAs per SM this configuration is sized for (1 or 2)
   static constexpr bool STEM = STEM_;            // GEMM1 = im2col(3x3 s2 stem conv), CIN = 27 taps
   static constexpr bool RES = RES_;
   static constexpr bool WSTREAM = WSTREAM_ > 0;  // weights streamed per chunk (ring of WSTREAM_ slots) instead of resident
@@ -146,6 +155,8 @@ struct FusedCfg {
   static_assert(FACES_ == 1 || RO_ == WO, "multi-face tiles hold whole faces");
   static_assert(XA_COL + MT1 * CIN_P <= 512, "TMEM columns");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+  // two CTAs per SM: 228 KB minus 1 KB reserved per CTA minus the static barriers; both CTAs allocate TM_COLS columns
+  static_assert(OCC_ == 1 || (OCC_ == 2 && SMEM_BYTES <= 112 * 1024 && TM_COLS <= 256), "occupancy-2 budget");
   static_assert(N2 % 16 == 0 && N2 <= 256, "MMA N");
   static_assert(WSTREAM_ == 0 || (WSTREAM_ >= 2 && WSTREAM_ <= 4 && NCHUNK >= WSTREAM_), "weight ring");
 };
@@ -178,7 +189,7 @@ __device__ long long g_fused_trace[18 * 2 * 64 * 8];
 
 // NWW = worker warps (multiple of 4: TMEM lane quarter = warp % 4); the issuer is warp NWW.
 template <class C, int NWW>
-__global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const FusedArgs p) {
+__global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(const FusedArgs p) {
   constexpr int NWT = NWW * 32;          // worker threads
   constexpr int NWG = NWW / 4;           // worker groups: group g owns every NWG-th (tile, column-chunk) pair
   static_assert(NWW % 4 == 0 && NWW >= 4 && NWW <= 16, "worker warps");
@@ -545,33 +556,33 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
             if (ox >= C::WO || oy >= C::RO) continue;
             const bool two = (oy + 1 < C::RO);
             const float* wq = dwc + j0;
-            float w[3][3][4];                                              // [ky][local kx][channel]
+            float2 w[3][3][2];                                             // [ky][local kx][channel pair] (FFMA2 operands)
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
               for (int kl = 0; kl < 3; ++kl) {
                 const float4 t4 = *reinterpret_cast<const float4*>(wq + (ky * 3 + (mir ? 2 - kl : kl)) * C::NC);
-                w[ky][kl][0] = t4.x; w[ky][kl][1] = t4.y; w[ky][kl][2] = t4.z; w[ky][kl][3] = t4.w;
+                w[ky][kl][0] = make_float2(t4.x, t4.y); w[ky][kl][1] = make_float2(t4.z, t4.w);
               }
-            float acc[2][2][4];                                            // [output row][local column][channel]
+            float2 acc[2][2][2];                                           // [output row][local column][channel pair]
             {
               const float4 b4 = *reinterpret_cast<const float4*>(wq + 9 * C::NC);
 #pragma unroll
               for (int ro = 0; ro < 2; ++ro)
 #pragma unroll
-                for (int a = 0; a < 2; ++a) { acc[ro][a][0] = b4.x; acc[ro][a][1] = b4.y; acc[ro][a][2] = b4.z; acc[ro][a][3] = b4.w; }
+                for (int a = 0; a < 2; ++a) { acc[ro][a][0] = make_float2(b4.x, b4.y); acc[ro][a][1] = make_float2(b4.z, b4.w); }
             }
             // window columns ox-1 .. ox+2 are Hs columns ox .. ox+3; local column ic is Hs column ox+ic (ox+3-ic mirrored)
             const float* hb = sH + (size_t)(f * C::HS_FACE + oy * C::HS_COLS + ox + (mir ? 3 : 0)) * C::HS_STRIDE + j0;
             const int cstep = mir ? -C::HS_STRIDE : C::HS_STRIDE;
 #pragma unroll
             for (int ic = 0; ic < 4; ++ic) {
-              float d[4][4];
+              float2 d[4][2];
 #pragma unroll
               for (int r = 0; r < 4; ++r) {
                 if (r == 3 && !two) continue;                              // row only the absent second output row needs
                 const float4 t4 = *reinterpret_cast<const float4*>(hb + r * (C::HS_COLS * C::HS_STRIDE) + ic * cstep);
-                d[r][0] = t4.x; d[r][1] = t4.y; d[r][2] = t4.z; d[r][3] = t4.w;
+                d[r][0] = make_float2(t4.x, t4.y); d[r][1] = make_float2(t4.z, t4.w);
               }
 #pragma unroll
               for (int a = 0; a < 2; ++a) {
@@ -580,10 +591,10 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) acc[0][a][j] = fmaf(d[ky][j], w[ky][kl][j], acc[0][a][j]);
+                  for (int j = 0; j < 2; ++j) acc[0][a][j] = ffma2(d[ky][j], w[ky][kl][j], acc[0][a][j]);
                   if (two) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[1][a][j] = fmaf(d[ky + 1][j], w[ky][kl][j], acc[1][a][j]);
+                    for (int j = 0; j < 2; ++j) acc[1][a][j] = ffma2(d[ky + 1][j], w[ky][kl][j], acc[1][a][j]);
                   }
                 }
               }
@@ -598,8 +609,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                 if (col >= C::WO) continue;                                // odd width: the last pair has one column
                 const int m2 = f * C::M2F + (oy + ro) * C::WO + col;
                 uint32_t h0, l0, h1, l1;
-                split2_f16<false>(__saturatef(acc[ro][a][0]) * kOut, __saturatef(acc[ro][a][1]) * kOut, h0, l0);
-                split2_f16<false>(__saturatef(acc[ro][a][2]) * kOut, __saturatef(acc[ro][a][3]) * kOut, h1, l1);
+                split2_f16<false>(__saturatef(acc[ro][a][0].x) * kOut, __saturatef(acc[ro][a][0].y) * kOut, h0, l0);
+                split2_f16<false>(__saturatef(acc[ro][a][1].x) * kOut, __saturatef(acc[ro][a][1].y) * kOut, h1, l1);
                 uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16 + qh * 8;
                 *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
                 *reinterpret_cast<uint2*>(dst + C::A2_PLANE) = make_uint2(l0, l1);
@@ -646,23 +657,23 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                 const float* wbase = dwc + kg * 8;
                 const float* h0 = sH + (size_t)(f * C::HS_FACE + (oy * C::STRIDE) * C::HS_COLS + ox * C::STRIDE) * C::HS_STRIDE + kg * 8;
                 const bool two = !single && (oy + 1 < C::RO);                // second output row exists and is ours
-                float acc0[8], acc1[8];
+                float2 acc0[4], acc1[4];                                     // channel pairs (FFMA2 operands)
                 {
                   const float4 a = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q0);
                   const float4 e = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q1);
-                  acc0[0] = a.x; acc0[1] = a.y; acc0[2] = a.z; acc0[3] = a.w; acc0[4] = e.x; acc0[5] = e.y; acc0[6] = e.z; acc0[7] = e.w;
+                  acc0[0] = make_float2(a.x, a.y); acc0[1] = make_float2(a.z, a.w); acc0[2] = make_float2(e.x, e.y); acc0[3] = make_float2(e.z, e.w);
   #pragma unroll
-                  for (int j = 0; j < 8; ++j) acc1[j] = acc0[j];
+                  for (int j = 0; j < 4; ++j) acc1[j] = acc0[j];
                 }
   #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
-                  float w[3][8];
+                  float2 w[3][4];
   #pragma unroll
                   for (int dy = 0; dy < 3; ++dy) {
                     const float4 a = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q0);
                     const float4 e = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q1);
-                    w[dy][0] = a.x; w[dy][1] = a.y; w[dy][2] = a.z; w[dy][3] = a.w;
-                    w[dy][4] = e.x; w[dy][5] = e.y; w[dy][6] = e.z; w[dy][7] = e.w;
+                    w[dy][0] = make_float2(a.x, a.y); w[dy][1] = make_float2(a.z, a.w);
+                    w[dy][2] = make_float2(e.x, e.y); w[dy][3] = make_float2(e.z, e.w);
                   }
   #pragma unroll
                   for (int wr = 0; wr < NR; ++wr) {
@@ -670,14 +681,14 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                     const float* hp = h0 + (wr * C::HS_COLS + dx) * C::HS_STRIDE;
                     const float4 a = *reinterpret_cast<const float4*>(hp + q0);
                     const float4 e = *reinterpret_cast<const float4*>(hp + q1);
-                    const float d[8] = {a.x, a.y, a.z, a.w, e.x, e.y, e.z, e.w};
+                    const float2 d[4] = {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(e.x, e.y), make_float2(e.z, e.w)};
                     if (wr < 3) {
   #pragma unroll
-                      for (int j = 0; j < 8; ++j) acc0[j] = fmaf(d[j], w[wr][j], acc0[j]);
+                      for (int j = 0; j < 4; ++j) acc0[j] = ffma2(d[j], w[wr][j], acc0[j]);
                     }
                     if (RPI == 2 && wr >= C::STRIDE) {
   #pragma unroll
-                      for (int j = 0; j < 8; ++j) acc1[j] = fmaf(d[j], w[wr - C::STRIDE][j], acc1[j]);
+                      for (int j = 0; j < 4; ++j) acc1[j] = ffma2(d[j], w[wr - C::STRIDE][j], acc1[j]);
                     }
                   }
                 }
@@ -687,7 +698,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                   uint32_t h[4], l[4];
   #pragma unroll
                   for (int j = 0; j < 4; ++j)
-                    split2_f16<false>(__saturatef(acc0[2 * j]) * kOut, __saturatef(acc0[2 * j + 1]) * kOut, h[j], l[j]);
+                    split2_f16<false>(__saturatef(acc0[j].x) * kOut, __saturatef(acc0[j].y) * kOut, h[j], l[j]);
                   uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16;
                   *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
                   *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
@@ -697,7 +708,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                   uint32_t h[4], l[4];
   #pragma unroll
                   for (int j = 0; j < 4; ++j)
-                    split2_f16<false>(__saturatef(acc1[2 * j]) * kOut, __saturatef(acc1[2 * j + 1]) * kOut, h[j], l[j]);
+                    split2_f16<false>(__saturatef(acc1[j].x) * kOut, __saturatef(acc1[j].y) * kOut, h[j], l[j]);
                   uint8_t* dst = sA2 + (m3 >> 7) * (128 * C::NC * 2) + ((m3 & 127) >> 3) * 128 + kg * 2048 + (m3 & 7) * 16;
                   *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
                   *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
@@ -727,23 +738,23 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                 const float* wbase = dwc + kg * 8;
                 const float* h0 = sH + (size_t)(f * C::HS_FACE + (oy * C::STRIDE) * C::HS_COLS + ox * C::STRIDE) * C::HS_STRIDE + kg * 8;
                 const bool two = (RPI == 2) && (oy + 1 < C::RO);             // second output row exists
-                float acc0[8], acc1[8];
+                float2 acc0[4], acc1[4];                                     // channel pairs (FFMA2 operands)
                 {
                   const float4 a = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q0);
                   const float4 e = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q1);
-                  acc0[0] = a.x; acc0[1] = a.y; acc0[2] = a.z; acc0[3] = a.w; acc0[4] = e.x; acc0[5] = e.y; acc0[6] = e.z; acc0[7] = e.w;
+                  acc0[0] = make_float2(a.x, a.y); acc0[1] = make_float2(a.z, a.w); acc0[2] = make_float2(e.x, e.y); acc0[3] = make_float2(e.z, e.w);
   #pragma unroll
-                  for (int j = 0; j < 8; ++j) acc1[j] = acc0[j];
+                  for (int j = 0; j < 4; ++j) acc1[j] = acc0[j];
                 }
   #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
-                  float w[3][8];
+                  float2 w[3][4];
   #pragma unroll
                   for (int dy = 0; dy < 3; ++dy) {
                     const float4 a = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q0);
                     const float4 e = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q1);
-                    w[dy][0] = a.x; w[dy][1] = a.y; w[dy][2] = a.z; w[dy][3] = a.w;
-                    w[dy][4] = e.x; w[dy][5] = e.y; w[dy][6] = e.z; w[dy][7] = e.w;
+                    w[dy][0] = make_float2(a.x, a.y); w[dy][1] = make_float2(a.z, a.w);
+                    w[dy][2] = make_float2(e.x, e.y); w[dy][3] = make_float2(e.z, e.w);
                   }
   #pragma unroll
                   for (int wr = 0; wr < NR; ++wr) {
@@ -751,14 +762,14 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                     const float* hp = h0 + (wr * C::HS_COLS + dx) * C::HS_STRIDE;
                     const float4 a = *reinterpret_cast<const float4*>(hp + q0);
                     const float4 e = *reinterpret_cast<const float4*>(hp + q1);
-                    const float d[8] = {a.x, a.y, a.z, a.w, e.x, e.y, e.z, e.w};
+                    const float2 d[4] = {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(e.x, e.y), make_float2(e.z, e.w)};
                     if (wr < 3) {
   #pragma unroll
-                      for (int j = 0; j < 8; ++j) acc0[j] = fmaf(d[j], w[wr][j], acc0[j]);
+                      for (int j = 0; j < 4; ++j) acc0[j] = ffma2(d[j], w[wr][j], acc0[j]);
                     }
                     if (RPI == 2 && wr >= C::STRIDE) {
   #pragma unroll
-                      for (int j = 0; j < 8; ++j) acc1[j] = fmaf(d[j], w[wr - C::STRIDE][j], acc1[j]);
+                      for (int j = 0; j < 4; ++j) acc1[j] = ffma2(d[j], w[wr - C::STRIDE][j], acc1[j]);
                     }
                   }
                 }
@@ -768,7 +779,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                   uint32_t h[4], l[4];
   #pragma unroll
                   for (int j = 0; j < 4; ++j)
-                    split2_f16<false>(__saturatef(acc0[2 * j]) * kOut, __saturatef(acc0[2 * j + 1]) * kOut, h[j], l[j]);
+                    split2_f16<false>(__saturatef(acc0[j].x) * kOut, __saturatef(acc0[j].y) * kOut, h[j], l[j]);
                   uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16;
                   *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
                   *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
@@ -778,7 +789,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
                   uint32_t h[4], l[4];
   #pragma unroll
                   for (int j = 0; j < 4; ++j)
-                    split2_f16<false>(__saturatef(acc1[2 * j]) * kOut, __saturatef(acc1[2 * j + 1]) * kOut, h[j], l[j]);
+                    split2_f16<false>(__saturatef(acc1[j].x) * kOut, __saturatef(acc1[j].y) * kOut, h[j], l[j]);
                   uint8_t* dst = sA2 + (m3 >> 7) * (128 * C::NC * 2) + ((m3 & 127) >> 3) * 128 + kg * 2048 + (m3 & 7) * 16;
                   *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
                   *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
@@ -1050,6 +1061,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const F
 // CTAs; the remainder becomes single-face groups when those still fit in one wave.
 template <class C>
 inline void fused_tile_plan(int batch, int sms, int& split, int& face_groups) {
+  sms *= C::OCC;                                            // CTAs of one wave
   if constexpr (C::FACES == 2) {
     const int full = batch / 2, odd = batch & 1, rem = full % sms;
     split = (2 * rem + odd <= sms) ? full - rem : full;
@@ -1062,6 +1074,18 @@ inline void fused_tile_plan(int batch, int sms, int& split, int& face_groups) {
 
 // ---- the instantiations used by the backbone (SURVEY.md section 8(a) shape table) -------------------
 //                          CIN CHID NC COUT  W  S  RO FACES RES    STEM   weight ring slots (0 = resident)
+#if SYN_OCC2
+// occupancy-2 shapes: smaller strips / chunks so that two CTAs (8 worker warps each) share an SM
+using FusedStemB1 = FusedCfg<27, 32, 32, 16, 60, 1, 4, 1, false, true, 0, 2>;         // features[0] + features[1]
+using FusedB2 = FusedCfg<16, 96, 32, 24, 60, 2, 3, 1, false, false, 0, 2>;            // features[2]
+using FusedB3 = FusedCfg<24, 144, 16, 24, 30, 1, 10, 1, true, false, 0, 2>;           // features[3]
+using FusedB4 = FusedCfg<24, 144, 16, 32, 30, 2, 5, 1, false, false, 0, 2>;           // features[4]
+using FusedB56 = FusedCfg<32, 192, 32, 32, 15, 1, 15, 1, true, false, 3, 2>;          // features[5], [6]
+using FusedB7 = FusedCfg<32, 192, 32, 64, 15, 2, 8, 1, false, false, 3, 2>;           // features[7]
+using FusedB8 = FusedCfg<64, 384, 32, 64, 8, 1, 8, 2, true, false, 3, 2>;             // features[8..10]
+using FusedB11 = FusedCfg<64, 384, 32, 96, 8, 1, 8, 2, false, false, 2, 2>;           // features[11]
+using FusedB12 = FusedCfg<96, 576, 32, 96, 8, 1, 8, 2, true, false, 2, 2>;            // features[12], [13]
+#else
 using FusedStemB1 = FusedCfg<27, 32, 32, 16, 60, 1, SYN_RO_STEM, 1, false, true, 0>;    // features[0] + features[1]
 using FusedB2 = FusedCfg<16, 96, 32, 24, 60, 2, SYN_RO_B2, 1, false, false, 0>;       // features[2]
 using FusedB3 = FusedCfg<24, 144, 16, 24, 30, 1, 15, 1, true, false, 0>;      // features[3]
@@ -1071,6 +1095,7 @@ using FusedB7 = FusedCfg<32, 192, SYN_NC_B7, 64, 15, 2, 8, 1, false, false, 0>; 
 using FusedB8 = FusedCfg<64, 384, 64, 64, 8, 1, 8, 2, true, false, 3>;         // features[8..10]
 using FusedB11 = FusedCfg<64, 384, 64, 96, 8, 1, 8, 2, false, false, 2>;       // features[11]
 using FusedB12 = FusedCfg<96, 576, SYN_NC_B12, 96, 8, 1, 8, 2, true, false, SYN_NC_B12 == 32 ? 3 : 2>;        // features[12], [13]
+#endif
 using FusedB14 = FusedCfg<96, 576, SYN_NC_B14, 160, 8, 2, 4, 2, false, false, SYN_NC_B14 == 32 ? 3 : 2>;      // features[14]
 using FusedB15 = FusedCfg<160, 960, 32, 160, 4, 1, 4, 8, true, false, 2>;      // features[15], [16]
 using FusedB17 = FusedCfg<160, 960, SYN_NC_B17, 320, 4, 1, 4, 8, false, false, SYN_NC_B17 == 16 ? 3 : 2>;     // features[17]

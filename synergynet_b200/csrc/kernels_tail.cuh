@@ -124,12 +124,19 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_conv_pool_kernel(const T
       tc_fence_before_sync();
       mbar_arrive(smem_u32(&bar_dfree[buf]));
     }
-  } else if (tid == 12 * 32) {
+  } else if (warp == 12) {
     // ------------------------------ MMA issuer ----------------------------------------------------
-    mbar_expect_tx(smem_u32(&bar_w), kTailWBytes);
-    bulk_g2s(smem_u32(sW), p.wimg + (size_t)slice * kTailWBytes, kTailWBytes, smem_u32(&bar_w));
+    // converged warp, MMA batches under one elect.sync with hoisted descriptors (a `tid == X` branch costs
+    // ~170 cycles per MMA against the 64-cycle operand-read floor of these M = N = 128 SS MMAs)
+    if (elect_one()) {
+      mbar_expect_tx(smem_u32(&bar_w), kTailWBytes);
+      bulk_g2s(smem_u32(sW), p.wimg + (size_t)slice * kTailWBytes, kTailWBytes, smem_u32(&bar_w));
+    }
+    __syncwarp();
     mbar_wait(smem_u32(&bar_w), 0, p.err);
     const uint32_t idesc = make_idesc_f16(128, 128);
+    const uint32_t d_hi = smem_desc_hi(128);
+    const uint32_t w_lo = smem_desc_lo(smem_u32(sW), 2048), x_lo = smem_desc_lo(smem_u32(sX), 2048);
     uint32_t g = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int buf = i & 1;
@@ -139,18 +146,21 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_conv_pool_kernel(const T
         const int s = g & 1;
         mbar_wait(smem_u32(&bar_xfull[s]), (g >> 1) & 1, p.err);
         tc_fence_after_sync();
+        if (elect_one()) {
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a_base = smem_u32(sW) + kc * 2 * kTailPlane + (pass == 2 ? kTailPlane : 0);   // W: hi,hi,lo
-          const uint32_t b_base = smem_u32(sX) + s * kTailXStage + (pass == 1 ? kTailPlane : 0);       // X: hi,lo,hi
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a_off = kc * 2 * kTailPlane + (pass == 2 ? kTailPlane : 0);   // W: hi,hi,lo
+            const uint32_t b_off = s * kTailXStage + (pass == 1 ? kTailPlane : 0);       // X: hi,lo,hi
 #pragma unroll
-          for (int ks = 0; ks < kTailKC / 16; ++ks)
-            umma_f16(tmem + buf * 128, make_smem_desc(a_base + ks * 4096, 2048, 128),
-                     make_smem_desc(b_base + ks * 4096, 2048, 128), idesc, (kc > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < kTailKC / 16; ++ks)
+              umma_f16(tmem + buf * 128, desc64(d_hi, w_lo + ((a_off + ks * 4096) >> 4)),
+                       desc64(d_hi, x_lo + ((b_off + ks * 4096) >> 4)), idesc, (kc > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&bar_xempty[s]));
+          if (kc == kTailChunks - 1) umma_commit(smem_u32(&bar_dfull[buf]));
         }
-        umma_commit(smem_u32(&bar_xempty[s]));
+        __syncwarp();
       }
-      umma_commit(smem_u32(&bar_dfull[buf]));
     }
   }
   tc_fence_before_sync();

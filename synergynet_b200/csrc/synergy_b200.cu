@@ -517,12 +517,16 @@ int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, 
 #endif
   fused_tile_plan<C>(batch, h->sm_count, a.split, a.face_groups);
   const int ntiles = a.face_groups * C::STRIPS;
-  const int grid = std::min(ntiles, h->sm_count);
+  const int grid = std::min(ntiles, C::OCC * h->sm_count);
   int rc;
-  switch (fused_worker_warps()) {
-    case 8: rc = launch_fused_nww<C, 8>(h, a, grid, st); break;
-    case 12: rc = launch_fused_nww<C, 12>(h, a, grid, st); break;
-    default: rc = launch_fused_nww<C, 16>(h, a, grid, st); break;
+  if constexpr (C::OCC == 2) {
+    rc = launch_fused_nww<C, 8>(h, a, grid, st);            // two co-resident CTAs per SM, 8 worker warps each
+  } else {
+    switch (fused_worker_warps()) {
+      case 8: rc = launch_fused_nww<C, 8>(h, a, grid, st); break;
+      case 12: rc = launch_fused_nww<C, 12>(h, a, grid, st); break;
+      default: rc = launch_fused_nww<C, 16>(h, a, grid, st); break;
+    }
   }
   if (rc != SYN_OK) return rc;
   SYN_LAUNCH_CHECK("fused_mbconv_kernel");
