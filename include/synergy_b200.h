@@ -48,9 +48,12 @@ enum {
                               /* accumulation in TMEM: meets the 1e-4 parity bar (a bf16 split, the  */
                               /* first version, measured 1.7e-4 and was dropped); convs unfused      */
   SYN_ENGINE_TC_BF16X3 = 1,   /* old name of SYN_ENGINE_TC_SPLIT3                                    */
-  SYN_ENGINE_TC_FUSED = 2     /* default: the same arithmetic with the stem + all 17 inverted-       */
+  SYN_ENGINE_TC_FUSED = 2,    /* default: the same arithmetic with the stem + all 17 inverted-       */
                               /* residual blocks each fused into one kernel (expand -> depthwise ->  */
                               /* project, hidden tensor on chip), last conv fused with the pooling   */
+  SYN_ENGINE_TC_FUSED_1PASS = 3 /* NOT parity-grade, never the default: engine 2 with ONE fp16 MMA per */
+                              /* product (hi*hi only) in the backbone.  Exists to show how much of    */
+                              /* the step is the 3x precision tax; misses the 1e-4 bar */
 };
 
 typedef struct syn_handle syn_handle_t;
@@ -129,6 +132,30 @@ int syn_forward_landmarks_u8(syn_handle_t* h, const uint8_t* x_u8_dev, int batch
 int syn_forward_landmarks_host_u8(syn_handle_t* h, const uint8_t* x_u8_host, int batch,
                                   float* params62_host, float* lmk_host);
 
+/* ---- PointNet refinement heads and the training-forward losses -------------
+ * net 0 = MLP_for (backbone_nets/pointnet_backbone.py:7-64): layer 0..8 = conv1..conv9 (+bn1..bn9);
+ * net 1 = MLP_rev (:67-106): layer 0..4 = conv1..conv5, 5/6/7 = conv6_1 / conv6_2 / conv6_3 (+their BN).
+ * Conv1d weights are (cout, cin, 1) fp32 host arrays, BatchNorm1d is eval-mode and folded at commit. */
+int syn_pointnet_set_layer(syn_handle_t* h, int net, int layer, const float* w_host, int cout, int cin,
+                           const float* conv_bias_host, const float* bn_weight_host, const float* bn_bias_host,
+                           const float* bn_mean_host, const float* bn_var_host, float eps);
+int syn_pointnet_commit(syn_handle_t* h, int net);            /* after syn_commit */
+/* MLP_for.forward(x, avgpool, shape_code, expr_code) (pointnet_backbone.py:31-64) as called at
+ * model_building.py:149-150: lmk_dev (B,3,68), pool1280_dev (B,1280), params62_dev (B,62; columns 12:52 and
+ * 52:62 are the shape / expression codes) -> residual_dev (B,3,68) = point_residual and/or
+ * refined_dev (B,3,68) = lmk + 0.05 * point_residual (either may be NULL). */
+int syn_mlp_for(syn_handle_t* h, const float* lmk_dev, const float* pool1280_dev, const float* params62_dev,
+                int batch, float* residual_dev, float* refined_dev, void* stream);
+/* MLP_rev.forward (pointnet_backbone.py:90-106, model_building.py:153): lmk_dev (B,3,68) -> (B,62). */
+int syn_mlp_rev(syn_handle_t* h, const float* lmk_dev, int batch, float* params62_dev, void* stream);
+/* WingLoss(omega=10, epsilon=2) (loss_definition.py:8-27): mean over the B*3*n_pts coordinates -> out_dev[0]. */
+int syn_wing_loss(syn_handle_t* h, const float* pred_dev, const float* target_dev, int batch, int n_pts,
+                  float* out_dev, void* stream);
+/* ParamLoss (loss_definition.py:29-42), one value per sample -> out_dev (B): mode 0 = 'normal', 1 = 'only_3dmm'
+ * (input[:, :50] against target[:, 12:62], as the reference does). */
+int syn_param_loss(syn_handle_t* h, const float* input_dev, const float* target_dev, int batch, int mode,
+                   float* out_dev, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------------*/
 /* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
 int64_t syn_launch_count(const syn_handle_t* h);
@@ -139,8 +166,16 @@ int64_t syn_launch_count(const syn_handle_t* h);
 int syn_set_timing(syn_handle_t* h, int on);
 int syn_get_timings(syn_handle_t* h, float* ms_out, const char** names_out, int max_entries, int* n_out);
 /* Synchronise the device and report (then clear) the sticky flag a bounded in-kernel wait raises
- * when it times out (pipeline protocol bug); *flag_out = 0 means no kernel ever timed out. */
+ * when it times out (pipeline protocol bug); *flag_out = 0 means no kernel ever timed out.
+ * While the flag is raised every compute entry point returns SYN_ERR_CUDA instead of results. */
 int syn_poll_error(syn_handle_t* h, int* flag_out);
+/* The same flag WITHOUT synchronising or clearing (it lives in mapped host memory): cheap enough to
+ * call after any host-side synchronisation point. */
+int syn_peek_error(const syn_handle_t* h, int* flag_out);
+/* Synchronise and report (then clear) the "activation clamped" flag: the split-fp16 engines scale
+ * block inputs by 64 and clamp to the fp16 range, i.e. |x| > ~937 saturates; the fp32 engine
+ * (SYN_ENGINE_SIMT_FP32) has no such limit.  *flag_out != 0: results of engines 1-3 are suspect. */
+int syn_poll_saturation(syn_handle_t* h, int* flag_out);
 /* Run the backbone on x_dev but stop after convolution `layer` (0..51) and copy its NHWC
  * activation (batch*h_out*h_out*cout floats, residual already added for project convs) to
  * out_dev.  Per-layer parity tests only. */

@@ -133,6 +133,10 @@ def mobilenet_v2(pretrained: bool = False, **_):
 
 
 class _PointMLPParams(nn.Module):
+    """Parameter container in the reference's key schema; ``forward`` runs in the sm_100a library through the engine
+    of the model that owns the module (``_engine_provider`` is installed by ``model_building._SynergyBase``)."""
+    _NET = -1
+
     def __init__(self, num_pts, convs, bns):
         super().__init__()
         for name, (ci, co) in convs.items():
@@ -140,14 +144,19 @@ class _PointMLPParams(nn.Module):
         for name, c in bns.items():
             setattr(self, name, nn.BatchNorm1d(c))
         self.num_pts = num_pts
+        object.__setattr__(self, '_engine_provider', None)
 
-    def forward(self, *a, **k):  # pragma: no cover
-        raise RuntimeError('PointNet refinement heads are training-only in the reference '
-                           '(model_building.py:149-155) and outside the inference hot path')
+    def _engine(self, t):
+        if self._engine_provider is None:
+            raise RuntimeError(f'{type(self).__name__}: not attached to a SynergyNet model (its engine owns the GPU state)')
+        if self.num_pts != 68:
+            raise RuntimeError('the sm_100a PointNet heads are built for 68 landmarks (MLP_for(68) / MLP_rev(68))')
+        return self._engine_provider(t, self._NET)
 
 
 class MLP_for(_PointMLPParams):
-    """Key schema of pointnet_backbone.py:7-29 (forwardDirection.*, 63 keys)."""
+    """pointnet_backbone.py:7-64 (forwardDirection.*, 63 keys)."""
+    _NET = 0
 
     def __init__(self, num_pts):
         chans = [(3, 64), (64, 64), (64, 64), (64, 128), (128, 1024), (2418, 512), (512, 256),
@@ -155,9 +164,20 @@ class MLP_for(_PointMLPParams):
         super().__init__(num_pts, {f'conv{i + 1}': c for i, c in enumerate(chans)},
                          {f'bn{i + 1}': c[1] for i, c in enumerate(chans)})
 
+    def forward(self, x, other_input1=None, other_input2=None, other_input3=None):
+        """point_residual (B,3,68) from landmarks x (B,3,68), avgpool (B,1280), shape code (B,40), expression code (B,10)
+        (pointnet_backbone.py:31-64; eval-mode BatchNorm)."""
+        import torch
+        params = torch.zeros((x.shape[0], 62), device=x.device, dtype=torch.float32)
+        params[:, 12:52] = other_input2
+        params[:, 52:62] = other_input3
+        res, _ = self._engine(x).mlp_for(x, other_input1, params)
+        return res if x.is_cuda else res.to(x.device)
+
 
 class MLP_rev(_PointMLPParams):
-    """Key schema of pointnet_backbone.py:67-88 (reverseDirection.*, 56 keys)."""
+    """pointnet_backbone.py:67-106 (reverseDirection.*, 56 keys)."""
+    _NET = 1
 
     def __init__(self, num_pts):
         chans = [(3, 64), (64, 64), (64, 64), (64, 128), (128, 1024)]
@@ -167,3 +187,8 @@ class MLP_rev(_PointMLPParams):
             convs[f'conv{tag}'] = (1024, dim)
             bns[f'bn{tag}'] = dim
         super().__init__(num_pts, convs, bns)
+
+    def forward(self, x, other_input1=None, other_input2=None, other_input3=None):
+        """(B,62) = [rot12 | shape40 | expr10] regressed back from landmarks x (B,3,68) (pointnet_backbone.py:90-106)."""
+        out = self._engine(x).mlp_rev(x)
+        return out if x.is_cuda else out.to(x.device)

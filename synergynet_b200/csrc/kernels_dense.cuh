@@ -250,4 +250,184 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------------------------
+// Face-major variant for the dense mesh (configs[2]).  The kernel above walks vertex-tile major: a CTA writes 512 B
+// to each of 64 faces x 3 rows and moves on to OTHER faces, so every DRAM page is touched once per visit (measured:
+// 2.1 TB/s of 6.5).  Here a CTA keeps one 64-face tile and walks over consecutive vertex tiles: each of its 192
+// output rows grows by 512 contiguous bytes per item, which L2 write-back turns into long DRAM bursts.  The price is
+// a new basis tile per item; it streams from L2 (40 MB image, resident) coordinate plane by coordinate plane (32 KB =
+// hi + lo of one coordinate) through a 4-slot ring, two planes ahead of the MMAs.
+//   bar_pfull[slot]   plane landed                                                    loader -> issuer
+//   bar_pempty[slot]  the 12 MMAs that read the plane are complete (tcgen05.commit)  -> loader
+//   bar_mfull[slot]   meta rows of item i (slot i % 4) landed                         loader -> epilogue
+//   bar_bfull / bar_dfull / bar_dfree as above
+constexpr int kFmPlane = 2 * kDnAPlane;                   // 32 KB: [hi|lo] of one coordinate of one vertex tile
+constexpr int kFmPSlots = 4, kFmMetaSlots = 4;
+constexpr int kFmSmem = kFmPSlots * kFmPlane + kFmMetaSlots * kDnMetaTile + kDnBSlots * kDnBSlot + 1024;
+static_assert(kDnATile == 3 * kFmPlane, "basis tile = three coordinate planes");
+static_assert(kFmSmem <= 227 * 1024, "shared memory");
+
+__global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const DenseArgs p) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_pfull[kFmPSlots], bar_pempty[kFmPSlots], bar_mfull[kFmMetaSlots], bar_bfull[kDnBSlots],
+      bar_dfull[2], bar_dfree[2];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sP = smem;                                                                      // plane ring
+  float* sMeta = reinterpret_cast<float*>(smem + kFmPSlots * kFmPlane);                   // kFmMetaSlots meta tiles
+  uint8_t* sB = smem + kFmPSlots * kFmPlane + kFmMetaSlots * kDnMetaTile;                 // alpha + pose ring
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int items = p.n_vtiles * p.n_ftiles;
+  const int per = (items + gridDim.x - 1) / gridDim.x;
+  const int it0 = min((int)blockIdx.x * per, items), it1 = min(it0 + per, items);
+  const int n_items = it1 - it0;
+
+  if (tid == 0) {
+    for (int i = 0; i < kFmPSlots; ++i) { mbar_init(smem_u32(&bar_pfull[i]), 1); mbar_init(smem_u32(&bar_pempty[i]), 1); }
+    for (int i = 0; i < kFmMetaSlots; ++i) mbar_init(smem_u32(&bar_mfull[i]), 1);
+    for (int i = 0; i < kDnBSlots; ++i) mbar_init(smem_u32(&bar_bfull[i]), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_dfull[i]), 1);
+      mbar_init(smem_u32(&bar_dfree[i]), kDnEpiWarps * 16);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kDnEpiWarps) tmem_alloc<512>(smem_u32(&tmem_base_s));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < kDnEpiWarps) {
+    // ------------------------------ epilogue (two groups of 8 warps, alternate items) -----------------------------
+    const int grp = warp >> 3, half = (warp >> 2) & 1;
+    const int lane_v = tid & 127;
+    for (int i = grp; i < n_items; i += 2) {
+      const int it = it0 + i;
+      const int ft = it / p.n_vtiles, vt = it - ft * p.n_vtiles;
+      const int sb = i % kDnBSlots;
+      mbar_wait(smem_u32(&bar_bfull[sb]), (uint32_t)(i / kDnBSlots) & 1, p.err);      // pose tile visible to this thread
+      mbar_wait(smem_u32(&bar_mfull[i % kFmMetaSlots]), (uint32_t)(i / kFmMetaSlots) & 1, p.err);   // meta rows visible
+      mbar_wait(smem_u32(&bar_dfull[grp]), (uint32_t)(i >> 1) & 1, p.err);
+      tc_fence_after_sync();
+      const float* m = sMeta + (i % kFmMetaSlots) * (kDnMetaTile / 4);
+      const float ux = m[0 * 128 + lane_v], uy = m[1 * 128 + lane_v], uz = m[2 * 128 + lane_v];
+      const float ox = m[3 * 128 + lane_v], oy = m[4 * 128 + lane_v], oz = m[5 * 128 + lane_v];
+      const int v = vt * 128 + lane_v;
+#pragma unroll
+      for (int rnd = 0; rnd < 2; ++rnd) {                            // 2 x 16 faces per thread
+        const int fofs = half * 32 + rnd * 16;
+        const float* pose = reinterpret_cast<const float*>(sB + sb * kDnBSlot + kDnBTile) + fofs * 12;
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + grp * 192 + fofs;
+        float sx[16], sy[16], sz[16];
+        tmem_ld16x3(trow, trow + 64, trow + 128, sx, sy, sz);
+        const int b0 = ft * kDnFaces + fofs;
+        if (v < p.nver) {
+#pragma unroll
+          for (int f = 0; f < 16; ++f) {
+            if (b0 + f < p.batch) {
+              const float4 r0 = *reinterpret_cast<const float4*>(pose + f * 12);
+              const float4 r1 = *reinterpret_cast<const float4*>(pose + f * 12 + 4);
+              const float4 r2 = *reinterpret_cast<const float4*>(pose + f * 12 + 8);
+              const float X = fmaf(sx[f], ox, ux), Y = fmaf(sy[f], oy, uy), Z = fmaf(sz[f], oz, uz);
+              float vx = fmaf(r0.x, X, fmaf(r0.y, Y, r0.z * Z)) + r0.w;
+              float vy = fmaf(r1.x, X, fmaf(r1.y, Y, r1.z * Z)) + r1.w;
+              float vz = fmaf(r2.x, X, fmaf(r2.y, Y, r2.z * Z)) + r2.w;
+              if (p.transform) vy = (float)(kImg + 1) - vy;          // model_building.py:129,137
+              float* o = p.out + (size_t)(b0 + f) * 3 * p.nver + v;
+              __stcs(o, vx); __stcs(o + p.nver, vy); __stcs(o + 2 * (size_t)p.nver, vz);
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(smem_u32(&bar_dfree[grp]));
+    }
+  } else if (warp == kDnEpiWarps) {
+    // ------------------------------ loader + MMA issuer (converged warp, elect.sync) ------------------------------
+    const uint32_t idesc = make_idesc_f16(128, kDnFaces);
+    const uint32_t d_hi = smem_desc_hi(128);
+    const int n_planes = 3 * n_items;
+    int next_plane = 0;                                               // next plane to request
+    auto dfree_wait = [&](int j) { mbar_wait(smem_u32(&bar_dfree[j & 1]), (uint32_t)(j >> 1) & 1, p.err); };
+    // Request planes up to (and including) `upto`.  Plane q reuses the slot of plane q - 4, whose MMAs must be complete
+    // (bar_pempty, consumed strictly in order).  The meta rows of item i go to slot i % 4, last read by the epilogue
+    // of item i - 4: plane 0 of item i is never requested before the MMAs of item i - 2 were issued, and those waited
+    // for dfree(i - 4), so that slot is known to be free without another wait.
+    auto request_planes = [&](int upto) {
+      for (; next_plane <= upto && next_plane < n_planes; ++next_plane) {
+        const int q = next_plane, slot = q % kFmPSlots, i = q / 3, c = q - 3 * i;
+        if (q >= kFmPSlots) mbar_wait(smem_u32(&bar_pempty[slot]), (uint32_t)(q / kFmPSlots - 1) & 1, p.err);
+        if (elect_one()) {
+          const int it = it0 + i;
+          const int ft = it / p.n_vtiles, vt = it - ft * p.n_vtiles;
+          mbar_expect_tx(smem_u32(&bar_pfull[slot]), kFmPlane);
+          bulk_g2s(smem_u32(sP + slot * kFmPlane), p.basis_img + (size_t)vt * kDnATile + (size_t)c * kFmPlane, kFmPlane,
+                   smem_u32(&bar_pfull[slot]));
+          if (c == 0) {
+            const int ms = i % kFmMetaSlots;
+            mbar_expect_tx(smem_u32(&bar_mfull[ms]), kDnMetaTile);
+            bulk_g2s(smem_u32(sMeta + ms * (kDnMetaTile / 4)), p.meta + (size_t)vt * 6 * 128, kDnMetaTile, smem_u32(&bar_mfull[ms]));
+          }
+        }
+        __syncwarp();
+      }
+    };
+    auto load_b = [&](int i, int s) {
+      if (elect_one()) {
+        const int ft = (it0 + i) / p.n_vtiles;
+        uint8_t* dst = sB + s * kDnBSlot;
+        mbar_expect_tx(smem_u32(&bar_bfull[s]), kDnBSlot);
+        bulk_g2s(smem_u32(dst), p.alpha_img + (size_t)ft * kDnBTile, kDnBTile, smem_u32(&bar_bfull[s]));
+        bulk_g2s(smem_u32(dst + kDnBTile), p.pose + (size_t)ft * kDnFaces * 12, kDnPoseTile, smem_u32(&bar_bfull[s]));
+      }
+      __syncwarp();
+    };
+    for (int k = 0; k < kDnBSlots - 1; ++k)
+      if (k < n_items) load_b(k, k);
+    request_planes(kFmPSlots - 2);                                   // planes 0..2 in flight before the first MMA
+    for (int i = 0; i < n_items; ++i) {
+      const int s = i & 1, sb = i % kDnBSlots;
+      mbar_wait(smem_u32(&bar_bfull[sb]), (uint32_t)(i / kDnBSlots) & 1, p.err);
+      if (i >= 2) dfree_wait(i - 2);                                 // TMEM buffer s drained
+      const uint32_t b_lo = smem_desc_lo(smem_u32(sB + sb * kDnBSlot), 1024);
+      for (int c = 0; c < 3; ++c) {
+        const int q = 3 * i + c, slot = q % kFmPSlots;
+        request_planes(q + 2);                                       // keep two planes ahead of the MMAs in flight
+        mbar_wait(smem_u32(&bar_pfull[slot]), (uint32_t)(q / kFmPSlots) & 1, p.err);
+        tc_fence_after_sync();
+        const uint32_t a_lo = smem_desc_lo(smem_u32(sP + slot * kFmPlane), 2048);
+        if (elect_one()) {
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a_off = (pass == 2 ? kDnAPlane : 0);                     // W: hi,hi,lo
+            const uint32_t b_off = (pass == 1 ? kDnBPlane : 0);                     // alpha: hi,lo,hi
+#pragma unroll
+            for (int ks = 0; ks < kDnK / 16; ++ks)
+              umma_f16(tmem + s * 192 + c * 64, desc64(d_hi, a_lo + ((a_off + ks * 4096) >> 4)),
+                       desc64(d_hi, b_lo + ((b_off + ks * 2048) >> 4)), idesc, (pass > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&bar_pempty[slot]));                  // the plane may be overwritten once these MMAs are done
+          if (c == 2) umma_commit(smem_u32(&bar_dfull[s]));
+        }
+        __syncwarp();
+      }
+      // alpha/pose three items ahead, into the slot last used by item i-1 (its MMAs and epilogue are done)
+      if (i + kDnBSlots - 1 < n_items) {
+        if (i >= 1) dfree_wait(i - 1);
+        load_b(i + kDnBSlots - 1, (i + kDnBSlots - 1) % kDnBSlots);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kDnEpiWarps) {
+    __syncwarp();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
 }  // namespace syn

@@ -48,17 +48,22 @@ constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 #ifndef SYN_RO_B4
 #define SYN_RO_B4 15
 #endif
+// programmatic dependent launch over the fused launches (measured -1.1 % of the step, round 2)
 #ifndef SYN_PDL
-#define SYN_PDL 0
-#endif
-#ifndef SYN_DW_SPLIT_LAST
-#define SYN_DW_SPLIT_LAST 0
-#endif
-#ifndef SYN_EPI2_STAGED
-#define SYN_EPI2_STAGED 0
+#define SYN_PDL 1
 #endif
 #ifndef SYN_DW2_SMALL
 #define SYN_DW2_SMALL 1
+#endif
+// SYN_DW3: depthwise items of one channel quad x 2 output rows x 5 output columns on the stride-1 60^2 / 30^2 / 15^2 maps
+// (15.2 shared-memory loads per 16 outputs instead of 26 + conflicted tap loads)
+#ifndef SYN_DW3
+#define SYN_DW3 1
+#endif
+// output columns of a DW3 item: 3 (76 live registers; 17 warps leave 96 per thread: 5 warps share one sub-partition's
+// 16 K registers) or 5 (fewer loads per output, needs ~105 registers: spills unless the CTA has <= 16 warps)
+#ifndef SYN_DW3_S
+#define SYN_DW3_S 3
 #endif
 #ifndef SYN_DW2_MAXW
 #define SYN_DW2_MAXW (SYN_OCC2 ? 60 : 30)
@@ -117,10 +122,20 @@ struct FusedCfg {
   static constexpr int ROWS_MAX = (RWIN < W_ ? RWIN : W_);               // valid input rows per face
   static constexpr int M1_MAX = FACES_ * ROWS_MAX * W_;
   static constexpr int MT1 = ceil_div_c(M1_MAX, 128);
-  static constexpr int M2F = RO_ * WO;                                   // output pixels per face
+  // DW3 (register-blocked 2 x 5 depthwise items, lanes = NS column segments x NR row pairs): the lane mapping is
+  // bank-conflict free only for certain row pitches of the hidden window (HS_COLS) and of the GEMM2 operand (WOP)
+  static constexpr int DW3_S = SYN_DW3_S;                                // output columns per item (odd)
+  static constexpr bool DW3 = SYN_DW3 && STRIDE_ == 1 && (WO % 15 == 0);                  // 60, 30, 15
+  static constexpr int DW3_NS = (WO >= 60) ? 4 : 2, DW3_NR = 8 / DW3_NS;
+  // pitch of an output row in the GEMM2 M index (pad columns are computed by the MMA and never read)
+  static constexpr int WOP = !DW3 ? WO : (DW3_NS == 4 ? WO + ((6 - WO % 4) % 4) : WO | 1);
+  static constexpr int M2F = RO_ * WOP;                                  // GEMM2 rows per face
   static constexpr int M2_MAX = FACES_ * M2F;
   static constexpr int MT2 = ceil_div_c(M2_MAX, 128);
-  static constexpr int HS_COLS = W_ + 2, HS_FACE = RWIN * HS_COLS, HS_PIX = FACES_ * HS_FACE, HS_STRIDE = NC_ + 4;
+  static constexpr int HS_COLS = (DW3 && DW3_NS == 2) ? ((W_ + 2) | 1) : W_ + 2;      // DW3 with 4 row-pair lanes: odd pitch
+  static constexpr int HS_FACE = RWIN * HS_COLS, HS_PIX = FACES_ * HS_FACE, HS_STRIDE = NC_ + 4;
+  static constexpr int DWS = NC_ + 4;     // floats between the tap rows of a chunk: mirrored lanes of the 2x2 depthwise read
+                                          // taps kx and 2-kx, which must not lie a multiple of 128 bytes apart
   static constexpr int D2_COL = round_up_c(MT1 * NC_, 32);
   // EPI1 TMEM loads kept in flight per wait (measured per map size, scripts/ab_variants.sh)
   static constexpr int EPI1_BATCH = STEM_ ? SYN_EB_STEM : W_ >= 30 ? SYN_EB_WIDE : W_ >= 15 ? SYN_EB_MID : SYN_EB_SMALL;
@@ -134,7 +149,7 @@ struct FusedCfg {
   static constexpr int W3_PLANE = COUT_P * NC_ * 2;
   static constexpr int DW_ROWS = 12;   // 9 taps, depthwise bias, expand bias b1, expand output scale s1
   static constexpr int CH_W1 = 0, CH_W3 = 2 * W1_PLANE, CH_DW = CH_W3 + 2 * W3_PLANE;
-  static constexpr int CHUNK_BYTES = round_up_c(CH_DW + DW_ROWS * NC_ * 4, 128);
+  static constexpr int CHUNK_BYTES = round_up_c(CH_DW + DW_ROWS * DWS * 4, 128);
   static constexpr int W_BYTES = B3_BYTES + NCHUNK * CHUNK_BYTES;
   static constexpr int WSTAGES = WSTREAM_ > 0 ? WSTREAM_ : NCHUNK;       // chunk slots held in smem
   // ---- shared memory carve-up --------------------------------------------------------------------
@@ -159,6 +174,13 @@ struct FusedCfg {
   static_assert(OCC_ == 1 || (OCC_ == 2 && SMEM_BYTES <= 112 * 1024 && TM_COLS <= 256), "occupancy-2 budget");
   static_assert(N2 % 16 == 0 && N2 <= 256, "MMA N");
   static_assert(WSTREAM_ == 0 || (WSTREAM_ >= 2 && WSTREAM_ <= 4 && NCHUNK >= WSTREAM_), "weight ring");
+  // DW3 bank-conflict conditions.  Window loads: lane (s, r) of a quarter-warp reads 16 bytes at group offset
+  // S*G*s + 2*HS_COLS*G*r (S = DW3_S, G = HS_STRIDE/4, both odd) and the eight offsets must differ mod 8; operand stores: 8-byte halves
+  // at 16-byte slot (S*s + 2*WOP*r) mod 8.  NS=4,NR=2 needs the row-pair term = 4 (mod 8), NS=2,NR=4 needs it = 2 or 6.
+  static_assert(!DW3 || ((HS_STRIDE / 4) % 2 == 1), "pixel pitch must be an odd number of 16-byte groups");
+  static_assert(!DW3 || (DW3_NS == 4 ? (2 * HS_COLS * (HS_STRIDE / 4)) % 8 == 4 : (2 * HS_COLS * (HS_STRIDE / 4)) % 4 == 2), "window row pitch");
+  static_assert(!DW3 || (DW3_NS == 4 ? (2 * WOP) % 8 == 4 : (2 * WOP) % 4 == 2), "operand row pitch");
+  static_assert(!DW3 || FACES_ == 1 || WOP == WO, "padded output rows only with one face per tile");
 };
 
 struct FusedArgs {
@@ -169,7 +191,9 @@ struct FusedArgs {
   int batch;
   int split;             // two-face configs: face groups >= split hold ONE face (tail wave, see fused_tile_plan)
   int face_groups;       // number of face groups (tiles = face_groups * STRIPS)
-  int* err;
+  int* err;              // sticky time-out flag of the bounded mbarrier waits (mapped pinned host memory)
+  int* sat;              // sticky "a block input was clamped to the fp16 range" flag (device memory)
+  int npass;             // 3 = split-fp16 x3 (hi*hi + hi*lo + lo*hi); 1 = single fp16 pass (SYN_ENGINE_TC_FUSED_1PASS)
 #ifdef SYN_FUSED_TRACE
   int trace_id;          // backbone block of this launch (1..17)
 #endif
@@ -324,32 +348,38 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
       {
         constexpr int KG = C::CIN_P / 8;
         constexpr int ITERS = (C::MT1 * KG + NWG - 1) / NWG;             // items per thread
-        constexpr int PB = C::STEM ? 1 : (ITERS < SYN_PREP_BATCH ? ITERS : SYN_PREP_BATCH);
+        constexpr int PB = ITERS < SYN_PREP_BATCH ? ITERS : SYN_PREP_BATCH;
         const int n_items = mt1 * KG;
         for (int e0 = wg; e0 < n_items; e0 += PB * NWG) {
           float v[PB][8];
           if constexpr (C::STEM) {
-            const int t = e0 / KG, kg = e0 - t * KG;
-            const int mr = t * 128 + row;                     // FACES == 1
+            // im2col of the 3x3 stride-2 pad-1 stem conv from the staged rows: k = (ci*3+ky)*3+kx.  All PB items of a
+            // thread are gathered before the first conversion (independent shared loads in flight instead of one
+            // load -> convert -> TMEM-store chain per item); the kg switch makes every tap offset a compile-time constant.
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[0][j] = 0.f;
-            if (mr < M1) {
-              // im2col of the 3x3 stride-2 pad-1 stem conv from the staged rows: k = (ci*3+ky)*3+kx;
-              // the kg switch makes every tap offset a compile-time constant
-              const int yl = mr / C::W, xx = mr - yl * C::W;
-              const float* base = sIn + (2 * yl) * C::IN_STRIDE + 2 * xx - 1;   // column 2xx-1+kx; -1 is the zero pad
+            for (int u = 0; u < PB; ++u) {
 #pragma unroll
-              for (int kgc = 0; kgc < KG; ++kgc)
-                if (kg == kgc) {
+              for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+              const int e = e0 + u * NWG;
+              if (e >= n_items) continue;
+              const int t = e / KG, kg = e - t * KG;
+              const int mr = t * 128 + row;                     // FACES == 1
+              if (mr < M1) {
+                const int yl = mr / C::W, xx = mr - yl * C::W;
+                const float* base = sIn + (2 * yl) * C::IN_STRIDE + 2 * xx - 1;   // column 2xx-1+kx; -1 is the zero pad
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const int k = kgc * 8 + j;
-                    if (k < 27) {
-                      const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
-                      if (kx > 0 || xx > 0) v[0][j] = base[(ci * C::IN_ROWS + ky) * C::IN_STRIDE + kx];
+                for (int kgc = 0; kgc < KG; ++kgc)
+                  if (kg == kgc) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const int k = kgc * 8 + j;
+                      if (k < 27) {
+                        const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+                        if (kx > 0 || xx > 0) v[u][j] = base[(ci * C::IN_ROWS + ky) * C::IN_STRIDE + kx];
+                      }
                     }
                   }
-                }
+              }
             }
           } else {
             float4 qa[PB], qb[PB];
@@ -380,6 +410,10 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
             if (e < n_items) {                                // warp-uniform: tcgen05.st is .sync.aligned
               const int t = e / KG, kg = e - t * KG;
               uint32_t h[4], l[4];
+              float vmax = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) vmax = fmaxf(vmax, fabsf(v[u][j]));
+              if (vmax * kActScale > 60000.f) *p.sat = 1;          // the clamp below changes a value: tell the host (sticky)
 #pragma unroll
               for (int j = 0; j < 4; ++j) split2_f16(v[u][2 * j] * kActScale, v[u][2 * j + 1] * kActScale, h[j], l[j]);
               // TMEM lane = GEMM row of this thread; 8 K values = 4 columns of fp16 pairs
@@ -416,9 +450,9 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
       }
     };
 #if SYN_PDL
-    // EXPERIMENTAL (-DSYN_PDL=1, never run): programmatic dependent launch.  Everything above (barriers,
-    // TMEM, the zeroed window, the weight image) does not depend on the previous kernel; its output -- this
-    // kernel's input -- is first touched below, and this kernel's first global store comes later still.
+    // Programmatic dependent launch: everything above (barriers, TMEM, the zeroed window, the weight image) does not
+    // depend on the previous kernel; its output -- this kernel's input -- is first touched below, and this kernel's
+    // first global store comes later still.
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
     if ((int)blockIdx.x < ntiles) prep(blockIdx.x);
@@ -472,7 +506,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
           // EPI1: 8 columns (one channel octet) per TMEM load; the expand scale is one power of two per
           // layer (row 11 is constant) and the octet's biases stay in registers, so an element costs one
           // FFMA.SAT plus a quarter of a 16-byte shared store
-          const float sc1 = dwc[11 * C::NC];
+          const float sc1 = dwc[11 * C::DWS];
           int cur_k = -1;
           float bq[8];
           const int n_e = mt1 * KPG;
@@ -495,8 +529,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
                 const int t = e / KPG, kq = grp * KPG + (e - t * KPG), j0 = kq * 8;
                 if (kq != cur_k) {
                   cur_k = kq;
-                  const float4 b0 = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0);
-                  const float4 b1 = *reinterpret_cast<const float4*>(dwc + 10 * C::NC + j0 + 4);
+                  const float4 b0 = *reinterpret_cast<const float4*>(dwc + 10 * C::DWS + j0);
+                  const float4 b1 = *reinterpret_cast<const float4*>(dwc + 10 * C::DWS + j0 + 4);
                   bq[0] = b0.x; bq[1] = b0.y; bq[2] = b0.z; bq[3] = b0.w; bq[4] = b1.x; bq[5] = b1.y; bq[6] = b1.z; bq[7] = b1.w;
                 }
                 const int m = t * 128 + row;
@@ -526,7 +560,89 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
           ++n_g2;
         }
         SYN_TRACE(0, c, 4);
-        if constexpr (C::STRIDE == 1 && ((C::WO >= 15 && C::WO <= SYN_DW2_MAXW) || (SYN_DW2_SMALL && C::WO == 8))) {
+        if constexpr (C::DW3) {
+          // Stride-1 60^2 / 30^2 / 15^2 maps.  The depthwise phase is bound by shared-memory wavefronts (every LDS.128 of
+          // a warp costs four), so an item is register-blocked as far as the register file allows: ONE channel quad x
+          // TWO output rows x S = 3 (5) output columns = 4 x (S + 2) window loads + 10 tap loads per 8 S outputs: 20 (15.2)
+          // per 16 outputs; the 2 x 2 items below need 26 and their mirrored tap loads used to conflict.  A unit of 16
+          // threads = 8 lanes (NS column segments x NR row pairs) x the two quads of a channel octet.  Segments
+          // are S pixels = an odd number of 16-byte groups apart, row pairs 2 * HS_COLS pixels: with the row pitches
+          // FusedCfg asserts, the eight window addresses of a quarter-warp and the sixteen 8-byte operand stores of a
+          // half-warp fall on different banks.
+          constexpr int NS = C::DW3_NS, NR = C::DW3_NR, S = C::DW3_S, NSEG = C::WO / S, RP2 = (C::RO + 1) / 2;
+          constexpr int XGU = (NSEG + NS - 1) / NS, RPGU = (RP2 + NR - 1) / NR, UPK = XGU * RPGU;   // units per (face, octet)
+          const int l8 = tid & 7, qh = (tid >> 3) & 1;
+          const int ls = l8 % NS, lr = l8 / NS;
+          const int units = KPG * nfaces * UPK;
+          for (int u = gtid >> 4; u < units; u += TPG / 16) {
+            const int kgl = u / (nfaces * UPK), r1 = u - kgl * (nfaces * UPK);
+            const int f = r1 / UPK, r2 = r1 - f * UPK;
+            const int rpg = r2 / XGU, xg = r2 - rpg * XGU;
+            const int kg = grp * KPG + kgl, j0 = kg * 8 + qh * 4;
+            const int seg = xg * NS + ls, oy = 2 * (rpg * NR + lr);
+            if (seg >= NSEG || oy >= C::RO) continue;
+            const int ox0 = S * seg;
+            const bool two = (oy + 1 < C::RO);
+            const float* wq = dwc + j0;
+            float2 w[3][3][2];                                             // [ky][kx][channel pair]
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const float4 t4 = *reinterpret_cast<const float4*>(wq + (ky * 3 + kx) * C::DWS);
+                w[ky][kx][0] = make_float2(t4.x, t4.y); w[ky][kx][1] = make_float2(t4.z, t4.w);
+              }
+            float2 acc[2][S][2];                                           // [output row][output column][channel pair]
+            {
+              const float4 b4 = *reinterpret_cast<const float4*>(wq + 9 * C::DWS);
+#pragma unroll
+              for (int ro = 0; ro < 2; ++ro)
+#pragma unroll
+                for (int a = 0; a < S; ++a) { acc[ro][a][0] = make_float2(b4.x, b4.y); acc[ro][a][1] = make_float2(b4.z, b4.w); }
+            }
+            // window columns ox0-1 .. ox0+S are Hs columns ox0 .. ox0+S+1; window rows oy .. oy+3
+            const float* hb = sH + (size_t)(f * C::HS_FACE + oy * C::HS_COLS + ox0) * C::HS_STRIDE + j0;
+#pragma unroll
+            for (int ic = 0; ic < S + 2; ++ic) {
+              float2 d[4][2];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                if (r == 3 && !two) continue;                              // row only the absent second output row needs
+                const float4 t4 = *reinterpret_cast<const float4*>(hb + (r * C::HS_COLS + ic) * C::HS_STRIDE);
+                d[r][0] = make_float2(t4.x, t4.y); d[r][1] = make_float2(t4.z, t4.w);
+              }
+#pragma unroll
+              for (int a = 0; a < S; ++a) {
+                const int kx = ic - a;
+                if (kx < 0 || kx > 2) continue;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) acc[0][a][j] = ffma2(d[ky][j], w[ky][kx][j], acc[0][a][j]);
+                  if (two) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) acc[1][a][j] = ffma2(d[ky + 1][j], w[ky][kx][j], acc[1][a][j]);
+                  }
+                }
+              }
+            }
+            constexpr float kOut = 6.0f * kActScale;
+#pragma unroll
+            for (int ro = 0; ro < 2; ++ro) {
+              if (ro == 1 && !two) continue;
+#pragma unroll
+              for (int a = 0; a < S; ++a) {
+                const int m2 = f * C::M2F + (oy + ro) * C::WOP + ox0 + a;
+                uint32_t h0, l0, h1, l1;
+                split2_f16<false>(__saturatef(acc[ro][a][0].x) * kOut, __saturatef(acc[ro][a][0].y) * kOut, h0, l0);
+                split2_f16<false>(__saturatef(acc[ro][a][1].x) * kOut, __saturatef(acc[ro][a][1].y) * kOut, h1, l1);
+                uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16 + qh * 8;
+                *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(dst + C::A2_PLANE) = make_uint2(l0, l1);
+              }
+            }
+          }
+        } else if constexpr (C::STRIDE == 1 && ((C::WO >= 15 && C::WO <= SYN_DW2_MAXW) || (SYN_DW2_SMALL && C::WO == 8))) {
           // Stride-1 30^2, 15^2 and 8^2 maps (on the 60^2 map of block 1 the units do not divide evenly between
           // the channel groups and the row-pair items below are faster): the window loads of the depthwise
           // conv are what the shared-memory pipe spends its time on, so an item is register-blocked over a 2 x 2 output patch
@@ -561,12 +677,12 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
               for (int kl = 0; kl < 3; ++kl) {
-                const float4 t4 = *reinterpret_cast<const float4*>(wq + (ky * 3 + (mir ? 2 - kl : kl)) * C::NC);
+                const float4 t4 = *reinterpret_cast<const float4*>(wq + (ky * 3 + (mir ? 2 - kl : kl)) * C::DWS);
                 w[ky][kl][0] = make_float2(t4.x, t4.y); w[ky][kl][1] = make_float2(t4.z, t4.w);
               }
             float2 acc[2][2][2];                                           // [output row][local column][channel pair]
             {
-              const float4 b4 = *reinterpret_cast<const float4*>(wq + 9 * C::NC);
+              const float4 b4 = *reinterpret_cast<const float4*>(wq + 9 * C::DWS);
 #pragma unroll
               for (int ro = 0; ro < 2; ++ro)
 #pragma unroll
@@ -607,7 +723,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
               for (int a = 0; a < 2; ++a) {
                 const int col = ox + (mir ? 1 - a : a);
                 if (col >= C::WO) continue;                                // odd width: the last pair has one column
-                const int m2 = f * C::M2F + (oy + ro) * C::WO + col;
+                const int m2 = f * C::M2F + (oy + ro) * C::WOP + col;
                 uint32_t h0, l0, h1, l1;
                 split2_f16<false>(__saturatef(acc[ro][a][0].x) * kOut, __saturatef(acc[ro][a][0].y) * kOut, h0, l0);
                 split2_f16<false>(__saturatef(acc[ro][a][1].x) * kOut, __saturatef(acc[ro][a][1].y) * kOut, h1, l1);
@@ -643,88 +759,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
           // the float offsets of the first / second quad); only the final operand store swaps them back.
           const bool swz = (C::STRIDE == 2) && (l8 & 4);
           const int q0 = swz ? 4 : 0, q1 = 4 - q0;
-          if constexpr (SYN_DW_SPLIT_LAST && RPI == 2 && GY == 1) {
-            // EXPERIMENTAL (-DSYN_DW_SPLIT_LAST=1, compiled, never run on a GPU): when the row-pair items do not
-            // fill the last round of the group's item slots (stem: 24 item groups on 16 slots), the pair items
-            // of that round are split into single-row items so that every slot has work: 1.6 rounds instead of 2.
-            auto item = [&](int kg, int it, int rowsel, bool single) {
-              const int f = it / PER_FACE, r2 = it - f * PER_FACE;
-              const int rpg = r2 / XG, xg = r2 - rpg * XG;
-              // single rows with GY == 2: the two rows of a quarter-warp lie RPG rows apart (an even number),
-              // which keeps the two half-rows of lanes on disjoint bank groups
-              const int ox = xg * GX + lx, oy = 2 * (rpg * GY + ly) + rowsel;
-              if (ox < C::WO && oy < C::RO) {
-                const float* wbase = dwc + kg * 8;
-                const float* h0 = sH + (size_t)(f * C::HS_FACE + (oy * C::STRIDE) * C::HS_COLS + ox * C::STRIDE) * C::HS_STRIDE + kg * 8;
-                const bool two = !single && (oy + 1 < C::RO);                // second output row exists and is ours
-                float2 acc0[4], acc1[4];                                     // channel pairs (FFMA2 operands)
-                {
-                  const float4 a = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q0);
-                  const float4 e = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q1);
-                  acc0[0] = make_float2(a.x, a.y); acc0[1] = make_float2(a.z, a.w); acc0[2] = make_float2(e.x, e.y); acc0[3] = make_float2(e.z, e.w);
-  #pragma unroll
-                  for (int j = 0; j < 4; ++j) acc1[j] = acc0[j];
-                }
-  #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                  float2 w[3][4];
-  #pragma unroll
-                  for (int dy = 0; dy < 3; ++dy) {
-                    const float4 a = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q0);
-                    const float4 e = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q1);
-                    w[dy][0] = make_float2(a.x, a.y); w[dy][1] = make_float2(a.z, a.w);
-                    w[dy][2] = make_float2(e.x, e.y); w[dy][3] = make_float2(e.z, e.w);
-                  }
-  #pragma unroll
-                  for (int wr = 0; wr < NR; ++wr) {
-                    if (wr >= 3 && !two) continue;                           // rows only the (absent) second pixel needs
-                    const float* hp = h0 + (wr * C::HS_COLS + dx) * C::HS_STRIDE;
-                    const float4 a = *reinterpret_cast<const float4*>(hp + q0);
-                    const float4 e = *reinterpret_cast<const float4*>(hp + q1);
-                    const float2 d[4] = {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(e.x, e.y), make_float2(e.z, e.w)};
-                    if (wr < 3) {
-  #pragma unroll
-                      for (int j = 0; j < 4; ++j) acc0[j] = ffma2(d[j], w[wr][j], acc0[j]);
-                    }
-                    if (RPI == 2 && wr >= C::STRIDE) {
-  #pragma unroll
-                      for (int j = 0; j < 4; ++j) acc1[j] = ffma2(d[j], w[wr - C::STRIDE][j], acc1[j]);
-                    }
-                  }
-                }
-                constexpr float kOut = 6.0f * kActScale;                   // relu6(x) * kActScale = sat(x/6) * 384
-                const int m2 = f * C::M2F + oy * C::WO + ox;
-                {
-                  uint32_t h[4], l[4];
-  #pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    split2_f16<false>(__saturatef(acc0[j].x) * kOut, __saturatef(acc0[j].y) * kOut, h[j], l[j]);
-                  uint8_t* dst = sA2 + (m2 >> 7) * (128 * C::NC * 2) + ((m2 & 127) >> 3) * 128 + kg * 2048 + (m2 & 7) * 16;
-                  *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
-                  *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
-                }
-                if (two) {
-                  const int m3 = m2 + C::WO;
-                  uint32_t h[4], l[4];
-  #pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    split2_f16<false>(__saturatef(acc1[j].x) * kOut, __saturatef(acc1[j].y) * kOut, h[j], l[j]);
-                  uint8_t* dst = sA2 + (m3 >> 7) * (128 * C::NC * 2) + ((m3 & 127) >> 3) * 128 + kg * 2048 + (m3 & 7) * 16;
-                  *reinterpret_cast<uint4*>(dst) = swz ? make_uint4(h[2], h[3], h[0], h[1]) : make_uint4(h[0], h[1], h[2], h[3]);
-                  *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
-                }
-              }
-            };
-            const int T = KPG * per_kg, S = TPG / 8, slot = gtid >> 3;
-            const int L = T % S;                                           // pair items left for a partial last round
-            const bool split = (L > 0) && (2 * L <= S);
-            const int t_pairs = split ? T - L : T;
-            for (int G = slot; G < t_pairs; G += S) item(grp * KPG + G / per_kg, G % per_kg, 0, false);
-            if (split && (slot >> 1) < L) {
-              const int G = t_pairs + (slot >> 1);
-              item(grp * KPG + G / per_kg, G % per_kg, slot & 1, true);
-            }
-          } else {
+          {
             const int kg_end = (grp + 1) * KPG;                              // this group's channel octets
             int kg = grp * KPG, it = gtid >> 3;
             while (it >= per_kg && kg < kg_end) { it -= per_kg; ++kg; }
@@ -740,8 +775,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
                 const bool two = (RPI == 2) && (oy + 1 < C::RO);             // second output row exists
                 float2 acc0[4], acc1[4];                                     // channel pairs (FFMA2 operands)
                 {
-                  const float4 a = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q0);
-                  const float4 e = *reinterpret_cast<const float4*>(wbase + 9 * C::NC + q1);
+                  const float4 a = *reinterpret_cast<const float4*>(wbase + 9 * C::DWS + q0);
+                  const float4 e = *reinterpret_cast<const float4*>(wbase + 9 * C::DWS + q1);
                   acc0[0] = make_float2(a.x, a.y); acc0[1] = make_float2(a.z, a.w); acc0[2] = make_float2(e.x, e.y); acc0[3] = make_float2(e.z, e.w);
   #pragma unroll
                   for (int j = 0; j < 4; ++j) acc1[j] = acc0[j];
@@ -751,8 +786,8 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
                   float2 w[3][4];
   #pragma unroll
                   for (int dy = 0; dy < 3; ++dy) {
-                    const float4 a = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q0);
-                    const float4 e = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::NC + q1);
+                    const float4 a = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::DWS + q0);
+                    const float4 e = *reinterpret_cast<const float4*>(wbase + (dy * 3 + dx) * C::DWS + q1);
                     w[dy][0] = make_float2(a.x, a.y); w[dy][1] = make_float2(a.z, a.w);
                     w[dy][2] = make_float2(e.x, e.y); w[dy][3] = make_float2(e.z, e.w);
                   }
@@ -774,7 +809,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
                   }
                 }
                 constexpr float kOut = 6.0f * kActScale;                   // relu6(x) * kActScale = sat(x/6) * 384
-                const int m2 = f * C::M2F + oy * C::WO + ox;
+                const int m2 = f * C::M2F + oy * C::WOP + ox;
                 {
                   uint32_t h[4], l[4];
   #pragma unroll
@@ -785,7 +820,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
                   *reinterpret_cast<uint4*>(dst + C::A2_PLANE) = swz ? make_uint4(l[2], l[3], l[0], l[1]) : make_uint4(l[0], l[1], l[2], l[3]);
                 }
                 if (two) {
-                  const int m3 = m2 + C::WO;
+                  const int m3 = m2 + C::WOP;
                   uint32_t h[4], l[4];
   #pragma unroll
                   for (int j = 0; j < 4; ++j)
@@ -810,65 +845,47 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
       prefetch_x(tile + 2 * (int)gridDim.x);
       // ---- EPI2: s3*D2 + b3 (+ skip) -> global NHWC --------------------------------------------------
       SYN_TRACE(0, 63, 2);
+      constexpr int JW = (C::COUT_P % 32 == 0 && C::MT2 * (C::COUT_P / 32) >= 2 * NWG) ? 32
+                         : (C::MT2 * (C::COUT_P / 16) >= 2 * NWG) ? 16 : 8;
+      constexpr int JC = C::COUT_P / JW;
+      // GEMM2 row m2 -> output pixel of the tile (rows are padded to WOP pixels when DW3 needs it); -1 = no pixel
+      auto out_pixel = [&](int m2) -> int {
+        if (m2 >= M2) return -1;
+        if constexpr (C::WOP == C::WO) return m2;                  // tiles are contiguous in NHWC memory
+        const int oyl = m2 / C::WOP, oxl = m2 - oyl * C::WOP;
+        return oxl < C::WO ? oyl * C::WO + oxl : -1;
+      };
+      // The skip connection (stride 1, CIN == COUT: the same pixel of the block input) is a dependent global load per
+      // 16 bytes of output: fetch it BEFORE waiting for the last GEMM2, one item ahead of its use afterwards.
+      float4 res_cur[JW / 4];
+      auto load_res = [&](int e, float4 (&r)[JW / 4]) {
+        if constexpr (C::RES) {
+          const int t = e / JC, j0 = (e - t * JC) * JW;
+          const int pix = out_pixel(t * 128 + row);
+#pragma unroll
+          for (int j = 0; j < JW; j += 4) {
+            r[j / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pix >= 0 && j0 + j < C::COUT)
+              r[j / 4] = __ldg(reinterpret_cast<const float4*>(p.x + ((size_t)(f0 * C::W + oy0) * C::W + pix) * C::CIN + j0 + j));
+          }
+        }
+      };
+      if constexpr (C::RES) {
+        if (wg < mt2 * JC) load_res(wg, res_cur);
+      }
       mbar_wait(smem_u32(&bar_g2), n_g2 & 1, p.err);
       ++n_g2;
       tc_fence_after_sync();
       SYN_TRACE(0, 63, 3);
-      if constexpr (SYN_EPI2_STAGED && NWG == 4) {
-        // EXPERIMENTAL (-DSYN_EPI2_STAGED=1, compiled and reviewed but not yet run on a GPU): EPI2 through a
-        // shared-memory transpose.  With lane = pixel every 16-byte global store / skip load of a warp touches
-        // 32 different lines; here the four 128-thread slices take four adjacent 8-channel column blocks of
-        // one M tile, stage a [128 px][32 ch] block (16 KB in the A2 region, free after the last GEMM2; the
-        // 16-byte chunk index is XORed with the row so that both directions are conflict-free) and write it
-        // back with lanes along the channels: 128 contiguous bytes per pixel.
-        float* stage = reinterpret_cast<float*>(sA2);
-        constexpr int JB = (C::COUT_P + 31) / 32;
-        for (int t = 0; t < mt2; ++t) {
-          for (int jb = 0; jb < JB; ++jb) {
-            const int j0 = jb * 32 + wg * 8;
-            if (j0 < C::COUT_P) {                                 // warp-uniform (tcgen05.ld is .sync.aligned)
-              float v[8];
-              tmem_ld8(tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::D2_COL + t * C::COUT_P + j0, v);
-              const float4 b0 = *reinterpret_cast<const float4*>(sB3 + j0), b1 = *reinterpret_cast<const float4*>(sB3 + j0 + 4);
-              const float4 s0 = *reinterpret_cast<const float4*>(sB3 + C::COUT_P + j0);
-              const float4 s1 = *reinterpret_cast<const float4*>(sB3 + C::COUT_P + j0 + 4);
-              float* srow = stage + row * 32;
-              *reinterpret_cast<float4*>(srow + (((2 * wg) ^ (row & 7)) << 2)) =
-                  make_float4(fmaf(v[0], s0.x, b0.x), fmaf(v[1], s0.y, b0.y), fmaf(v[2], s0.z, b0.z), fmaf(v[3], s0.w, b0.w));
-              *reinterpret_cast<float4*>(srow + (((2 * wg + 1) ^ (row & 7)) << 2)) =
-                  make_float4(fmaf(v[4], s1.x, b1.x), fmaf(v[5], s1.y, b1.y), fmaf(v[6], s1.z, b1.z), fmaf(v[7], s1.w, b1.w));
-            }
-            asm volatile("bar.sync 5, %0;" ::"n"(NWT) : "memory");
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {                         // 128 px x 8 chunks of 16 B over 512 threads
-              const int idx = tid + k * NWT, px = idx >> 3, c4 = idx & 7;
-              const int m2 = t * 128 + px, j = jb * 32 + c4 * 4;
-              if (m2 < M2 && j < C::COUT) {
-                float4 o = *reinterpret_cast<const float4*>(stage + px * 32 + ((c4 ^ (px & 7)) << 2));
-                const size_t pix = (size_t)(f0 * C::WO + oy0) * C::WO + m2;   // tiles are contiguous in NHWC memory
-                if constexpr (C::RES) {                           // stride 1, CIN == COUT: same pixel of the block input
-                  const float4 r = __ldg(reinterpret_cast<const float4*>(p.x + pix * C::CIN + j));
-                  o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                }
-                *reinterpret_cast<float4*>(p.y + pix * C::COUT + j) = o;
-              }
-            }
-            asm volatile("bar.sync 5, %0;" ::"n"(NWT) : "memory");   // the stage (and, after the last item, A2) may be rewritten
-          }
-        }
-      } else {
-        constexpr int JW = (C::COUT_P % 32 == 0 && C::MT2 * (C::COUT_P / 32) >= 2 * NWG) ? 32
-                           : (C::MT2 * (C::COUT_P / 16) >= 2 * NWG) ? 16 : 8;
-        constexpr int JC = C::COUT_P / JW;
+      {
         for (int e = wg; e < mt2 * JC; e += NWG) {
           const int t = e / JC, j0 = (e - t * JC) * JW;
-          const int m2 = t * 128 + row;
-          // tiles are contiguous in NHWC memory: (face f0, output row oy0) + m2 pixels
-          float* orow = p.y + ((size_t)(f0 * C::WO + oy0) * C::WO + m2) * C::COUT;
+          const int pix = out_pixel(t * 128 + row);
+          float* orow = p.y + ((size_t)(f0 * C::WO + oy0) * C::WO + max(pix, 0)) * C::COUT;
           float v[JW];
           const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + C::D2_COL + t * C::COUT_P + j0;
           if constexpr (JW == 32) tmem_ld32(taddr, v); else if constexpr (JW == 16) tmem_ld16(taddr, v); else tmem_ld8(taddr, v);
-          if (m2 < M2) {
+          if (pix >= 0) {
 #pragma unroll
             for (int j = 0; j < JW; j += 4) {
               if (j0 + j < C::COUT) {
@@ -876,14 +893,16 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
                 const float4 sc = *reinterpret_cast<const float4*>(sB3 + C::COUT_P + j0 + j);
                 float4 o = make_float4(fmaf(v[j], sc.x, bb.x), fmaf(v[j + 1], sc.y, bb.y), fmaf(v[j + 2], sc.z, bb.z),
                                        fmaf(v[j + 3], sc.w, bb.w));
-                if constexpr (C::RES) {      // stride 1, CIN == COUT: same pixel of the block input
-                  const float4 r = *reinterpret_cast<const float4*>(
-                      p.x + ((size_t)(f0 * C::W + oy0) * C::W + m2) * C::CIN + j0 + j);
+                if constexpr (C::RES) {
+                  const float4 r = res_cur[j / 4];
                   o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                 }
                 *reinterpret_cast<float4*>(orow + j0 + j) = o;
               }
             }
+          }
+          if constexpr (C::RES) {                                  // next item's skip values: in flight during its TMEM load
+            if (e + NWG < mt2 * JC) load_res(e + NWG, res_cur);
           }
         }
       }
@@ -938,6 +957,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
         const uint32_t xa = tmem + C::XA_COL + t * C::CIN_P;     // A from TMEM: N/2 cycles per MMA, no smem read of X
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
+          if (pass >= p.npass) break;                              // single-pass engine: hi * hi only
 #pragma unroll
           for (int ks = 0; ks < C::CIN_P / 16; ++ks)
             umma_f16_ts(tmem + t * C::NC, xa + (pass == 2 ? C::CIN_P / 2 : 0) + ks * 8,
@@ -958,6 +978,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
         const uint32_t ab = a2_lo + ((t * (128 * C::NC * 2)) >> 4);
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
+          if (pass >= p.npass) break;
 #pragma unroll
           for (int ks = 0; ks < C::NC / 16; ++ks)
 #pragma unroll

@@ -1,0 +1,255 @@
+// General fp32-accurate GEMM / implicit-GEMM convolution on tcgen05 for the layers outside the fused MobileNetV2
+// blocks: the PointNet refinement heads MLP_for / MLP_rev (reference backbone_nets/pointnet_backbone.py:31-64,
+// 90-106; Conv1d(k=1) + BatchNorm1d + ReLU over B x 68 points) and the ResNet-50 backbone variant
+// (backbone_nets/resnet_backbone.py:227-249; 1x1 / 3x3 convolutions + BatchNorm2d + ReLU, NHWC here).
+//
+//   out[m, n] = act( sum_k A[m, k] * W[n, k] * oscale[n] + bias[n] + addend[m / group, n] + residual[m, n] )
+//
+// Precision: the split-fp16 x3 scheme of kernels_tc.cuh, but with a DYNAMIC power-of-two scale per A row instead of
+// the fixed kActScale: the producing layer's epilogue records max|x| of every row (`rowmax`, atomicMax on the fp32
+// bit pattern), and the consumer scales row m by 2^e(m) so that its largest element lands in [2^13, 2^14) before
+// the hi/lo split -- exact, undone by one multiply in the epilogue, and immune to the |x| < ~937 range limit of
+// the fixed scale (ReLU outputs of these layers are unbounded).
+//
+// Roles: warps 0-3 = producers (thread = GEMM row: gathers the fp32 row -- or, in conv mode, the k x k x C patch of
+// an NHWC pixel -- splits it and stores the canonical K-major operand), then the epilogue; warp 4 = bulk-copy of the
+// pre-packed weight chunks + MMA issue (converged warp, elect.sync).  K streams in chunks of 32 through a 2-stage
+// ring; two CTAs share an SM (96 KB smem, 256 TMEM columns each) so one tile's loads overlap the other's MMAs.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace syn {
+
+constexpr int kGmKC = 32;                                 // K chunk
+constexpr int kGmThreads = 160;
+constexpr int kGmMaxNr = 256;
+constexpr int kGmStageA = 128 * kGmKC * 2;                // 8 KB: one plane (hi or lo) of the A tile
+constexpr int kGmStageB = kGmMaxNr * kGmKC * 2;           // 16 KB
+constexpr int kGmStage = 2 * kGmStageA + 2 * kGmStageB;   // 48 KB
+constexpr int kGmSmem = 2 * kGmStage + 1024;
+
+enum { kActNone = 0, kActRelu6 = 1, kActRelu = 2 };
+
+struct GemmArgs {
+  const float* A;            // plain mode: [M][lda]; conv mode: NHWC activations (B, H, W, C)
+  const uint8_t* Wimg;       // per n-range, per K chunk: [hi plane nr x kc][lo plane]  (pack_gemm_weights)
+  const float* bias;         // [N] (BatchNorm folded), never null
+  const float* oscale;       // [N]: 1 / weight scale of the channel
+  const float* addend;       // nullable: [M / addend_group][N], broadcast over the rows of a group (PointNet conv6)
+  const float* residual;     // nullable: [M][N], added before the activation (ResNet shortcut)
+  float* out;                // nullable: [M][N]
+  const unsigned* rowmax_in; // max|a| per source row as fp32 bits (conv mode: per input pixel)
+  unsigned* rowmax_out;      // nullable: atomicMax of |out| per output row
+  unsigned* colmax_out;      // nullable: max over the rows of a group per channel (PointNet max-pool; values >= 0)
+  int addend_group, colmax_group;
+  int M, K, N, Kp, nr, lda, act;
+  // conv mode (ksize > 0): implicit GEMM over k = (ky * ksize + kx) * C + c
+  int ksize, stride, pad, H, W, C, HO, WO;
+  int* err;
+};
+
+// exponent e such that max * 2^e lies in [2^13, 2^14); max == 0 (all-zero row) -> 0
+__device__ __forceinline__ int gemm_row_exp(unsigned maxbits) {
+  const int be = (int)((maxbits >> 23) & 0xffu);
+  if (be == 0 || be == 255) return 0;                 // zero / denormal row, or inf / nan (propagates unscaled)
+  return max(-100, min(100, 13 - (be - 127)));
+}
+__device__ __forceinline__ float exp2i(int e) { return __uint_as_float((unsigned)(e + 127) << 23); }   // |e| <= 126
+
+__global__ void __launch_bounds__(kGmThreads, 2) tc_gemm_kernel(const GemmArgs p) {
+  using namespace tc;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_acc;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.x * 128;
+  const int n0 = blockIdx.y * p.nr;
+  const int nchunks = (p.Kp + kGmKC - 1) / kGmKC;
+  const uint8_t* wimg = p.Wimg + (size_t)blockIdx.y * (size_t)p.nr * p.Kp * 4;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_full[i]), 129);      // 128 producer arrivals + the weight copy's expect_tx arrival
+      mbar_init(smem_u32(&bar_empty[i]), 1);
+    }
+    mbar_init(smem_u32(&bar_acc), 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<256>(smem_u32(&tmem_base_s));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  auto stage_a = [&](int s, int plane) { return smem + s * kGmStage + plane * kGmStageA; };
+  auto stage_b = [&](int s, int plane) { return smem + s * kGmStage + 2 * kGmStageA + plane * kGmStageB; };
+
+  if (warp < 4) {
+    // ------------------------------ producers ---------------------------------------------------
+    const int row = tid, m = m0 + row;
+    const bool row_ok = m < p.M;
+    int b = 0, oy = 0, ox = 0;
+    unsigned mx = 0;
+    if (p.ksize > 0) {
+      if (row_ok) {
+        b = m / (p.HO * p.WO);
+        const int r = m - b * p.HO * p.WO;
+        oy = r / p.WO; ox = r - oy * p.WO;
+        for (int ky = 0; ky < p.ksize; ++ky)
+          for (int kx = 0; kx < p.ksize; ++kx) {
+            const int iy = oy * p.stride - p.pad + ky, ix = ox * p.stride - p.pad + kx;
+            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) mx = max(mx, p.rowmax_in[((size_t)b * p.H + iy) * p.W + ix]);
+          }
+      }
+    } else if (row_ok) {
+      mx = p.rowmax_in[m];
+    }
+    const int e_row = gemm_row_exp(mx);
+    const float a_scale = exp2i(e_row);
+    const float* arow = p.A + (size_t)m * p.lda;
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c & 1, use = c >> 1;
+      const int k0 = c * kGmKC;
+      const int kc = min(kGmKC, p.Kp - k0);
+      mbar_wait(smem_u32(&bar_empty[s]), (use & 1) ^ 1, p.err);
+      uint8_t* ah = stage_a(s, 0) + (row >> 3) * 128 + (row & 7) * 16;
+      uint8_t* al = stage_a(s, 1) + (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll 2
+      for (int kg = 0; kg < kc / 8; ++kg) {
+        const int k = k0 + kg * 8;
+        const float* src = nullptr;
+        if (row_ok && k < p.K) {
+          if (p.ksize > 0) {
+            const int tap = k / p.C, cc = k - tap * p.C;
+            const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+            const int iy = oy * p.stride - p.pad + ky, ix = ox * p.stride - p.pad + kx;
+            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) src = p.A + (((size_t)b * p.H + iy) * p.W + ix) * p.C + cc;
+          } else {
+            src = arow + k;
+          }
+        }
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), e = a;
+        if (src != nullptr) {                                 // K and C are multiples of 8, rows 16-byte aligned
+          a = __ldg(reinterpret_cast<const float4*>(src));
+          e = __ldg(reinterpret_cast<const float4*>(src + 4));
+        }
+        uint32_t h[4], l[4];
+        split2_f16(a.x * a_scale, a.y * a_scale, h[0], l[0]);
+        split2_f16(a.z * a_scale, a.w * a_scale, h[1], l[1]);
+        split2_f16(e.x * a_scale, e.y * a_scale, h[2], l[2]);
+        split2_f16(e.z * a_scale, e.w * a_scale, h[3], l[3]);
+        *reinterpret_cast<uint4*>(ah + kg * 2048) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(al + kg * 2048) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&bar_full[s]));
+    }
+    // ------------------------------ epilogue ----------------------------------------------------
+    mbar_wait(smem_u32(&bar_acc), 0, p.err);
+    tc_fence_after_sync();
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const int ncols = min(p.nr, p.N - n0);
+    const float inv_a = exp2i(-e_row);
+    float* orow = p.out ? p.out + (size_t)m * p.N + n0 : nullptr;
+    const float* rrow = p.residual ? p.residual + (size_t)m * p.N + n0 : nullptr;
+    const float* arow2 = p.addend ? p.addend + (size_t)(m / p.addend_group) * p.N + n0 : nullptr;
+    unsigned* crow = p.colmax_out ? p.colmax_out + (size_t)(m / p.colmax_group) * p.N + n0 : nullptr;
+    float rmax = 0.f;
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      float v[16];
+      tmem_ld16(trow + c0, v);                              // warp-collective: no divergence above
+      if (!row_ok) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (c0 + j >= ncols) break;
+        const int n = n0 + c0 + j;
+        float o = fmaf(v[j] * inv_a, p.oscale[n], p.bias[n]);
+        if (arow2) o += arow2[c0 + j];
+        if (rrow) o += rrow[c0 + j];
+        if (p.act == kActRelu6) o = relu6f(o); else if (p.act == kActRelu) o = fmaxf(o, 0.f);
+        rmax = fmaxf(rmax, fabsf(o));
+        if (orow) orow[c0 + j] = o;
+        if (crow) atomicMax(crow + c0 + j, __float_as_uint(o));      // o >= 0 (ReLU): the bit pattern orders like the value
+      }
+    }
+    if (row_ok && p.rowmax_out != nullptr) atomicMax(p.rowmax_out + m, __float_as_uint(rmax));
+  } else {
+    // ------------------------------ weight loader + MMA issuer (converged warp) -------------------
+    const uint32_t idesc = make_idesc_f16(128, p.nr);
+    const uint32_t lbo_b = (uint32_t)(p.nr >> 3) * 128;
+    const uint32_t d_hi = smem_desc_hi(128);
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c & 1, use = c >> 1;
+      const int k0 = c * kGmKC;
+      const int kc = min(kGmKC, p.Kp - k0);
+      mbar_wait(smem_u32(&bar_empty[s]), (use & 1) ^ 1, p.err);
+      if (elect_one()) {
+        const uint32_t plane_bytes = (uint32_t)p.nr * kc * 2;
+        const uint8_t* src = wimg + (size_t)p.nr * k0 * 4;    // chunks of this range are consecutive
+        mbar_expect_tx(smem_u32(&bar_full[s]), 2 * plane_bytes);
+        bulk_g2s(smem_u32(stage_b(s, 0)), src, plane_bytes, smem_u32(&bar_full[s]));
+        bulk_g2s(smem_u32(stage_b(s, 1)), src + plane_bytes, plane_bytes, smem_u32(&bar_full[s]));
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(&bar_full[s]), use & 1, p.err);
+      tc_fence_after_sync();
+      const uint32_t a_lo = smem_desc_lo(smem_u32(stage_a(s, 0)), 2048);
+      const uint32_t b_lo = smem_desc_lo(smem_u32(stage_b(s, 0)), lbo_b);
+      if (elect_one()) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {                 // hi*hi, hi*lo, lo*hi
+          const uint32_t a_off = (pass == 2 ? kGmStageA : 0), b_off = (pass == 1 ? kGmStageB : 0);
+          for (int ks = 0; ks < kc / 16; ++ks)
+            umma_f16(tmem, desc64(d_hi, a_lo + ((a_off + ks * 4096) >> 4)), desc64(d_hi, b_lo + ((b_off + ks * 2 * lbo_b) >> 4)),
+                     idesc, (c > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bar_empty[s]));
+        if (c == nchunks - 1) umma_commit(smem_u32(&bar_acc));
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+// ---- small CUDA-core helpers of the same layer families ---------------------------------------------------------
+// K < 8 first layer (PointNet conv1: 3 -> 64 on the landmark coordinates): out[m, n] = act(sum_k A[m,k] W[k,n] + b[n]).
+// A is read through (row stride, element stride) so that the (B,3,68) landmark tensor is consumed in place:
+// row m = (b, point) reads x[b, k, point].
+__global__ void small_k_layer_kernel(const float* __restrict__ x, const float* __restrict__ Wkn, const float* __restrict__ bias,
+                                     float* __restrict__ out, unsigned* __restrict__ rowmax_out, int M, int K, int N, int pts,
+                                     int act) {
+  const int m = blockIdx.x * blockDim.y + threadIdx.y;
+  if (m >= M) return;
+  const int b = m / pts, pt = m - b * pts;
+  float a[8];
+  for (int k = 0; k < K; ++k) a[k] = x[((size_t)b * K + k) * pts + pt];
+  float rmax = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float o = bias[n];
+    for (int k = 0; k < K; ++k) o = fmaf(a[k], Wkn[k * N + n], o);
+    if (act == kActRelu) o = fmaxf(o, 0.f);
+    out[(size_t)m * N + n] = o;
+    rmax = fmaxf(rmax, fabsf(o));
+  }
+  for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+  if (threadIdx.x == 0 && rowmax_out != nullptr) rowmax_out[m] = __float_as_uint(rmax);
+}
+
+// rowmax of an arbitrary [M][K] fp32 matrix (inputs that no GEMM epilogue produced)
+__global__ void rowmax_kernel(const float* __restrict__ A, unsigned* __restrict__ rowmax, int M, int K, int lda) {
+  const int m = blockIdx.x * blockDim.y + threadIdx.y;
+  if (m >= M) return;
+  float r = 0.f;
+  for (int k = threadIdx.x; k < K; k += 32) r = fmaxf(r, fabsf(A[(size_t)m * lda + k]));
+  for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+  if (threadIdx.x == 0) rowmax[m] = __float_as_uint(r);
+}
+
+}  // namespace syn

@@ -32,6 +32,7 @@ struct TailArgs {
   int batch;
   int ctas_per_slice;
   int* err;
+  int npass;             // 3 = split-fp16 x3, 1 = single fp16 pass
 };
 
 __global__ void __launch_bounds__(kTailThreads, 1) tail_conv_pool_kernel(const TailArgs p) {
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) tail_conv_pool_kernel(const T
         if (elect_one()) {
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
+            if (pass >= p.npass) break;
             const uint32_t a_off = kc * 2 * kTailPlane + (pass == 2 ? kTailPlane : 0);   // W: hi,hi,lo
             const uint32_t b_off = s * kTailXStage + (pass == 1 ? kTailPlane : 0);       // X: hi,lo,hi
 #pragma unroll

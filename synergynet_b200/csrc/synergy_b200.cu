@@ -14,6 +14,8 @@
 #include "kernels_fused.cuh"
 #include "kernels_tail.cuh"
 #include "kernels_dense.cuh"
+#include "kernels_gemm.cuh"
+#include "kernels_loss.cuh"
 
 using namespace syn;
 
@@ -32,10 +34,16 @@ struct DevConv {
 
 }  // namespace
 
+struct syn_heads;       // PointNet refinement heads (heads_host.inl)
+void syn_heads_destroy(syn_heads* s);
+
 struct syn_handle {
   int device = 0;
+  syn_heads* heads = nullptr;
   int sm_count = 0;
   int engine = SYN_ENGINE_TC_FUSED;            // default: fused tcgen05 engine; 0/1 remain for cross-checks
+  int npass() const { return engine == SYN_ENGINE_TC_FUSED_1PASS ? 1 : 3; }
+  bool fused() const { return engine == SYN_ENGINE_TC_FUSED || engine == SYN_ENGINE_TC_FUSED_1PASS; }
   bool committed = false;
   int64_t launches = 0;
   // optional per-launch timing (syn_set_timing): events recorded after every kernel of a call
@@ -65,7 +73,9 @@ struct syn_handle {
   size_t tc_osc_off[kNumConv] = {};
   size_t tc_off[kNumConv] = {};
   int tc_nr[kNumConv] = {}, tc_nranges[kNumConv] = {}, tc_kp[kNumConv] = {};
-  int* d_err = nullptr;                        // raised by a bounded mbarrier wait that timed out
+  int* d_err = nullptr;                        // raised by a bounded mbarrier wait that timed out: mapped pinned HOST memory,
+                                               // so every entry point can look at it without synchronising the device
+  int* d_sat = nullptr;                        // device flag: a block input left the fp16 range of the split engines and was clamped
   bool tc_ready = false;
   // fused stem+block1 and blocks 2..7 (kernels_fused.cuh): one weight image per fused launch
   uint8_t* d_fused = nullptr;
@@ -212,7 +222,7 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
   const Plan& P = plan();
   int rc = ensure_workspace(h, batch);
   if (rc != SYN_OK) return rc;
-  if (x_u8 != nullptr && h->engine != SYN_ENGINE_TC_FUSED) {
+  if (x_u8 != nullptr && !h->fused()) {
     // engines whose stem reads fp32: normalise into a scratch buffer first
     if (batch > h->x_f32_batch) {
       SYN_CUDA(cudaDeviceSynchronize());
@@ -239,7 +249,7 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
 
   int cur = 0;
   int li = 1;
-  if (h->engine == SYN_ENGINE_TC_FUSED) {
+  if (h->fused()) {
     // stem + block 1, then blocks 2..7, each one fused launch; only block outputs exist
     if (stop_layer >= 0 && stop_layer <= 50 && (stop_layer < 2 || (stop_layer - 2) % 3 != 0))
       return fail(SYN_ERR_UNSUPPORTED, "conv %d lives inside a fused block and is never materialised", stop_layer);
@@ -271,7 +281,7 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
       float* pooled = pool ? pool : h->d_pool_tmp;
       TailArgs t;
       t.x = h->buf_io[cur]; t.wimg = h->d_tail_w; t.bias = h->dconv[51].bias; t.oscale = h->d_tail_osc;
-      t.pooled = pooled; t.batch = batch; t.err = h->d_err;
+      t.pooled = pooled; t.batch = batch; t.err = h->d_err; t.npass = h->npass();
       const int ntiles = (batch + kTailFaces - 1) / kTailFaces;
       t.ctas_per_slice = std::max(1, std::min(ntiles, h->sm_count / 10));
       tail_conv_pool_kernel<<<10 * t.ctas_per_slice, kTailThreads, kTailSmem, st>>>(t);
@@ -348,6 +358,15 @@ int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense,
   a.n_vtiles = dense ? h->dn_vtiles : h->sp_vtiles;
   a.n_ftiles = n_ftiles; a.transform = transform; a.err = h->d_err;
   const int items = a.n_vtiles * a.n_ftiles;
+  // dense mesh: face-major walk with streamed basis planes (long contiguous output runs per CTA); the 68-landmark
+  // basis is one vertex tile, where the two kernels do the same work -- keep the simpler one there.
+  static const bool fm_off = getenv("SYN_DENSE_VERTEX_MAJOR") != nullptr;      // A/B switch for measurements
+  if (dense && !fm_off) {
+    dense_recon_fm_kernel<<<std::min(items, h->sm_count), kDnThreads, kFmSmem, st>>>(a);
+    SYN_LAUNCH_CHECK("dense_recon_fm_kernel");
+    mark(h, st, "dense_recon_fm_kernel");
+    return SYN_OK;
+  }
   dense_recon_tc_kernel<<<std::min(items, h->sm_count), kDnThreads, kDnSmem, st>>>(a);
   SYN_LAUNCH_CHECK("dense_recon_tc_kernel");
   mark(h, st, "dense_recon_tc_kernel");
@@ -455,11 +474,11 @@ void pack_fused(std::vector<uint8_t>& img, const float* w1, int K, const float* 
         const size_t off = (size_t)(n / 8) * 128 + (size_t)(k / 8) * ((C::NC / 8) * 128) + (n % 8) * 16 + (k % 8) * 2;
         put(chunk + C::CH_W1 + off, w1[(size_t)k * C::CHID + ch] * s1, C::W1_PLANE);
       }
-      for (int t = 0; t < 9; ++t) d[t * C::NC + n] = dw[(size_t)t * C::CHID + ch];
+      for (int t = 0; t < 9; ++t) d[t * C::DWS + n] = dw[(size_t)t * C::CHID + ch];
       // the hidden activation is kept as relu6(h)/6 in [0,1] (kernels_fused.cuh): fold the 1/6 here
-      d[9 * C::NC + n] = bdw[ch] / 6.0f;
-      d[10 * C::NC + n] = b1[ch] / 6.0f;
-      d[11 * C::NC + n] = 1.0f / (6.0f * kActScaleHost * s1);
+      d[9 * C::DWS + n] = bdw[ch] / 6.0f;
+      d[10 * C::DWS + n] = b1[ch] / 6.0f;
+      d[11 * C::DWS + n] = 1.0f / (6.0f * kActScaleHost * s1);
     }
     for (int n = 0; n < C::COUT; ++n)
       for (int k = 0; k < C::NC; ++k) {
@@ -485,7 +504,16 @@ int launch_fused_nww(syn_handle* h, const FusedArgs& a, int grid, cudaStream_t s
   static bool attr_set[16] = {};
   if (!attr_set[h->device & 15]) {
     SYN_CUDA(cudaFuncSetAttribute(fused_mbconv_kernel<C, NWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    if (C::OCC > 1)   // two CTAs per SM only fit with the largest shared-memory carve-out: ask for it explicitly
+      SYN_CUDA(cudaFuncSetAttribute(fused_mbconv_kernel<C, NWW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
     attr_set[h->device & 15] = true;
+    if (getenv("SYN_DEBUG_OCC") != nullptr) {
+      int nb = -1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_mbconv_kernel<C, NWW>, (NWW + 1) * 32, C::SMEM_BYTES);
+      fprintf(stderr, "[syn] fused CIN=%d CHID=%d W=%d: %d worker warps, %d B smem, %d TMEM cols -> %d CTA(s)/SM (sized for %d)\n",
+              C::CIN, C::CHID, C::W, NWW, C::SMEM_BYTES, C::TM_COLS, nb, C::OCC);
+    }
   }
 #if SYN_PDL
   // programmatic dependent launch (experimental, see kernels_fused.cuh): the kernel may start while its
@@ -511,7 +539,7 @@ template <class C>
 int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, cudaStream_t st, const uint8_t* x_u8) {
   FusedArgs a;
   a.x_u8 = x_u8;
-  a.x = x; a.wimg = h->d_fused + h->fused_off[block]; a.y = y; a.batch = batch; a.err = h->d_err;
+  a.x = x; a.wimg = h->d_fused + h->fused_off[block]; a.y = y; a.batch = batch; a.err = h->d_err; a.sat = h->d_sat; a.npass = h->npass();
 #ifdef SYN_FUSED_TRACE
   a.trace_id = block;
 #endif
@@ -646,8 +674,9 @@ void syn_destroy(syn_handle_t* h) {
   if (h == nullptr) return;
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
+  syn_heads_destroy(h->heads);
   cudaFree(h->d_weights); cudaFree(h->d_head_w); cudaFree(h->d_head_b); cudaFree(h->d_mean);
-  cudaFree(h->d_std); cudaFree(h->d_sparse); cudaFree(h->d_dense); cudaFree(h->d_tcw); cudaFree(h->d_err); cudaFree(h->d_fused); cudaFree(h->d_tc_oscale);
+  cudaFree(h->d_std); cudaFree(h->d_sparse); cudaFree(h->d_dense); cudaFree(h->d_tcw); cudaFreeHost(h->d_err); cudaFree(h->d_sat); cudaFree(h->d_fused); cudaFree(h->d_tc_oscale);
   cudaFree(h->buf_io[0]); cudaFree(h->buf_io[1]); cudaFree(h->buf_hid); cudaFree(h->buf_dw);
   cudaFree(h->d_params_tmp); cudaFree(h->d_pool_tmp); cudaFree(h->d_tail_w); cudaFree(h->d_tail_osc); cudaFree(h->d_x_f32);
   cudaFree(h->d_sp_img); cudaFree(h->d_dn_img); cudaFree(h->d_sp_meta); cudaFree(h->d_dn_meta); cudaFree(h->d_ascale);
@@ -802,8 +831,12 @@ int syn_commit(syn_handle_t* h) {
     SYN_CUDA(cudaMemcpy(h->d_tcw, all.data(), all.size(), cudaMemcpyHostToDevice));
     int rc_o = upload(&h->d_tc_oscale, osc_all);
     if (rc_o != SYN_OK) return rc_o;
-    if (h->d_err == nullptr) SYN_CUDA(cudaMalloc(&h->d_err, sizeof(int)));
-    SYN_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+    if (h->d_err == nullptr) {
+      SYN_CUDA(cudaHostAlloc(&h->d_err, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));   // UVA: same pointer on the device
+      SYN_CUDA(cudaMalloc(&h->d_sat, sizeof(int)));
+    }
+    *reinterpret_cast<volatile int*>(h->d_err) = 0;
+    SYN_CUDA(cudaMemset(h->d_sat, 0, sizeof(int)));
     SYN_CUDA(cudaFuncSetAttribute(tc_pointwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     h->tc_ready = true;
   }
@@ -891,6 +924,7 @@ int syn_commit(syn_handle_t* h) {
       if ((rc = upload(&h->d_dn_meta, meta)) != SYN_OK) return rc;
     }
     SYN_CUDA(cudaFuncSetAttribute(dense_recon_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDnSmem));
+    SYN_CUDA(cudaFuncSetAttribute(dense_recon_fm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmSmem));
   }
   h->committed = true;
   return SYN_OK;
@@ -898,16 +932,23 @@ int syn_commit(syn_handle_t* h) {
 
 int syn_set_engine(syn_handle_t* h, int engine) {
   if (h == nullptr) return fail(SYN_ERR_INVALID, "syn_set_engine: null handle");
-  if (engine != SYN_ENGINE_SIMT_FP32 && engine != SYN_ENGINE_TC_BF16X3 && engine != SYN_ENGINE_TC_FUSED)
+  if (engine != SYN_ENGINE_SIMT_FP32 && engine != SYN_ENGINE_TC_BF16X3 && engine != SYN_ENGINE_TC_FUSED &&
+      engine != SYN_ENGINE_TC_FUSED_1PASS)
     return fail(SYN_ERR_UNSUPPORTED, "syn_set_engine: engine %d not available in this build", engine);
   h->engine = engine;
   return SYN_OK;
 }
 int syn_get_engine(const syn_handle_t* h) { return h ? h->engine : -1; }
 
+// The time-out flag of the bounded in-kernel waits is sticky and lives in mapped host memory: a call that finds it
+// raised (by a kernel of an earlier call) refuses to run instead of returning garbage with SYN_OK;
+// syn_poll_error reports and clears it.
 #define SYN_CHECK_READY(h, name)                                                         \
   if ((h) == nullptr) return fail(SYN_ERR_INVALID, name ": null handle");                \
   if (!(h)->committed) return fail(SYN_ERR_STATE, name ": weights not committed (syn_commit)"); \
+  if ((h)->d_err != nullptr && *reinterpret_cast<volatile int*>((h)->d_err) != 0)        \
+    return fail(SYN_ERR_CUDA, name ": a kernel of an earlier call timed out in a pipeline wait; its results and " \
+                              "everything after it are invalid (syn_poll_error reports and clears the flag)"); \
   (h)->tn = 0
 
 int syn_forward(syn_handle_t* h, const float* x, int batch, float* params, float* pool, void* stream) {
@@ -1041,6 +1082,9 @@ static int forward_landmarks_host_impl(syn_handle_t* h, const void* x_host, int 
                              cudaMemcpyDeviceToHost, h->s_compute));
   SYN_CUDA(cudaStreamSynchronize(h->s_compute));
   SYN_CUDA(cudaStreamSynchronize(h->s_copy));
+  if (h->d_err != nullptr && *reinterpret_cast<volatile int*>(h->d_err) != 0)
+    return fail(SYN_ERR_CUDA, "forward_landmarks_host: a kernel timed out in a pipeline wait; the outputs are invalid "
+                              "(syn_poll_error reports and clears the flag)");
   return SYN_OK;
 }
 
@@ -1049,6 +1093,24 @@ int syn_forward_landmarks_host_u8(syn_handle_t* h, const uint8_t* x_host, int ba
   if (x_host == nullptr || lmk_host == nullptr || batch <= 0)
     return fail(SYN_ERR_INVALID, "syn_forward_landmarks_host_u8: bad argument");
   return forward_landmarks_host_impl(h, x_host, 1, batch, params_host, lmk_host);
+}
+
+int syn_peek_error(const syn_handle_t* h, int* flag_out) {
+  if (h == nullptr || flag_out == nullptr) return fail(SYN_ERR_INVALID, "syn_peek_error: null argument");
+  *flag_out = h->d_err != nullptr ? *reinterpret_cast<volatile int*>(h->d_err) : 0;
+  return SYN_OK;
+}
+
+int syn_poll_saturation(syn_handle_t* h, int* flag_out) {
+  if (h == nullptr || flag_out == nullptr) return fail(SYN_ERR_INVALID, "syn_poll_saturation: null argument");
+  DeviceGuard g(h->device);
+  SYN_CUDA(cudaDeviceSynchronize());
+  *flag_out = 0;
+  if (h->d_sat != nullptr) {
+    SYN_CUDA(cudaMemcpy(flag_out, h->d_sat, sizeof(int), cudaMemcpyDeviceToHost));
+    SYN_CUDA(cudaMemset(h->d_sat, 0, sizeof(int)));
+  }
+  return SYN_OK;
 }
 
 int64_t syn_launch_count(const syn_handle_t* h) { return h ? h->launches : -1; }
@@ -1079,8 +1141,8 @@ int syn_poll_error(syn_handle_t* h, int* flag_out) {
   SYN_CUDA(cudaDeviceSynchronize());
   *flag_out = 0;
   if (h->d_err != nullptr) {
-    SYN_CUDA(cudaMemcpy(flag_out, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-    SYN_CUDA(cudaMemset(h->d_err, 0, sizeof(int)));
+    *flag_out = *reinterpret_cast<volatile int*>(h->d_err);
+    *reinterpret_cast<volatile int*>(h->d_err) = 0;
   }
   return SYN_OK;
 }
@@ -1115,3 +1177,5 @@ int syn_debug_forward_until(syn_handle_t* h, const float* x, int batch, int laye
 }
 
 }  // extern "C"
+
+#include "heads_host.inl"

@@ -92,7 +92,8 @@ __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* 
     if ((it & 255u) == 0) {
       if (err_flag != nullptr && *reinterpret_cast<volatile int*>(err_flag) != 0) return false;
       if (globaltimer_ns() - t0 > 2000000000ull) {
-        if (err_flag != nullptr) atomicExch(err_flag, 1);
+        // the flag lives in mapped pinned host memory (the host reads it without a device sync): plain store
+        if (err_flag != nullptr) { *reinterpret_cast<volatile int*>(err_flag) = 1; __threadfence_system(); }
         return false;
       }
     }

@@ -6,6 +6,8 @@ arithmetic of the path runs in ``libsynergy_b200.so``.
 from __future__ import annotations
 
 import ctypes as C
+import threading
+import warnings
 from typing import Dict, Optional
 
 import numpy as np
@@ -38,6 +40,12 @@ class Engine:
         self.n_pts = 0
         self.n_vert = 0
         self._keep = []
+        # The C handle is not re-entrant and all calls share one activation workspace: serialise the host threads
+        # (nn.DataParallel replicas use one engine per device, but user threads may share a model) and order
+        # consecutive calls that arrive on different CUDA streams with an event.
+        self._lock = threading.RLock()
+        self._last_stream = None
+        self._last_event = None
 
     def close(self):
         if getattr(self, '_h', None):
@@ -117,15 +125,54 @@ class Engine:
         return x.to(torch.float32).contiguous()
 
     def _stream(self) -> int:
-        return torch.cuda.current_stream(self.device).cuda_stream
+        """Current torch stream of the engine's device; if the previous call ran on another stream, that
+        stream's work is ordered before this call (the workspace buffers are shared)."""
+        st = torch.cuda.current_stream(self.device)
+        if self._last_stream is not None and self._last_stream != st.cuda_stream and self._last_event is not None:
+            st.wait_event(self._last_event)
+        return st.cuda_stream
+
+    def _done(self) -> None:
+        st = torch.cuda.current_stream(self.device)
+        if self._last_event is None:
+            self._last_event = torch.cuda.Event()
+        self._last_event.record(st)
+        self._last_stream = st.cuda_stream
+
+    def raise_if_error(self) -> None:
+        """Cheap (no device sync) look at the sticky time-out flag of the bounded in-kernel waits; call it after a
+        host-side synchronisation point (``.cpu()``, ``synchronize``) before trusting the outputs."""
+        fn = getattr(self._lib, 'syn_peek_error', None)
+        if fn is None:
+            return
+        flag = C.c_int(0)
+        _lib.check(fn(self._h, C.byref(flag)))
+        if flag.value:
+            raise _lib.SynergyLibError(2, 'a kernel timed out in a pipeline wait; outputs are invalid '
+                                          '(Engine.poll_error() reports and clears the flag)')
+
+    def poll_saturation(self, warn: bool = True) -> int:
+        """Device sync + sticky "a block input was clamped to the fp16 range" flag of the split-fp16 engines
+        (|x| > ~937 at a block input).  Non-zero: use ``set_engine(0)`` (fp32) for this checkpoint."""
+        fn = getattr(self._lib, 'syn_poll_saturation', None)
+        if fn is None:
+            return 0
+        flag = C.c_int(0)
+        _lib.check(fn(self._h, C.byref(flag)))
+        if flag.value and warn:
+            warnings.warn('synergynet_b200: an activation left the range of the split-fp16 tensor-core engines and was '
+                          'clamped; results differ from fp32 -- use set_engine(0) for this checkpoint', RuntimeWarning)
+        return int(flag.value)
 
     def forward(self, x: torch.Tensor, want_pool: bool = False):
         x = self._check_x(x)
         b = x.shape[0]
         params = torch.empty((b, N_PARAMS), device=self.device, dtype=torch.float32)
         pool = torch.empty((b, 1280), device=self.device, dtype=torch.float32) if want_pool else None
-        _lib.check(self._lib.syn_forward(self._h, x.data_ptr(), b, params.data_ptr(),
-                                         pool.data_ptr() if want_pool else None, self._stream()))
+        with self._lock:
+            _lib.check(self._lib.syn_forward(self._h, x.data_ptr(), b, params.data_ptr(),
+                                             pool.data_ptr() if want_pool else None, self._stream()))
+            self._done()
         return (params, pool) if want_pool else params
 
     def reconstruct(self, params: torch.Tensor, dense: bool = False, whitening: bool = True,
@@ -138,8 +185,10 @@ class Engine:
         if n == 0:
             raise RuntimeError('dense basis not loaded' if dense else 'sparse basis not loaded')
         out = torch.empty((b, 3, n), device=self.device, dtype=torch.float32)
-        _lib.check(self._lib.syn_reconstruct(self._h, params.data_ptr(), b, int(dense), int(whitening),
-                                             int(transform), out.data_ptr(), self._stream()))
+        with self._lock:
+            _lib.check(self._lib.syn_reconstruct(self._h, params.data_ptr(), b, int(dense), int(whitening),
+                                                 int(transform), out.data_ptr(), self._stream()))
+            self._done()
         return out
 
     def forward_landmarks(self, x: torch.Tensor, want_params: bool = False):
@@ -150,9 +199,11 @@ class Engine:
         b = x.shape[0]
         lmk = torch.empty((b, 3, self.n_pts), device=self.device, dtype=torch.float32)
         params = torch.empty((b, N_PARAMS), device=self.device, dtype=torch.float32) if want_params else None
-        _lib.check(self._lib.syn_forward_landmarks(self._h, x.data_ptr(), b,
-                                                   params.data_ptr() if want_params else None,
-                                                   lmk.data_ptr(), self._stream()))
+        with self._lock:
+            _lib.check(self._lib.syn_forward_landmarks(self._h, x.data_ptr(), b,
+                                                       params.data_ptr() if want_params else None,
+                                                       lmk.data_ptr(), self._stream()))
+            self._done()
         return (lmk, params) if want_params else lmk
 
     def _forward_landmarks_u8(self, x: torch.Tensor, want_params: bool):
@@ -162,9 +213,11 @@ class Engine:
         b = x.shape[0]
         lmk = torch.empty((b, 3, self.n_pts), device=self.device, dtype=torch.float32)
         params = torch.empty((b, N_PARAMS), device=self.device, dtype=torch.float32) if want_params else None
-        _lib.check(self._lib.syn_forward_landmarks_u8(self._h, x.data_ptr(), b,
-                                                      params.data_ptr() if want_params else None,
-                                                      lmk.data_ptr(), self._stream()))
+        with self._lock:
+            _lib.check(self._lib.syn_forward_landmarks_u8(self._h, x.data_ptr(), b,
+                                                          params.data_ptr() if want_params else None,
+                                                          lmk.data_ptr(), self._stream()))
+            self._done()
         return (lmk, params) if want_params else lmk
 
     def forward_landmarks_host(self, x_host: torch.Tensor, lmk_host: Optional[torch.Tensor] = None,
@@ -172,19 +225,100 @@ class Engine:
         """End-to-end call on HOST tensors (pinned recommended): H2D, forward, landmarks, D2H."""
         if x_host.is_cuda or x_host.dtype not in (torch.float32, torch.uint8) or not x_host.is_contiguous():
             raise RuntimeError('x_host must be a contiguous fp32 (normalised) or uint8 (raw) CPU tensor')
+        if x_host.dim() != 4 or tuple(x_host.shape[1:]) != (3, 120, 120):
+            raise RuntimeError(f'expected (B,3,120,120) crops, got {tuple(x_host.shape)}')
         b = x_host.shape[0]
         if lmk_host is None:
             lmk_host = torch.empty((b, 3, self.n_pts), dtype=torch.float32)
+        # the C side writes B*3*n_pts and B*62 floats through these pointers: refuse anything it could overrun
+        for name, buf, need in (('lmk_host', lmk_host, b * 3 * self.n_pts), ('params_host', params_host, b * N_PARAMS)):
+            if buf is None:
+                continue
+            if buf.is_cuda or buf.dtype != torch.float32 or not buf.is_contiguous() or buf.numel() < need:
+                raise RuntimeError(f'{name} must be a contiguous CPU float32 tensor with at least {need} elements')
         fn = self._lib.syn_forward_landmarks_host_u8 if x_host.dtype == torch.uint8 else self._lib.syn_forward_landmarks_host
-        _lib.check(fn(
-            self._h, x_host.data_ptr(), b, params_host.data_ptr() if params_host is not None else None,
-            lmk_host.data_ptr()))
+        with self._lock:
+            _lib.check(fn(
+                self._h, x_host.data_ptr(), b, params_host.data_ptr() if params_host is not None else None,
+                lmk_host.data_ptr()))
         return lmk_host
+
+    # ---- PointNet refinement heads + losses (training-forward surface, model_building.py:141-157) --------------
+    _FOR_LAYERS = [f'conv{i}' for i in range(1, 10)]
+    _REV_LAYERS = ['conv1', 'conv2', 'conv3', 'conv4', 'conv5', 'conv6_1', 'conv6_2', 'conv6_3']
+
+    def load_pointnet(self, net: int, sd: Dict[str, torch.Tensor]) -> None:
+        """net 0: MLP_for state dict (conv1..conv9 + bn1..bn9), net 1: MLP_rev (conv1..5, conv6_1/2/3 + their BN);
+        keys without prefix, as ``module.state_dict()`` returns them (pointnet_backbone.py:7-29,67-88)."""
+        names = self._FOR_LAYERS if net == 0 else self._REV_LAYERS
+        with self._lock:
+            for i, cname in enumerate(names):
+                bname = 'bn' + cname[4:]
+                w = _host_f32(sd[f'{cname}.weight'])
+                cb = _host_f32(sd[f'{cname}.bias'])
+                bn = [_host_f32(sd[f'{bname}.{k}']) for k in ('weight', 'bias', 'running_mean', 'running_var')]
+                _lib.check(self._lib.syn_pointnet_set_layer(self._h, net, i, w.data_ptr(), w.shape[0], w.shape[1], cb.data_ptr(),
+                                                            *[t.data_ptr() for t in bn], 1e-5))
+            _lib.check(self._lib.syn_pointnet_commit(self._h, net))
+
+    def _dev_f32(self, t: torch.Tensor) -> torch.Tensor:
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def mlp_for(self, lmk: torch.Tensor, pool: torch.Tensor, params: torch.Tensor):
+        """(point_residual (B,3,68), lmk + 0.05 * point_residual) -- MLP_for.forward + model_building.py:150."""
+        lmk, pool, params = self._dev_f32(lmk), self._dev_f32(pool), self._dev_f32(params)
+        b = lmk.shape[0]
+        if tuple(lmk.shape[1:]) != (3, 68) or tuple(pool.shape) != (b, 1280) or tuple(params.shape) != (b, N_PARAMS):
+            raise RuntimeError(f'mlp_for: expected (B,3,68), (B,1280), (B,62); got {tuple(lmk.shape)}, {tuple(pool.shape)}, {tuple(params.shape)}')
+        res, ref = torch.empty_like(lmk), torch.empty_like(lmk)
+        with self._lock:
+            _lib.check(self._lib.syn_mlp_for(self._h, lmk.data_ptr(), pool.data_ptr(), params.data_ptr(), b, res.data_ptr(),
+                                             ref.data_ptr(), self._stream()))
+            self._done()
+        return res, ref
+
+    def mlp_rev(self, lmk: torch.Tensor) -> torch.Tensor:
+        lmk = self._dev_f32(lmk)
+        if lmk.dim() != 3 or tuple(lmk.shape[1:]) != (3, 68):
+            raise RuntimeError(f'mlp_rev: expected (B,3,68), got {tuple(lmk.shape)}')
+        out = torch.empty((lmk.shape[0], N_PARAMS), device=self.device, dtype=torch.float32)
+        with self._lock:
+            _lib.check(self._lib.syn_mlp_rev(self._h, lmk.data_ptr(), lmk.shape[0], out.data_ptr(), self._stream()))
+            self._done()
+        return out
+
+    def wing_loss(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """WingLoss(omega=10, epsilon=2) of two (B,3,N) tensors -> 0-d tensor (loss_definition.py:8-27)."""
+        pred, target = self._dev_f32(pred), self._dev_f32(target)
+        if pred.shape != target.shape or pred.dim() != 3 or pred.shape[1] != 3:
+            raise RuntimeError(f'wing_loss: expected two (B,3,N) tensors, got {tuple(pred.shape)} and {tuple(target.shape)}')
+        out = torch.empty((1,), device=self.device, dtype=torch.float32)
+        with self._lock:
+            _lib.check(self._lib.syn_wing_loss(self._h, pred.data_ptr(), target.data_ptr(), pred.shape[0], pred.shape[2],
+                                               out.data_ptr(), self._stream()))
+            self._done()
+        return out[0]
+
+    def param_loss(self, inp: torch.Tensor, target: torch.Tensor, mode: str = 'normal') -> torch.Tensor:
+        """ParamLoss (loss_definition.py:29-42): per-sample (B,) tensor; mode 'normal' or 'only_3dmm'."""
+        if mode not in ('normal', 'only_3dmm'):
+            raise RuntimeError(f"param_loss: mode must be 'normal' or 'only_3dmm', got {mode!r}")
+        inp, target = self._dev_f32(inp), self._dev_f32(target)
+        if inp.dim() != 2 or inp.shape[1] != N_PARAMS or target.shape != inp.shape:
+            raise RuntimeError('param_loss: expected two (B,62) tensors')
+        out = torch.empty((inp.shape[0],), device=self.device, dtype=torch.float32)
+        with self._lock:
+            _lib.check(self._lib.syn_param_loss(self._h, inp.data_ptr(), target.data_ptr(), inp.shape[0],
+                                                0 if mode == 'normal' else 1, out.data_ptr(), self._stream()))
+            self._done()
+        return out
 
     def debug_forward_until(self, x: torch.Tensor, layer: int) -> torch.Tensor:
         x = self._check_x(x)
         spec = conv_plan()[layer]
         out = torch.empty((x.shape[0], spec.h_out, spec.h_out, spec.cout), device=self.device, dtype=torch.float32)
-        _lib.check(self._lib.syn_debug_forward_until(self._h, x.data_ptr(), x.shape[0], layer,
-                                                     out.data_ptr(), self._stream()))
+        with self._lock:
+            _lib.check(self._lib.syn_debug_forward_until(self._h, x.data_ptr(), x.shape[0], layer,
+                                                         out.data_ptr(), self._stream()))
+            self._done()
         return out

@@ -39,7 +39,8 @@ class _Runtime:
     def __init__(self):
         self._engines: Dict[int, Engine] = {}
         self._sig: Dict[int, tuple] = {}
-        self._lock = threading.Lock()
+        self._pn_sig: Dict[tuple, tuple] = {}
+        self._lock = threading.RLock()
         self.engine_kind = None      # None: the library default (fused tcgen05 engine)
 
     @staticmethod
@@ -72,7 +73,19 @@ class _Runtime:
                 if self.engine_kind is not None:
                     eng.set_engine(self.engine_kind)
                 self._sig[idx] = sig
+                self._pn_sig.pop((idx, 0), None)          # a new commit rebuilds the library state: re-hand the heads
+                self._pn_sig.pop((idx, 1), None)
         return eng
+
+    def ensure_pointnet(self, eng: Engine, net: int, module: nn.Module) -> None:
+        """Hand the PointNet head ``module`` (net 0 = MLP_for, 1 = MLP_rev) to ``eng`` when its parameters changed."""
+        sd = {k: v for k, v in module.state_dict(keep_vars=True).items() if not k.endswith('num_batches_tracked')}
+        sig = self._signature(list(sd.values()))
+        key = (eng.device.index, net)
+        with self._lock:
+            if self._pn_sig.get(key) != sig:
+                eng.load_pointnet(net, sd)
+                self._pn_sig[key] = sig
 
 
 class I2P(nn.Module):
@@ -98,9 +111,25 @@ class I2P(nn.Module):
     def _engine(self, device) -> Engine:
         return self._rt.get(device, self._backbone_sd, self._basis_provider)
 
+    def _compute_device(self, t: Optional[torch.Tensor] = None) -> torch.device:
+        """Where the library runs for tensor ``t``: its own GPU, else the GPU the backbone lives on, else the current
+        CUDA device -- the reference wrappers are built on the CPU (synergy3DMM.py:71-77) and still usable as is."""
+        if t is not None and t.is_cuda:
+            return t.device
+        w = next(self.backbone.parameters())
+        if w.is_cuda:
+            return w.device
+        if not torch.cuda.is_available():
+            raise RuntimeError('synergynet_b200: no CUDA device (B200) visible; there is no CPU fallback')
+        return torch.device('cuda', torch.cuda.current_device())
+
     def forward_test(self, input):
-        """Testing time forward -> (param62, avgpool1280) (model_building.py:59-62)."""
-        params, pool = self._engine(input.device).forward(input, want_pool=True)
+        """Testing time forward -> (param62, avgpool1280) (model_building.py:59-62).  A CPU input is moved to the
+        compute GPU and the results come back on the CPU, as the reference's CPU model would return them."""
+        dev = self._compute_device(input)
+        params, pool = self._engine(dev).forward(input.to(dev), want_pool=True)
+        if not input.is_cuda:
+            params, pool = params.to(input.device), pool.to(input.device)
         return params, pool
 
     def forward(self, input, target):
@@ -132,6 +161,8 @@ class _SynergyBase(nn.Module):
             self.to(device)
         self._refresh_data_param()
         object.__setattr__(self.I2P, '_basis_provider', self._basis)
+        object.__setattr__(self.forwardDirection, '_engine_provider', self._pointnet_engine)
+        object.__setattr__(self.reverseDirection, '_engine_provider', self._pointnet_engine)
 
     def _refresh_data_param(self):
         self.data_param = [self.param_mean, self.param_std, self.w_shp_base, self.u_base, self.w_exp_base]
@@ -162,22 +193,62 @@ class _SynergyBase(nn.Module):
         space (reference model_building.py:106-139)."""
         if param.shape[1] != 62:
             raise RuntimeError('length of params mismatch')
-        dev = param.device if param.is_cuda else self.param_mean.device
-        return self._engine(dev).reconstruct(param, dense=dense, whitening=whitening, transform=transform)
+        dev = self._compute_device(param)
+        out = self._engine(dev).reconstruct(param.to(dev), dense=dense, whitening=whitening, transform=transform)
+        return out if param.is_cuda else out.to(param.device)
+
+    def _compute_device(self, t: Optional[torch.Tensor] = None) -> torch.device:
+        """GPU the library runs on for tensor ``t``: t's own device, else the device of the buffers, else the current
+        CUDA device (the no-argument reference wrappers are constructed on the CPU, synergy3DMM.py:71-114)."""
+        if t is not None and t.is_cuda:
+            return t.device
+        if self.param_mean.is_cuda:
+            return self.param_mean.device
+        if not torch.cuda.is_available():
+            raise RuntimeError('synergynet_b200: no CUDA device (B200) visible; there is no CPU fallback')
+        return torch.device('cuda', torch.cuda.current_device())
 
     def forward_test(self, input):
-        """test time forward (model_building.py:159-162): whitened (B,62) parameters."""
-        return self._engine(input.device).forward(input)
+        """test time forward (model_building.py:159-162): whitened (B,62) parameters (on the input's device)."""
+        dev = self._compute_device(input)
+        out = self._engine(dev).forward(input.to(dev))
+        return out if input.is_cuda else out.to(input.device)
 
     def forward_landmarks(self, input):
         """forward_test + reconstruct_vertex_62(dense=False) in one library call."""
-        return self._engine(input.device).forward_landmarks(input)
+        dev = self._compute_device(input)
+        out = self._engine(dev).forward_landmarks(input.to(dev))
+        return out if input.is_cuda else out.to(input.device)
+
+    def _pointnet_engine(self, t: torch.Tensor, net: int) -> Engine:
+        """Engine of the compute device with the weights of head ``net`` (0 = forwardDirection, 1 = reverseDirection)."""
+        eng = self._engine(self._compute_device(t))
+        self.I2P._rt.ensure_pointnet(eng, net, self.forwardDirection if net == 0 else self.reverseDirection)
+        return eng
 
     def forward(self, input, target):
-        raise NotImplementedError(
-            'SynergyNet.forward(input, target) is the training forward with the PointNet heads and '
-            'losses (model_building.py:141-157); it is listed as "next" (SURVEY.md section 8 f4) and '
-            'is not part of the inference hot path built here. Use forward_test().')
+        """The reference's training-time forward (model_building.py:141-157) in inference mode (eval BatchNorm, no
+        autograd): backbone -> landmarks of prediction and ground truth -> WingLoss / ParamLoss -> MLP_for refinement
+        -> MLP_rev -> the two cycle losses.  Returns the same dict of five (weighted) losses; the intermediate
+        tensors are kept in ``self.last_forward`` for inspection."""
+        dev = self._compute_device(input)
+        eng = self._engine(dev)
+        _3D_attr, avgpool = eng.forward(input.to(dev), want_pool=True)
+        _3D_attr_GT = target.to(device=dev, dtype=torch.float32)
+        vertex_lmk = eng.reconstruct(_3D_attr, dense=False)
+        vertex_GT_lmk = eng.reconstruct(_3D_attr_GT, dense=False)
+        self.loss['loss_LMK_f0'] = 0.05 * eng.wing_loss(vertex_lmk, vertex_GT_lmk)
+        self.loss['loss_Param_In'] = 0.02 * eng.param_loss(_3D_attr, _3D_attr_GT)
+        eng = self._pointnet_engine(input, 0)
+        point_residual, refined = eng.mlp_for(vertex_lmk, avgpool, _3D_attr)      # refined = lmk + 0.05 * residual (:150)
+        self.loss['loss_LMK_pointNet'] = 0.05 * eng.wing_loss(refined, vertex_GT_lmk)
+        eng = self._pointnet_engine(input, 1)
+        _3D_attr_S2 = eng.mlp_rev(refined)
+        self.loss['loss_Param_S2'] = 0.02 * eng.param_loss(_3D_attr_S2, _3D_attr_GT, mode='only_3dmm')
+        self.loss['loss_Param_S1S2'] = 0.001 * eng.param_loss(_3D_attr_S2, _3D_attr, mode='only_3dmm')
+        self.last_forward = {'_3D_attr': _3D_attr, 'avgpool': avgpool, 'vertex_lmk': vertex_lmk, 'vertex_GT_lmk': vertex_GT_lmk,
+                             'point_residual': point_residual, 'vertex_lmk_refined': refined, '_3D_attr_S2': _3D_attr_S2}
+        return self.loss
 
     def get_losses(self):
         return self.loss.keys()
@@ -209,7 +280,7 @@ class _SynergyBase(nn.Module):
         crops = [cv2.resize(crop_img(input, b), dsize=(120, 120), interpolation=interp) for b in boxes]
         batch = torch.from_numpy(np.stack(crops)).permute(0, 3, 1, 2).float()
         batch = ((batch - 127.5) / 128.0).contiguous()
-        dev = self.param_mean.device
+        dev = self._compute_device()
         eng = self._engine(dev)
         params = eng.forward(batch.to(dev))
         lmk = eng.reconstruct(params, dense=False).cpu().numpy()
