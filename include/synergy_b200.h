@@ -117,6 +117,21 @@ int syn_reconstruct(syn_handle_t* h, const float* params62_dev, int batch, int d
 int syn_forward_landmarks(syn_handle_t* h, const float* x_dev, int batch, float* params62_dev,
                           float* lmk_dev, void* stream);
 
+/* ---- image-space outputs of get_all_outputs ----------------------------------------
+ * _predict_vertices (utils/inference.py:127-138) fused into the reconstruction: vertices leave the GPU already in the
+ * coordinates of the original image.  roi5_dev (B,5) fp32 = kx, sx, ky, sy, kz with kx = (ex-sx)/120, ky = (ey-sy)/120,
+ * kz = (kx+ky)/2 evaluated in double on the host like the reference's Python scalars; whitening and the y flip are on. */
+int syn_reconstruct_image(syn_handle_t* h, const float* params62_dev, int batch, int dense, const float* roi5_dev,
+                          float* out_dev, void* stream);
+/* parse_pose + predict_pose (utils/inference.py:33-62,86-92,146-157) for B whitened vectors: angles_dev (B,3) fp64
+ * degrees [pitch-like x, yaw-like y, roll-like z in the reference's order], t3d_dev (B,3) fp32 (image coordinates when
+ * roi5_dev is given, crop coordinates when NULL). */
+int syn_pose_decode(syn_handle_t* h, const float* params62_dev, int batch, const float* roi5_dev, double* angles_dev,
+                    float* t3d_dev, void* stream);
+/* CenterCrop(margin, mode='test') of the reference loader (utils/ddfa.py:162-243, benchmark.py:116): the uint8 entry
+ * points read the `margin`-pixel frame of every crop as 0 before normalising.  0 (default) = off. */
+int syn_set_center_crop(syn_handle_t* h, int margin);
+
 /* ---- compute, host buffers (the end-to-end call: H2D of the crops, forward, landmarks, D2H) --
  * x_host (B,3,120,120) fp32, lmk_host (B,3,68), params62_host (B,62) or NULL.  Pinned host
  * memory is recommended; chunks are pipelined over internal streams.  Synchronous. */
@@ -155,6 +170,23 @@ int syn_wing_loss(syn_handle_t* h, const float* pred_dev, const float* target_de
  * (input[:, :50] against target[:, 12:62], as the reference does). */
 int syn_param_loss(syn_handle_t* h, const float* input_dev, const float* target_dev, int batch, int mode,
                    float* out_dev, void* stream);
+
+/* ---- ResNet-50 backbone variant (BASELINE.json configs[4]; backbone_nets/resnet_backbone.py:227-249) -----------
+ * 53 convolutions in execution order: 0 = conv1 (7x7/s2); then per Bottleneck conv1, conv2, conv3 and -- first block of a
+ * stage -- downsample.0 (syn_resnet_conv_desc gives each one's geometry).  Weights OIHW fp32 + eval BatchNorm2d, as
+ * for syn_set_conv_bn.  Heads: the four Linear layers concatenated in the reference's OUTPUT order
+ * fc_ori | fc_shape | fc_exp | fc_tex -> (102, 2048) weights, (102) bias (:242-246).
+ * syn_resnet50_forward: x_dev (B,3,120,120) NCHW -> out102_dev (B,102) exactly what ResNet._forward_impl returns;
+ * pool2048_dev (B,2048) = the flattened avgpool, may be NULL.  (The reference's I2P unpacks two values from this
+ * backbone and fails; the Python shim adapts: params = out[:, :62], pool = the 2048-d feature.) */
+int syn_resnet_num_convs(void);                              /* 53 */
+int syn_resnet_conv_desc(int idx, syn_conv_desc_t* out);
+int syn_resnet_set_conv(syn_handle_t* h, int idx, const float* w_host, int64_t w_numel, const float* bn_weight_host,
+                        const float* bn_bias_host, const float* bn_mean_host, const float* bn_var_host, float eps);
+int syn_resnet_set_heads(syn_handle_t* h, const float* w102x2048_host, const float* b102_host);
+int syn_resnet_commit(syn_handle_t* h);                      /* after syn_commit */
+int syn_resnet50_forward(syn_handle_t* h, const float* x_dev, int batch, float* out102_dev, float* pool2048_dev,
+                         void* stream);
 
 /* ---- introspection ---------------------------------------------------------------------------*/
 /* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */

@@ -212,6 +212,90 @@ def predict_pose(param: np.ndarray, pack, roi_box) -> Tuple[list, np.ndarray]:
     return angles, t3d
 
 
+# ---- PointNet refinement heads and the training-forward losses ---------------------------------------------
+
+def _pn_layer(sd, x, conv, bn):
+    """F.relu(bn(conv(x))) with eval-mode BatchNorm1d, as every layer of pointnet_backbone.py:32-62 / 91-102."""
+    y = F.conv1d(x, sd[f'{conv}.weight'], sd[f'{conv}.bias'])
+    y = F.batch_norm(y, sd[f'{bn}.running_mean'], sd[f'{bn}.running_var'], sd[f'{bn}.weight'], sd[f'{bn}.bias'],
+                     False, 0.0, BN_EPS)
+    return F.relu(y)
+
+
+@torch.no_grad()
+def mlp_for_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, avgpool: torch.Tensor, shape_code: torch.Tensor,
+                    expr_code: torch.Tensor, prefix: str = 'forwardDirection.') -> torch.Tensor:
+    """MLP_for.forward, backbone_nets/pointnet_backbone.py:31-64: x (B,3,N) -> point residual (B,3,N)."""
+    sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    n = x.shape[2]
+    out = _pn_layer(sd, x, 'conv1', 'bn1')                                  # :32
+    out = _pn_layer(sd, out, 'conv2', 'bn2')                                # :33
+    point_features = out                                                    # :34
+    out = _pn_layer(sd, out, 'conv3', 'bn3')
+    out = _pn_layer(sd, out, 'conv4', 'bn4')
+    out = _pn_layer(sd, out, 'conv5', 'bn5')
+    global_features = F.max_pool1d(out, n)                                  # :38
+    rep = lambda t: t.unsqueeze(2).repeat(1, 1, n) if t.dim() == 2 else t.repeat(1, 1, n)   # :39,49-56
+    cat = torch.cat([point_features, rep(global_features), rep(avgpool), rep(shape_code), rep(expr_code)], 1)   # :58
+    out = _pn_layer(sd, cat, 'conv6', 'bn6')
+    out = _pn_layer(sd, out, 'conv7', 'bn7')
+    out = _pn_layer(sd, out, 'conv8', 'bn8')
+    return _pn_layer(sd, out, 'conv9', 'bn9')                               # :62 (ReLU on the output too)
+
+
+@torch.no_grad()
+def mlp_rev_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = 'reverseDirection.') -> torch.Tensor:
+    """MLP_rev.forward, backbone_nets/pointnet_backbone.py:90-106: x (B,3,N) -> (B,62)."""
+    sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    out = x
+    for i in range(1, 6):                                                   # :91-95
+        out = _pn_layer(sd, out, f'conv{i}', f'bn{i}')
+    g = F.max_pool1d(out, x.shape[2])                                       # :96
+    heads = [_pn_layer(sd, g, f'conv6_{i}', f'bn6_{i}') for i in (1, 2, 3)]   # :99-101
+    return torch.cat(heads, 1).squeeze(2)                                   # :104
+
+
+def wing_loss(pred: torch.Tensor, target: torch.Tensor, omega: float = 10, epsilon: float = 2) -> torch.Tensor:
+    """WingLoss.forward, loss_definition.py:15-27."""
+    import math
+    n_points = pred.shape[2]
+    y_hat = pred.transpose(1, 2).contiguous().view(-1, 3 * n_points)
+    y = target.transpose(1, 2).contiguous().view(-1, 3 * n_points)
+    delta_y = (y - y_hat).abs()
+    d1, d2 = delta_y[delta_y < omega], delta_y[delta_y >= omega]
+    loss1 = omega * torch.log(1 + d1 / epsilon)
+    C = omega - omega * math.log(1 + omega / epsilon)
+    loss2 = d2 - C
+    return (loss1.sum() + loss2.sum()) / (len(loss1) + len(loss2))
+
+
+def param_loss(inp: torch.Tensor, target: torch.Tensor, mode: str = 'normal') -> torch.Tensor:
+    """ParamLoss.forward, loss_definition.py:35-42 (one value per sample)."""
+    mse = lambda a, b: (a - b) ** 2
+    if mode == 'normal':
+        return torch.sqrt(mse(inp[:, :12], target[:, :12]).mean(1) + mse(inp[:, 12:], target[:, 12:]).mean(1))
+    return torch.sqrt(mse(inp[:, :50], target[:, 12:62]).mean(1))          # 'only_3dmm'
+
+
+@torch.no_grad()
+def synergy_forward(sd: Dict[str, torch.Tensor], basis: Dict[str, np.ndarray], x: torch.Tensor, target: torch.Tensor):
+    """SynergyNet.forward(input, target) in eval mode, model_building.py:141-157: the five weighted losses and the
+    intermediate tensors."""
+    attr, avgpool = mobilenetv2_forward(sd, x)                              # :142 (I2P.forward)
+    gt = target.float()
+    lmk = torch.from_numpy(reconstruct_vertex_62(attr.numpy(), basis))      # :144
+    lmk_gt = torch.from_numpy(reconstruct_vertex_62(gt.numpy(), basis))     # :145
+    loss = {'loss_LMK_f0': 0.05 * wing_loss(lmk, lmk_gt), 'loss_Param_In': 0.02 * param_loss(attr, gt)}   # :146-147
+    residual = mlp_for_forward(sd, lmk, avgpool, attr[:, 12:52], attr[:, 52:62])   # :149
+    refined = lmk + 0.05 * residual                                         # :150
+    loss['loss_LMK_pointNet'] = 0.05 * wing_loss(refined, lmk_gt)           # :151
+    attr_s2 = mlp_rev_forward(sd, refined)                                  # :153
+    loss['loss_Param_S2'] = 0.02 * param_loss(attr_s2, gt, mode='only_3dmm')        # :154
+    loss['loss_Param_S1S2'] = 0.001 * param_loss(attr_s2, attr, mode='only_3dmm')   # :155
+    return loss, dict(_3D_attr=attr, avgpool=avgpool, vertex_lmk=lmk, vertex_GT_lmk=lmk_gt, point_residual=residual,
+                      vertex_lmk_refined=refined, _3D_attr_S2=attr_s2)
+
+
 def nme_vs_reference(lmk_new: np.ndarray, lmk_ref: np.ndarray) -> np.ndarray:
     """Landmark NME of ``lmk_new`` against ``lmk_ref`` (both (B,>=2,68) in crop coordinates)
     with the bbox-sqrt-area normaliser of benchmark_aflw2000.py:127-135."""
@@ -230,3 +314,34 @@ def max_rel_err(new, ref) -> float:
     new = np.asarray(new, np.float64)
     ref = np.asarray(ref, np.float64)
     return float(np.abs(new - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+# ---- ResNet-50 backbone variant (BASELINE.json configs[4]) ---------------------------------------------------------------
+
+@torch.no_grad()
+def resnet50_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = 'I2P.backbone.'):
+    """ResNet._forward_impl with Bottleneck blocks [3,4,6,3], backbone_nets/resnet_backbone.py:120-146,227-249.
+    Returns (out102 = ori|shape|exp|tex, pooled 2048-d feature).  The adapter of the B200 shim (and of the golden
+    vectors) for the (param62, avgpool) contract the reference's I2P expects is out102[:, :62], pooled."""
+    sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+    def bn(t, key):
+        return F.batch_norm(t, sd[key + '.running_mean'], sd[key + '.running_var'], sd[key + '.weight'], sd[key + '.bias'],
+                            False, 0.0, BN_EPS)
+
+    x = F.relu(bn(F.conv2d(x, sd['conv1.weight'], None, 2, 3), 'bn1'))                       # :229-231
+    x = F.max_pool2d(x, 3, 2, 1)                                                              # :232
+    for li, (blocks, stride) in enumerate(((3, 1), (4, 2), (6, 2), (3, 2)), 1):               # :234-237
+        for j in range(blocks):
+            pre = f'layer{li}.{j}'
+            st = stride if j == 0 else 1
+            out = F.relu(bn(F.conv2d(x, sd[f'{pre}.conv1.weight']), f'{pre}.bn1'))            # :126-128
+            out = F.relu(bn(F.conv2d(out, sd[f'{pre}.conv2.weight'], None, st, 1), f'{pre}.bn2'))   # :130-132
+            out = bn(F.conv2d(out, sd[f'{pre}.conv3.weight']), f'{pre}.bn3')                  # :134-135
+            identity = x
+            if j == 0:                                                                         # :137-138
+                identity = bn(F.conv2d(x, sd[f'{pre}.downsample.0.weight'], None, st), f'{pre}.downsample.1')
+            x = F.relu(out + identity)                                                         # :140-141
+    pooled = torch.flatten(F.adaptive_avg_pool2d(x, 1), 1)                                     # :239-240
+    heads = [F.linear(pooled, sd[f'{k}.weight'], sd[f'{k}.bias']) for k in ('fc_ori', 'fc_shape', 'fc_exp', 'fc_tex')]
+    return torch.cat(heads, 1), pooled                                                         # :242-246

@@ -59,6 +59,15 @@ SIGNATURES = {
     'syn_mlp_rev': (_I, [_P, _F, _I, _F, _P]),
     'syn_wing_loss': (_I, [_P, _F, _F, _I, _I, _F, _P]),
     'syn_param_loss': (_I, [_P, _F, _F, _I, _I, _F, _P]),
+    'syn_reconstruct_image': (_I, [_P, _F, _I, _I, _F, _F, _P]),
+    'syn_pose_decode': (_I, [_P, _F, _I, _F, _F, _F, _P]),
+    'syn_set_center_crop': (_I, [_P, _I]),
+    'syn_resnet_num_convs': (_I, []),
+    'syn_resnet_conv_desc': (_I, [_I, C.POINTER(ConvDesc)]),
+    'syn_resnet_set_conv': (_I, [_P, _I, _F, _L, _F, _F, _F, _F, C.c_float]),
+    'syn_resnet_set_heads': (_I, [_P, _F, _F]),
+    'syn_resnet_commit': (_I, [_P]),
+    'syn_resnet50_forward': (_I, [_P, _F, _I, _F, _F, _P]),
     'syn_launch_count': (_L, [_P]),
     'syn_set_timing': (_I, [_P, _I]),
     'syn_get_timings': (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_char_p), _I, C.POINTER(C.c_int)]),
@@ -73,7 +82,8 @@ SIGNATURES = {
 # entry points every build must export (everything the compute path binds)
 _CORE = {n for n in SIGNATURES if n not in ('syn_peek_error', 'syn_poll_saturation', 'syn_pointnet_set_layer',
                                              'syn_pointnet_commit', 'syn_mlp_for', 'syn_mlp_rev', 'syn_wing_loss',
-                                             'syn_param_loss')}
+                                             'syn_param_loss', 'syn_reconstruct_image', 'syn_pose_decode', 'syn_set_center_crop', 'syn_resnet_num_convs', 'syn_resnet_conv_desc',
+                                             'syn_resnet_set_conv', 'syn_resnet_set_heads', 'syn_resnet_commit', 'syn_resnet50_forward')}
 
 
 def declared_symbols(header: str = HEADER_PATH):

@@ -192,3 +192,69 @@ class MLP_rev(_PointMLPParams):
         """(B,62) = [rot12 | shape40 | expr10] regressed back from landmarks x (B,3,68) (pointnet_backbone.py:90-106)."""
         out = self._engine(x).mlp_rev(x)
         return out if x.is_cuda else out.to(x.device)
+
+
+# ---- ResNet-50 backbone variant (reference backbone_nets/resnet_backbone.py:120-249; BASELINE.json configs[4]) -------
+
+class _Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.downsample = downsample
+
+
+class ResNet50Params(nn.Module):
+    """Key schema of ``resnet_backbone.resnet50()`` (conv1/bn1, layer1..4.{i}.conv{1,2,3}/bn{1,2,3}/downsample.{0,1},
+    fc_tex/fc_ori/fc_shape/fc_exp); parameter container, the forward pass runs in the sm_100a library."""
+    feature_dim = 2048
+
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        inplanes = 64
+        for li, (planes, blocks, stride) in enumerate(((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)), 1):
+            layers = []
+            for j in range(blocks):
+                ds = None
+                if j == 0:
+                    ds = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
+                layers.append(_Bottleneck(inplanes, planes, stride if j == 0 else 1, ds))
+                inplanes = planes * 4
+            setattr(self, f'layer{li}', nn.Sequential(*layers))
+        self.fc_tex = nn.Linear(2048, 40)
+        self.fc_ori = nn.Linear(2048, 12)
+        self.fc_shape = nn.Linear(2048, 40)
+        self.fc_exp = nn.Linear(2048, 10)
+        for m in self.modules():                                            # resnet_backbone.py:184-189
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError('ResNet50Params is a parameter container; the forward pass runs in the sm_100a library')
+
+
+def resnet50_conv_keys():
+    """(conv key, bn key) of the 53 convolutions in the execution order of the C ABI (syn_resnet_set_conv)."""
+    keys = [('conv1', 'bn1')]
+    for li, blocks in enumerate((3, 4, 6, 3), 1):
+        for j in range(blocks):
+            pre = f'layer{li}.{j}'
+            keys += [(f'{pre}.conv1', f'{pre}.bn1'), (f'{pre}.conv2', f'{pre}.bn2'), (f'{pre}.conv3', f'{pre}.bn3')]
+            if j == 0:
+                keys.append((f'{pre}.downsample.0', f'{pre}.downsample.1'))
+    return keys
+
+
+def resnet50(pretrained: bool = False, **_):
+    return ResNet50Params()

@@ -27,7 +27,8 @@ constexpr int kDnAPlane = 128 * kDnK * 2;                 // 16 KB: one plane (h
 constexpr int kDnATile = 3 * 2 * kDnAPlane;               // 96 KB per 128-vertex tile: [x|y|z][hi|lo]
 constexpr int kDnBPlane = kDnFaces * kDnK * 2;            // 8 KB
 constexpr int kDnBTile = 2 * kDnBPlane;                   // 16 KB per face tile: [hi|lo]
-constexpr int kDnPoseTile = kDnFaces * 12 * 4;            // 3 KB
+constexpr int kDnPoseStride = 20;                        // floats per face: [R|t] (12), crop->image affine kx, sx, ky, sy, kz, pad
+constexpr int kDnPoseTile = kDnFaces * kDnPoseStride * 4; // 5 KB
 constexpr int kDnBSlot = kDnBTile + kDnPoseTile;
 constexpr int kDnMetaTile = 128 * 6 * 4;                  // per vertex tile: u[3][128], 1/rowscale[3][128]
 constexpr int kDnBSlots = 4;                              // alpha/pose ring: loads run 3 items ahead of the MMAs
@@ -41,7 +42,7 @@ constexpr int kDnThreads = (kDnEpiWarps + 1) * 32;
 __global__ void __launch_bounds__(64) dense_alpha_kernel(const float* __restrict__ params, const float* __restrict__ mean,
                                                          const float* __restrict__ stdv, const float* __restrict__ ascale,
                                                          uint8_t* __restrict__ aimg, float* __restrict__ pose, int batch,
-                                                         int whitening) {
+                                                         int whitening, const float* __restrict__ roi5) {
   const int f = threadIdx.x, tile = blockIdx.x;
   const int b = tile * kDnFaces + f;
   float pr[kNumParams];
@@ -54,8 +55,14 @@ __global__ void __launch_bounds__(64) dense_alpha_kernel(const float* __restrict
     }
     pr[j] = v;
   }
+  float* prow = pose + (size_t)(tile * kDnFaces + f) * kDnPoseStride;
 #pragma unroll
-  for (int j = 0; j < 12; ++j) pose[(size_t)(tile * kDnFaces + f) * 12 + j] = pr[j];
+  for (int j = 0; j < 12; ++j) prow[j] = pr[j];
+  // crop -> image affine of _predict_vertices (utils/inference.py:127-138): x*kx+sx, y*ky+sy, z*kz (identity if absent)
+  const bool has = roi5 != nullptr && b < batch;
+  prow[12] = has ? roi5[(size_t)b * 5 + 0] : 1.f; prow[13] = has ? roi5[(size_t)b * 5 + 1] : 0.f;
+  prow[14] = has ? roi5[(size_t)b * 5 + 2] : 1.f; prow[15] = has ? roi5[(size_t)b * 5 + 3] : 0.f;
+  prow[16] = has ? roi5[(size_t)b * 5 + 4] : 1.f; prow[17] = prow[18] = prow[19] = 0.f;
   uint8_t* hi = aimg + (size_t)tile * kDnBTile + (f >> 3) * 128 + (f & 7) * 16;
 #pragma unroll
   for (int kg = 0; kg < kDnK / 8; ++kg) {
@@ -79,6 +86,7 @@ struct DenseArgs {
   const float* pose;
   float* out;                 // (B,3,nver)
   int batch, nver, n_vtiles, n_ftiles, transform;
+  int affine;                 // apply the per-face crop -> image affine stored behind the pose rows
   int* err;
 };
 
@@ -146,7 +154,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
 #pragma unroll
       for (int rnd = 0; rnd < 2; ++rnd) {                            // 2 x 16 faces per thread
         const int fofs = half * 32 + rnd * 16;
-        const float* pose = reinterpret_cast<const float*>(sB + sb * kDnBSlot + kDnBTile) + fofs * 12;
+        const float* pose = reinterpret_cast<const float*>(sB + sb * kDnBSlot + kDnBTile) + fofs * kDnPoseStride;
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + grp * 192 + fofs;
         float sx[16], sy[16], sz[16];
         tmem_ld16x3(trow, trow + 64, trow + 128, sx, sy, sz);   // three loads in flight, one wait
@@ -155,14 +163,20 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
 #pragma unroll
           for (int f = 0; f < 16; ++f) {
             if (b0 + f < p.batch) {
-              const float4 r0 = *reinterpret_cast<const float4*>(pose + f * 12);
-              const float4 r1 = *reinterpret_cast<const float4*>(pose + f * 12 + 4);
-              const float4 r2 = *reinterpret_cast<const float4*>(pose + f * 12 + 8);
+              const float4 r0 = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride);
+              const float4 r1 = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride + 4);
+              const float4 r2 = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride + 8);
               const float X = fmaf(sx[f], ox, ux), Y = fmaf(sy[f], oy, uy), Z = fmaf(sz[f], oz, uz);
               float vx = fmaf(r0.x, X, fmaf(r0.y, Y, r0.z * Z)) + r0.w;
               float vy = fmaf(r1.x, X, fmaf(r1.y, Y, r1.z * Z)) + r1.w;
               float vz = fmaf(r2.x, X, fmaf(r2.y, Y, r2.z * Z)) + r2.w;
               if (p.transform) vy = (float)(kImg + 1) - vy;          // model_building.py:129,137
+              if (p.affine) {                                        // utils/inference.py:131-136, numpy's fp32 mul then add
+                const float4 q = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride + 12);
+                vx = __fadd_rn(__fmul_rn(vx, q.x), q.y);
+                vy = __fadd_rn(__fmul_rn(vy, q.z), q.w);
+                vz = __fmul_rn(vz, pose[f * kDnPoseStride + 16]);
+              }
               float* o = p.out + (size_t)(b0 + f) * 3 * p.nver + v;
               __stcs(o, vx); __stcs(o + p.nver, vy); __stcs(o + 2 * (size_t)p.nver, vz);   // write-once stream
             }
@@ -186,7 +200,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
         uint8_t* dst = sB + s * kDnBSlot;
         mbar_expect_tx(smem_u32(&bar_bfull[s]), kDnBSlot);
         bulk_g2s(smem_u32(dst), p.alpha_img + (size_t)ft * kDnBTile, kDnBTile, smem_u32(&bar_bfull[s]));
-        bulk_g2s(smem_u32(dst + kDnBTile), p.pose + (size_t)ft * kDnFaces * 12, kDnPoseTile, smem_u32(&bar_bfull[s]));
+        bulk_g2s(smem_u32(dst + kDnBTile), p.pose + (size_t)ft * kDnFaces * kDnPoseStride, kDnPoseTile, smem_u32(&bar_bfull[s]));
       }
       __syncwarp();
     };
@@ -320,7 +334,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
 #pragma unroll
       for (int rnd = 0; rnd < 2; ++rnd) {                            // 2 x 16 faces per thread
         const int fofs = half * 32 + rnd * 16;
-        const float* pose = reinterpret_cast<const float*>(sB + sb * kDnBSlot + kDnBTile) + fofs * 12;
+        const float* pose = reinterpret_cast<const float*>(sB + sb * kDnBSlot + kDnBTile) + fofs * kDnPoseStride;
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + grp * 192 + fofs;
         float sx[16], sy[16], sz[16];
         tmem_ld16x3(trow, trow + 64, trow + 128, sx, sy, sz);
@@ -329,14 +343,20 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
 #pragma unroll
           for (int f = 0; f < 16; ++f) {
             if (b0 + f < p.batch) {
-              const float4 r0 = *reinterpret_cast<const float4*>(pose + f * 12);
-              const float4 r1 = *reinterpret_cast<const float4*>(pose + f * 12 + 4);
-              const float4 r2 = *reinterpret_cast<const float4*>(pose + f * 12 + 8);
+              const float4 r0 = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride);
+              const float4 r1 = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride + 4);
+              const float4 r2 = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride + 8);
               const float X = fmaf(sx[f], ox, ux), Y = fmaf(sy[f], oy, uy), Z = fmaf(sz[f], oz, uz);
               float vx = fmaf(r0.x, X, fmaf(r0.y, Y, r0.z * Z)) + r0.w;
               float vy = fmaf(r1.x, X, fmaf(r1.y, Y, r1.z * Z)) + r1.w;
               float vz = fmaf(r2.x, X, fmaf(r2.y, Y, r2.z * Z)) + r2.w;
               if (p.transform) vy = (float)(kImg + 1) - vy;          // model_building.py:129,137
+              if (p.affine) {                                        // utils/inference.py:131-136, numpy's fp32 mul then add
+                const float4 q = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride + 12);
+                vx = __fadd_rn(__fmul_rn(vx, q.x), q.y);
+                vy = __fadd_rn(__fmul_rn(vy, q.z), q.w);
+                vz = __fmul_rn(vz, pose[f * kDnPoseStride + 16]);
+              }
               float* o = p.out + (size_t)(b0 + f) * 3 * p.nver + v;
               __stcs(o, vx); __stcs(o + p.nver, vy); __stcs(o + 2 * (size_t)p.nver, vz);
             }
@@ -382,7 +402,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
         uint8_t* dst = sB + s * kDnBSlot;
         mbar_expect_tx(smem_u32(&bar_bfull[s]), kDnBSlot);
         bulk_g2s(smem_u32(dst), p.alpha_img + (size_t)ft * kDnBTile, kDnBTile, smem_u32(&bar_bfull[s]));
-        bulk_g2s(smem_u32(dst + kDnBTile), p.pose + (size_t)ft * kDnFaces * 12, kDnPoseTile, smem_u32(&bar_bfull[s]));
+        bulk_g2s(smem_u32(dst + kDnBTile), p.pose + (size_t)ft * kDnFaces * kDnPoseStride, kDnPoseTile, smem_u32(&bar_bfull[s]));
       }
       __syncwarp();
     };

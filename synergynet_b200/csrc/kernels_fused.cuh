@@ -58,7 +58,7 @@ constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 // SYN_DW3: depthwise items of one channel quad x 2 output rows x 5 output columns on the stride-1 60^2 / 30^2 / 15^2 maps
 // (15.2 shared-memory loads per 16 outputs instead of 26 + conflicted tap loads)
 #ifndef SYN_DW3
-#define SYN_DW3 1
+#define SYN_DW3 0      // measured SLOWER than the 2 x 2 items (2.46 vs 2.32 ms/step): one long item per thread serialises
 #endif
 // output columns of a DW3 item: 3 (76 live registers; 17 warps leave 96 per thread: 5 warps share one sub-partition's
 // 16 K registers) or 5 (fewer loads per output, needs ~105 registers: spills unless the CTA has <= 16 warps)
@@ -193,6 +193,7 @@ struct FusedArgs {
   int face_groups;       // number of face groups (tiles = face_groups * STRIPS)
   int* err;              // sticky time-out flag of the bounded mbarrier waits (mapped pinned host memory)
   int* sat;              // sticky "a block input was clamped to the fp16 range" flag (device memory)
+  int border;            // uint8 stem only: CenterCrop margin, pixels of the frame read as 0 (utils/ddfa.py:162-243); 0 = off
   int npass;             // 3 = split-fp16 x3 (hi*hi + hi*lo + lo*hi); 1 = single fp16 pass (SYN_ENGINE_TC_FUSED_1PASS)
 #ifdef SYN_FUSED_TRACE
   int trace_id;          // backbone block of this launch (1..17)
@@ -210,6 +211,18 @@ __device__ long long g_fused_trace[18 * 2 * 64 * 8];
 #else
 #define SYN_TRACE(role, chunk, ev) do { } while (0)
 #endif
+
+// Named barrier of a worker group with an IMMEDIATE id: with a register id ptxas reserves all 16 hardware barriers for
+// the CTA, and a second CTA cannot become resident on the SM (measured: occupancy 1 for the SYN_OCC2 shapes).
+template <int THREADS>
+__device__ __forceinline__ void group_bar_sync(int grp) {
+  switch (grp) {
+    case 0: asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;" ::"n"(THREADS) : "memory"); break;
+    case 2: asm volatile("bar.sync 3, %0;" ::"n"(THREADS) : "memory"); break;
+    default: asm volatile("bar.sync 4, %0;" ::"n"(THREADS) : "memory"); break;
+  }
+}
 
 // NWW = worker warps (multiple of 4: TMEM lane quarter = warp % 4); the issuer is warp NWW.
 template <class C, int NWW>
@@ -319,7 +332,15 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
             const int iy = iy_first + r;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (iy >= 0 && iy < kImg) {
-              const uchar4 u = *reinterpret_cast<const uchar4*>(p.x_u8 + ((size_t)(f0 * 3 + ci) * kImg + iy) * kImg + c4 * 4);
+              uchar4 u = *reinterpret_cast<const uchar4*>(p.x_u8 + ((size_t)(f0 * 3 + ci) * kImg + iy) * kImg + c4 * 4);
+              if (p.border > 0) {                                   // zero frame of the reference loader, before normalisation
+                const int col = c4 * 4;
+                const bool row_out = iy < p.border || iy >= kImg - p.border;
+                if (row_out || col < p.border || col >= kImg - p.border) u.x = 0;
+                if (row_out || col + 1 < p.border || col + 1 >= kImg - p.border) u.y = 0;
+                if (row_out || col + 2 < p.border || col + 2 >= kImg - p.border) u.z = 0;
+                if (row_out || col + 3 < p.border || col + 3 >= kImg - p.border) u.w = 0;
+              }
               v = make_float4(((float)u.x - 127.5f) / 128.0f, ((float)u.y - 127.5f) / 128.0f,
                               ((float)u.z - 127.5f) / 128.0f, ((float)u.w - 127.5f) / 128.0f);
             }
@@ -485,7 +506,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
         ++n_d1;
         tc_fence_after_sync();
         SYN_TRACE(0, c, 1);
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(TPG) : "memory");   // the group is done reading ITS Hs columns (DW c-1)
+        group_bar_sync<TPG>(grp);   // the group is done reading ITS Hs columns (DW c-1)
         SYN_TRACE(0, c, 2);
         if (c == 0) {
           // ---- strip mode: window rows outside the image must read as zero (may hold a previous tile);
@@ -553,7 +574,7 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
         SYN_TRACE(0, c, 3);
         tc_fence_before_sync();
         mbar_arrive(smem_u32(&bar_epi1));
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(TPG) : "memory");   // the group's channel columns of the window are complete
+        group_bar_sync<TPG>(grp);   // the group's channel columns of the window are complete
         // ---- DW: 3x3 depthwise on the window -> A2 operand ----------------------------------------
         if (c > 0) {                                        // A2 is free once GEMM2(c-1) has completed
           mbar_wait(smem_u32(&bar_g2), n_g2 & 1, p.err);

@@ -16,12 +16,68 @@ namespace syn {
 // uint8 crop -> fp32, `(img - 127.5) / 128` (synergy3DMM.py:192); used by the engines whose stem reads fp32.
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) normalize_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out,
-                                                           size_t n4) {
+                                                           size_t n4, int border) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
-  const uchar4 u = reinterpret_cast<const uchar4*>(in)[i];
+  uchar4 u = reinterpret_cast<const uchar4*>(in)[i];
+  if (border > 0) {            // CenterCrop(border, mode='test') of the reference loader (utils/ddfa.py:162-243): zero frame
+    const int col = (int)(i % (kImg / 4)) * 4, iy = (int)((i / (kImg / 4)) % kImg);
+    const bool row_out = iy < border || iy >= kImg - border;
+    if (row_out || col < border || col >= kImg - border) u.x = 0;
+    if (row_out || col + 1 < border || col + 1 >= kImg - border) u.y = 0;
+    if (row_out || col + 2 < border || col + 2 >= kImg - border) u.z = 0;
+    if (row_out || col + 3 < border || col + 3 >= kImg - border) u.w = 0;
+  }
   reinterpret_cast<float4*>(out)[i] = make_float4(((float)u.x - 127.5f) / 128.0f, ((float)u.y - 127.5f) / 128.0f,
                                                    ((float)u.z - 127.5f) / 128.0f, ((float)u.w - 127.5f) / 128.0f);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Pose decode, batched: parse_pose + predict_pose of the reference (utils/inference.py:33-62,86-92,146-157).
+//   P = (param * std + mean)[:12].reshape(3,4);  r1, r2 = rows / |rows| (fp32, like numpy);  r3 = r1 x r2;
+//   angles (degrees, fp64 like Python's math.asin / atan2 on the fp32 matrix), t3d = P[:,3] moved to image
+//   coordinates when a crop box is given: t3d[0] * (ex-sx)/120 + sx, t3d[1] * (ey-sy)/120 + sy.
+// roi rows hold the five fp32 numbers the host derived in double like numpy's scalar handling:
+//   kx = (ex-sx)/120, sx, ky = (ey-sy)/120, sy, kz = (kx+ky)/2.
+// -------------------------------------------------------------------------------------------------
+__global__ void pose_decode_kernel(const float* __restrict__ params, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                   const float* __restrict__ roi, double* __restrict__ angles, float* __restrict__ t3d, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  float P[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) P[j] = __fadd_rn(__fmul_rn(params[(size_t)b * kNumParams + j], stdv[j]), mean[j]);
+  // numpy: norm = sqrt(sum of squares) in fp32, sequential for three elements; no fused multiply-adds
+  const float n1 = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(P[0], P[0]), __fmul_rn(P[1], P[1])), __fmul_rn(P[2], P[2])));
+  const float n2 = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(P[4], P[4]), __fmul_rn(P[5], P[5])), __fmul_rn(P[6], P[6])));
+  const float r1[3] = {__fdiv_rn(P[0], n1), __fdiv_rn(P[1], n1), __fdiv_rn(P[2], n1)};
+  const float r2[3] = {__fdiv_rn(P[4], n2), __fdiv_rn(P[5], n2), __fdiv_rn(P[6], n2)};
+  // np.cross(r1, r2) row: (a1*b2 - a2*b1, a2*b0 - a0*b2, a0*b1 - a1*b0), each product rounded
+  const float r3[3] = {__fsub_rn(__fmul_rn(r1[1], r2[2]), __fmul_rn(r1[2], r2[1])),
+                       __fsub_rn(__fmul_rn(r1[2], r2[0]), __fmul_rn(r1[0], r2[2])),
+                       __fsub_rn(__fmul_rn(r1[0], r2[1]), __fmul_rn(r1[1], r2[0]))};
+  const double R00 = r1[0], R01 = r1[1], R02 = r1[2], R12 = r2[2], R20 = r3[0], R22 = r3[2];
+  const double kPi = 3.14159265358979323846;
+  double x, y, z;
+  if (R20 != 1.0 && R20 != -1.0) {                           // matrix2angle_corr, utils/inference.py:45-62
+    x = asin(R20);
+    y = atan2(R12 / cos(x), R22 / cos(x));
+    z = atan2(R01 / cos(x), R00 / cos(x));
+  } else {                                                   // gimbal lock
+    z = 0.0;
+    if (R20 == -1.0) { x = kPi / 2; y = z + atan2(R01, R02); }
+    else { x = -kPi / 2; y = -z + atan2(-R01, -R02); }
+  }
+  angles[(size_t)b * 3 + 0] = x * 180 / kPi;
+  angles[(size_t)b * 3 + 1] = y * 180 / kPi;
+  angles[(size_t)b * 3 + 2] = z * 180 / kPi;
+  float t0 = P[3], t1 = P[7];
+  if (roi != nullptr) {
+    const float* r = roi + (size_t)b * 5;
+    t0 = __fadd_rn(__fmul_rn(t0, r[0]), r[1]);
+    t1 = __fadd_rn(__fmul_rn(t1, r[2]), r[3]);
+  }
+  t3d[(size_t)b * 3 + 0] = t0; t3d[(size_t)b * 3 + 1] = t1; t3d[(size_t)b * 3 + 2] = P[11];
 }
 
 // -------------------------------------------------------------------------------------------------

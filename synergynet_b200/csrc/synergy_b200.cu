@@ -16,6 +16,7 @@
 #include "kernels_dense.cuh"
 #include "kernels_gemm.cuh"
 #include "kernels_loss.cuh"
+#include "kernels_resnet.cuh"
 
 using namespace syn;
 
@@ -36,12 +37,16 @@ struct DevConv {
 
 struct syn_heads;       // PointNet refinement heads (heads_host.inl)
 void syn_heads_destroy(syn_heads* s);
+struct syn_resnet;      // ResNet-50 backbone variant (resnet_host.inl)
+void syn_resnet_destroy(syn_resnet* s);
 
 struct syn_handle {
   int device = 0;
   syn_heads* heads = nullptr;
+  syn_resnet* resnet = nullptr;
   int sm_count = 0;
   int engine = SYN_ENGINE_TC_FUSED;            // default: fused tcgen05 engine; 0/1 remain for cross-checks
+  int center_crop = 0;                         // CenterCrop margin applied by the uint8 entry points (syn_set_center_crop)
   int npass() const { return engine == SYN_ENGINE_TC_FUSED_1PASS ? 1 : 3; }
   bool fused() const { return engine == SYN_ENGINE_TC_FUSED || engine == SYN_ENGINE_TC_FUSED_1PASS; }
   bool committed = false;
@@ -233,7 +238,7 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
       h->x_f32_batch = batch;
     }
     const size_t n4 = (size_t)batch * 3 * kImg * kImg / 4;
-    normalize_u8_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x_u8, h->d_x_f32, n4);
+    normalize_u8_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x_u8, h->d_x_f32, n4, h->center_crop);
     SYN_LAUNCH_CHECK("normalize_u8_kernel");
     mark(h, st, "normalize_u8_kernel");
     x = h->d_x_f32;
@@ -336,7 +341,7 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
 }
 
 int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense, int whitening, int transform,
-                       float* out, cudaStream_t st) {
+                       float* out, cudaStream_t st, const float* roi5 = nullptr) {
   const int n_ftiles = (batch + kDnFaces - 1) / kDnFaces;
   if (n_ftiles > h->recon_ftiles) {
     SYN_CUDA(cudaDeviceSynchronize());
@@ -347,7 +352,7 @@ int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense,
     h->recon_ftiles = n_ftiles;
   }
   dense_alpha_kernel<<<n_ftiles, 64, 0, st>>>(params, h->d_mean, h->d_std, h->d_ascale, h->d_alpha_img, h->d_pose, batch,
-                                             whitening);
+                                             whitening, roi5);
   SYN_LAUNCH_CHECK("dense_alpha_kernel");
   mark(h, st, "dense_alpha_kernel");
   DenseArgs a;
@@ -356,7 +361,7 @@ int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense,
   a.alpha_img = h->d_alpha_img; a.pose = h->d_pose; a.out = out; a.batch = batch;
   a.nver = dense ? (int)h->n_vert : h->n_pts;
   a.n_vtiles = dense ? h->dn_vtiles : h->sp_vtiles;
-  a.n_ftiles = n_ftiles; a.transform = transform; a.err = h->d_err;
+  a.n_ftiles = n_ftiles; a.transform = transform; a.affine = roi5 != nullptr; a.err = h->d_err;
   const int items = a.n_vtiles * a.n_ftiles;
   // dense mesh: face-major walk with streamed basis planes (long contiguous output runs per CTA); the 68-landmark
   // basis is one vertex tile, where the two kernels do the same work -- keep the simpler one there.
@@ -374,10 +379,11 @@ int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense,
 }
 
 int run_reconstruct(syn_handle* h, const float* params, int batch, int dense, int whitening,
-                    int transform, float* out, cudaStream_t st) {
+                    int transform, float* out, cudaStream_t st, const float* roi5 = nullptr) {
   if (dense && h->d_dense == nullptr) return fail(SYN_ERR_STATE, "dense basis not set (syn_set_basis_dense)");
   if (!dense && h->d_sparse == nullptr) return fail(SYN_ERR_STATE, "sparse basis not set (syn_set_basis_sparse)");
-  if (h->engine != SYN_ENGINE_SIMT_FP32) return run_reconstruct_tc(h, params, batch, dense, whitening, transform, out, st);
+  if (h->engine != SYN_ENGINE_SIMT_FP32 || roi5 != nullptr)     // the image-space variant exists on the tensor-core kernels only
+    return run_reconstruct_tc(h, params, batch, dense, whitening, transform, out, st, roi5);
   if (dense) {
     constexpr int F = 16;
     dim3 grid((unsigned)(h->dn_pad / 128), (batch + F - 1) / F);
@@ -539,7 +545,7 @@ template <class C>
 int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, cudaStream_t st, const uint8_t* x_u8) {
   FusedArgs a;
   a.x_u8 = x_u8;
-  a.x = x; a.wimg = h->d_fused + h->fused_off[block]; a.y = y; a.batch = batch; a.err = h->d_err; a.sat = h->d_sat; a.npass = h->npass();
+  a.x = x; a.wimg = h->d_fused + h->fused_off[block]; a.y = y; a.batch = batch; a.err = h->d_err; a.sat = h->d_sat; a.npass = h->npass(); a.border = h->center_crop;
 #ifdef SYN_FUSED_TRACE
   a.trace_id = block;
 #endif
@@ -675,6 +681,7 @@ void syn_destroy(syn_handle_t* h) {
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   syn_heads_destroy(h->heads);
+  syn_resnet_destroy(h->resnet);
   cudaFree(h->d_weights); cudaFree(h->d_head_w); cudaFree(h->d_head_b); cudaFree(h->d_mean);
   cudaFree(h->d_std); cudaFree(h->d_sparse); cudaFree(h->d_dense); cudaFree(h->d_tcw); cudaFreeHost(h->d_err); cudaFree(h->d_sat); cudaFree(h->d_fused); cudaFree(h->d_tc_oscale);
   cudaFree(h->buf_io[0]); cudaFree(h->buf_io[1]); cudaFree(h->buf_hid); cudaFree(h->buf_dw);
@@ -968,6 +975,16 @@ int syn_reconstruct(syn_handle_t* h, const float* params, int batch, int dense, 
   return run_reconstruct(h, params, batch, dense, whitening, transform, out, (cudaStream_t)stream);
 }
 
+int syn_reconstruct_image(syn_handle_t* h, const float* params, int batch, int dense, const float* roi5_dev, float* out,
+                          void* stream) {
+  SYN_CHECK_READY(h, "syn_reconstruct_image");
+  if (params == nullptr || out == nullptr || roi5_dev == nullptr || batch <= 0)
+    return fail(SYN_ERR_INVALID, "syn_reconstruct_image: bad argument");
+  DeviceGuard g(h->device);
+  if (h->timing) { mark(h, (cudaStream_t)stream, "start"); h->launches--; }
+  return run_reconstruct(h, params, batch, dense, 1, 1, out, (cudaStream_t)stream, roi5_dev);
+}
+
 int syn_forward_landmarks(syn_handle_t* h, const float* x, int batch, float* params, float* lmk,
                           void* stream) {
   SYN_CHECK_READY(h, "syn_forward_landmarks");
@@ -1095,6 +1112,26 @@ int syn_forward_landmarks_host_u8(syn_handle_t* h, const uint8_t* x_host, int ba
   return forward_landmarks_host_impl(h, x_host, 1, batch, params_host, lmk_host);
 }
 
+int syn_set_center_crop(syn_handle_t* h, int margin) {
+  if (h == nullptr || margin < 0 || margin >= kImg / 2) return fail(SYN_ERR_INVALID, "syn_set_center_crop: margin must be in [0, 60)");
+  h->center_crop = margin;
+  return SYN_OK;
+}
+
+int syn_pose_decode(syn_handle_t* h, const float* params62_dev, int batch, const float* roi5_dev, double* angles_dev,
+                    float* t3d_dev, void* stream) {
+  SYN_CHECK_READY(h, "syn_pose_decode");
+  if (params62_dev == nullptr || angles_dev == nullptr || t3d_dev == nullptr || batch <= 0)
+    return fail(SYN_ERR_INVALID, "syn_pose_decode: bad argument");
+  if (h->d_mean == nullptr) return fail(SYN_ERR_STATE, "syn_pose_decode: whitening not set");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  pose_decode_kernel<<<(batch + 127) / 128, 128, 0, st>>>(params62_dev, h->d_mean, h->d_std, roi5_dev, angles_dev, t3d_dev, batch);
+  SYN_LAUNCH_CHECK("pose_decode_kernel");
+  mark(h, st, "pose_decode_kernel");
+  return SYN_OK;
+}
+
 int syn_peek_error(const syn_handle_t* h, int* flag_out) {
   if (h == nullptr || flag_out == nullptr) return fail(SYN_ERR_INVALID, "syn_peek_error: null argument");
   *flag_out = h->d_err != nullptr ? *reinterpret_cast<volatile int*>(h->d_err) : 0;
@@ -1179,3 +1216,4 @@ int syn_debug_forward_until(syn_handle_t* h, const float* x, int batch, int laye
 }  // extern "C"
 
 #include "heads_host.inl"
+#include "resnet_host.inl"

@@ -128,11 +128,15 @@ class Engine:
         """Current torch stream of the engine's device; if the previous call ran on another stream, that
         stream's work is ordered before this call (the workspace buffers are shared)."""
         st = torch.cuda.current_stream(self.device)
+        if torch.cuda.is_current_stream_capturing():
+            return st.cuda_stream            # CUDA-graph capture: no cross-stream events (they would join the graph)
         if self._last_stream is not None and self._last_stream != st.cuda_stream and self._last_event is not None:
             st.wait_event(self._last_event)
         return st.cuda_stream
 
     def _done(self) -> None:
+        if torch.cuda.is_current_stream_capturing():
+            return
         st = torch.cuda.current_stream(self.device)
         if self._last_event is None:
             self._last_event = torch.cuda.Event()
@@ -190,6 +194,47 @@ class Engine:
                                                  int(transform), out.data_ptr(), self._stream()))
             self._done()
         return out
+
+    def reconstruct_image(self, params: torch.Tensor, roi5: torch.Tensor, dense: bool = False) -> torch.Tensor:
+        """reconstruct_vertex_62 + the crop -> image affine of _predict_vertices (utils/inference.py:127-138) in one
+        kernel: (B,3,N) vertices in the coordinates of the original image.  ``roi5`` (B,5) fp32 = kx, sx, ky, sy, kz
+        (``inference.roi_affine``)."""
+        params, roi5 = self._dev_f32(params), self._dev_f32(roi5)
+        b = params.shape[0]
+        if params.dim() != 2 or params.shape[1] != N_PARAMS:
+            raise RuntimeError('length of params mismatch')
+        if tuple(roi5.shape) != (b, 5):
+            raise RuntimeError(f'roi5 must be (B,5), got {tuple(roi5.shape)}')
+        n = self.n_vert if dense else self.n_pts
+        if n == 0:
+            raise RuntimeError('dense basis not loaded' if dense else 'sparse basis not loaded')
+        out = torch.empty((b, 3, n), device=self.device, dtype=torch.float32)
+        with self._lock:
+            _lib.check(self._lib.syn_reconstruct_image(self._h, params.data_ptr(), b, int(dense), roi5.data_ptr(), out.data_ptr(),
+                                                       self._stream()))
+            self._done()
+        return out
+
+    def pose_decode(self, params: torch.Tensor, roi5: Optional[torch.Tensor] = None):
+        """Batched parse_pose + predict_pose (utils/inference.py:33-62,86-92,146-157): (angles (B,3) float64 degrees,
+        t3d (B,3) float32 -- in image coordinates when ``roi5`` is given)."""
+        params = self._dev_f32(params)
+        b = params.shape[0]
+        if roi5 is not None:
+            roi5 = self._dev_f32(roi5)
+            if tuple(roi5.shape) != (b, 5):
+                raise RuntimeError(f'roi5 must be (B,5), got {tuple(roi5.shape)}')
+        ang = torch.empty((b, 3), device=self.device, dtype=torch.float64)
+        t3d = torch.empty((b, 3), device=self.device, dtype=torch.float32)
+        with self._lock:
+            _lib.check(self._lib.syn_pose_decode(self._h, params.data_ptr(), b, roi5.data_ptr() if roi5 is not None else None,
+                                                 ang.data_ptr(), t3d.data_ptr(), self._stream()))
+            self._done()
+        return ang, t3d
+
+    def set_center_crop(self, margin: int) -> None:
+        """CenterCrop(margin, mode='test') of the reference loader for the uint8 entry points (0 = off)."""
+        _lib.check(self._lib.syn_set_center_crop(self._h, int(margin)))
 
     def forward_landmarks(self, x: torch.Tensor, want_params: bool = False):
         """x: fp32 normalised crops, or raw uint8 crops (normalised on the device)."""
@@ -312,6 +357,33 @@ class Engine:
                                                 0 if mode == 'normal' else 1, out.data_ptr(), self._stream()))
             self._done()
         return out
+
+    # ---- ResNet-50 backbone variant (BASELINE.json configs[4]) ---------------------------------------------------
+    def load_resnet50(self, sd: Dict[str, torch.Tensor], prefix: str = '') -> None:
+        """Hand a ``resnet_backbone.resnet50()`` state dict to the library (53 conv+BN pairs in execution order, the four
+        Linear heads concatenated in the reference's output order ori | shape | exp | tex, resnet_backbone.py:242-246)."""
+        from .backbone import resnet50_conv_keys
+        with self._lock:
+            for i, (ck, bk) in enumerate(resnet50_conv_keys()):
+                w = _host_f32(sd[f'{prefix}{ck}.weight'])
+                bn = [_host_f32(sd[f'{prefix}{bk}.{k}']) for k in ('weight', 'bias', 'running_mean', 'running_var')]
+                _lib.check(self._lib.syn_resnet_set_conv(self._h, i, w.data_ptr(), w.numel(), *[t.data_ptr() for t in bn], 1e-5))
+            order = ('fc_ori', 'fc_shape', 'fc_exp', 'fc_tex')
+            w = torch.cat([_host_f32(sd[f'{prefix}{k}.weight']) for k in order]).contiguous()
+            b = torch.cat([_host_f32(sd[f'{prefix}{k}.bias']) for k in order]).contiguous()
+            _lib.check(self._lib.syn_resnet_set_heads(self._h, w.data_ptr(), b.data_ptr()))
+            _lib.check(self._lib.syn_resnet_commit(self._h))
+
+    def forward_resnet50(self, x: torch.Tensor):
+        """ResNet._forward_impl (resnet_backbone.py:227-249): (B,3,120,120) -> ((B,102) ori|shape|exp|tex, (B,2048) pooled)."""
+        x = self._check_x(x)
+        b = x.shape[0]
+        out = torch.empty((b, 102), device=self.device, dtype=torch.float32)
+        pool = torch.empty((b, 2048), device=self.device, dtype=torch.float32)
+        with self._lock:
+            _lib.check(self._lib.syn_resnet50_forward(self._h, x.data_ptr(), b, out.data_ptr(), pool.data_ptr(), self._stream()))
+            self._done()
+        return out, pool
 
     def debug_forward_until(self, x: torch.Tensor, layer: int) -> torch.Tensor:
         x = self._check_x(x)

@@ -54,6 +54,19 @@ def rescale_vertices(vertex: np.ndarray, roi_box: Sequence[float]) -> np.ndarray
     return out
 
 
+def roi_affine(roi_boxes: Sequence[Sequence[float]]) -> np.ndarray:
+    """(B,5) fp32 rows kx, sx, ky, sy, kz of the crop -> image map of ``_predict_vertices`` / ``predict_pose``
+    (utils/inference.py:129-136,150-154).  The reference evaluates the scales as Python floats (double) and numpy
+    rounds them to fp32 when they meet the fp32 vertex arrays; the same happens here, once per face, as index-like host
+    work -- the per-vertex arithmetic runs on the GPU (``Engine.reconstruct_image``)."""
+    out = np.empty((len(roi_boxes), 5), np.float32)
+    for i, box in enumerate(roi_boxes):
+        sx, sy, ex, ey = box[:4]
+        kx, ky = (ex - sx) / STD_SIZE, (ey - sy) / STD_SIZE
+        out[i] = (kx, sx, ky, sy, (kx + ky) / 2)
+    return out
+
+
 def decompose_camera(P: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Batched P2sRt (utils/inference.py:33-43): P (B,3,4) -> scale (B,), R (B,3,3), t (B,3)."""
     r1, r2 = P[:, 0, :3], P[:, 1, :3]

@@ -18,7 +18,7 @@ import torch.nn as nn
 from . import backbone as mobilenetv2_backbone
 from .backbone import MLP_for, MLP_rev
 from .engine import Engine
-from .inference import crop_img, predict_pose_batch, rescale_vertices, square_roi
+from .inference import crop_img, roi_affine, square_roi
 from .params import ParamsPack, get_param_pack, set_param_pack  # noqa: F401  (re-exported)
 
 _LOSS_KEYS = ('loss_LMK_f0', 'loss_LMK_pointNet', 'loss_Param_In', 'loss_Param_S2', 'loss_Param_S1S2')
@@ -96,11 +96,18 @@ class I2P(nn.Module):
         self.args = args
         if 'mobilenet_v2' in self.args.arch:
             self.backbone = getattr(mobilenetv2_backbone, args.arch)(pretrained=False)
+        elif self.args.arch == 'resnet50':
+            # BASELINE.json configs[4].  The reference's own I2P cannot run this backbone: ResNet._forward_impl returns
+            # ONE (B,102) tensor (resnet_backbone.py:242-249) and I2P unpacks two (model_building.py:55,61; SURVEY.md
+            # fact 4).  Adapter used here (and by the oracle / golden vectors): params = out[:, :62] (ori|shape|exp),
+            # avgpool = the 2048-d pooled feature.
+            self.backbone = mobilenetv2_backbone.resnet50(pretrained=False)
         elif any(k in self.args.arch for k in ('mobilenet', 'resnet', 'ghostnet', 'resnest')):
-            raise RuntimeError(f"arch '{args.arch}': only mobilenet_v2 is built for sm_100a in this "
-                               'round (SURVEY.md section 8; the other backbones are not on the hot path)')
+            raise RuntimeError(f"arch '{args.arch}': mobilenet_v2 and resnet50 are built for sm_100a "
+                               '(SURVEY.md section 8; the other backbones are not on the hot path)')
         else:
             raise RuntimeError("Please choose [mobilenet_v2, mobilenet_1, resnet50, or ghostnet]")
+        self._is_resnet = self.args.arch == 'resnet50'
         object.__setattr__(self, '_rt', _Runtime())
         object.__setattr__(self, '_basis_provider', None)
 
@@ -109,7 +116,27 @@ class I2P(nn.Module):
                 if not k.endswith('num_batches_tracked')}
 
     def _engine(self, device) -> Engine:
+        if self._is_resnet:
+            return self._resnet_engine(device)
         return self._rt.get(device, self._backbone_sd, self._basis_provider)
+
+    def _resnet_engine(self, device) -> Engine:
+        """Engine with the ResNet-50 weights: the shared library state (error flag, 3DMM bases for reconstruct) comes from
+        a commit of the MobileNetV2 path with a zero checkpoint of the right schema, then the ResNet layers are handed over."""
+        rt = self._rt
+        if not hasattr(rt, '_mbv2_stub'):
+            rt._mbv2_stub = {k: v for k, v in mobilenetv2_backbone.mobilenet_v2().state_dict().items()
+                             if not k.endswith('num_batches_tracked')}
+        eng = rt.get(device, lambda: rt._mbv2_stub, self._basis_provider)
+        sd = self._backbone_sd()
+        sig = rt._signature(list(sd.values()))
+        key = (eng.device.index, 'resnet50')
+        with rt._lock:
+            if rt._pn_sig.get(key) != sig or getattr(eng, '_resnet_commit_of', None) is not rt._sig.get(eng.device.index):
+                eng.load_resnet50(sd)
+                rt._pn_sig[key] = sig
+                eng._resnet_commit_of = rt._sig.get(eng.device.index)
+        return eng
 
     def _compute_device(self, t: Optional[torch.Tensor] = None) -> torch.device:
         """Where the library runs for tensor ``t``: its own GPU, else the GPU the backbone lives on, else the current
@@ -127,7 +154,11 @@ class I2P(nn.Module):
         """Testing time forward -> (param62, avgpool1280) (model_building.py:59-62).  A CPU input is moved to the
         compute GPU and the results come back on the CPU, as the reference's CPU model would return them."""
         dev = self._compute_device(input)
-        params, pool = self._engine(dev).forward(input.to(dev), want_pool=True)
+        if self._is_resnet:
+            out, pool = self._engine(dev).forward_resnet50(input.to(dev))
+            params = out[:, :62].contiguous()
+        else:
+            params, pool = self._engine(dev).forward(input.to(dev), want_pool=True)
         if not input.is_cuda:
             params, pool = params.to(input.device), pool.to(input.device)
         return params, pool
@@ -210,12 +241,16 @@ class _SynergyBase(nn.Module):
 
     def forward_test(self, input):
         """test time forward (model_building.py:159-162): whitened (B,62) parameters (on the input's device)."""
+        if self.I2P._is_resnet:
+            return self.I2P.forward_test(input)[0]
         dev = self._compute_device(input)
         out = self._engine(dev).forward(input.to(dev))
         return out if input.is_cuda else out.to(input.device)
 
     def forward_landmarks(self, input):
         """forward_test + reconstruct_vertex_62(dense=False) in one library call."""
+        if self.I2P._is_resnet:
+            return self.reconstruct_vertex_62(self.forward_test(input))
         dev = self._compute_device(input)
         out = self._engine(dev).forward_landmarks(input.to(dev))
         return out if input.is_cuda else out.to(input.device)
@@ -233,7 +268,12 @@ class _SynergyBase(nn.Module):
         tensors are kept in ``self.last_forward`` for inspection."""
         dev = self._compute_device(input)
         eng = self._engine(dev)
-        _3D_attr, avgpool = eng.forward(input.to(dev), want_pool=True)
+        _3D_attr, avgpool = self.I2P.forward_test(input.to(dev))
+        if avgpool.shape[1] != 1280:
+            raise RuntimeError('SynergyNet.forward: MLP_for.conv6 is hard-wired to a 1280-d image feature '
+                               '(pointnet_backbone.py:15,58: 2418 = 64 + 1024 + 1280 + 40 + 10); the resnet50 backbone pools '
+                               f'{avgpool.shape[1]} channels, so the refinement head cannot follow it (the reference fails '
+                               'here too, SURVEY.md fact 4).  Use forward_test() / reconstruct_vertex_62() with resnet50.')
         _3D_attr_GT = target.to(device=dev, dtype=torch.float32)
         vertex_lmk = eng.reconstruct(_3D_attr, dense=False)
         vertex_GT_lmk = eng.reconstruct(_3D_attr_GT, dense=False)
@@ -277,19 +317,21 @@ class _SynergyBase(nn.Module):
         if not boxes:
             return [], [], []
         interp = cv2.INTER_LANCZOS4 if self.resize_interpolation == 'lanczos4' else cv2.INTER_LINEAR
-        crops = [cv2.resize(crop_img(input, b), dsize=(120, 120), interpolation=interp) for b in boxes]
-        batch = torch.from_numpy(np.stack(crops)).permute(0, 3, 1, 2).float()
-        batch = ((batch - 127.5) / 128.0).contiguous()
+        # integer ROI crop + cv2 resize stay on the host (bit-exact index work / OpenCV's fixed-point Lanczos); everything
+        # after it is batched on the GPU: uint8 -> (v-127.5)/128, backbone, both reconstructions already mapped to image
+        # coordinates, pose decode.  One H2D of the uint8 crops, one D2H per output, no per-face arithmetic in Python.
+        crops = np.stack([cv2.resize(crop_img(input, b), dsize=(120, 120), interpolation=interp) for b in boxes])
         dev = self._compute_device()
         eng = self._engine(dev)
-        params = eng.forward(batch.to(dev))
-        lmk = eng.reconstruct(params, dense=False).cpu().numpy()
-        mesh = eng.reconstruct(params, dense=True).cpu().numpy()
-        p_np = params.cpu().numpy().astype(np.float32)
-        poses = predict_pose_batch(p_np, self.param_mean.cpu().numpy(), self.param_std.cpu().numpy(), boxes)
-        pts = [rescale_vertices(lmk[i], boxes[i]) for i in range(len(boxes))]
-        verts = [rescale_vertices(mesh[i], boxes[i]) for i in range(len(boxes))]
-        return pts, verts, poses
+        batch = torch.from_numpy(crops).permute(0, 3, 1, 2).contiguous().to(dev)                 # uint8 (B,3,120,120)
+        _, params = eng.forward_landmarks(batch, want_params=True)
+        roi5 = torch.from_numpy(roi_affine(boxes)).to(dev)
+        lmk = eng.reconstruct_image(params, roi5, dense=False).cpu().numpy()
+        mesh = eng.reconstruct_image(params, roi5, dense=True).cpu().numpy()
+        ang, t3d = eng.pose_decode(params, roi5)
+        ang, t3d = ang.cpu().numpy(), t3d.cpu().numpy()
+        eng.raise_if_error()
+        return list(lmk), list(mesh), [[ang[i].tolist(), t3d[i]] for i in range(len(boxes))]
 
 
 class SynergyNet(_SynergyBase):

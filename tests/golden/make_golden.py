@@ -99,6 +99,46 @@ def main():
         out[f'feat{i:02d}_sub'] = f[0, :, ::FEAT_STRIDE, ::FEAT_STRIDE].numpy()
         out[f'feat{i:02d}_absmean'] = np.float64(f.abs().double().mean().item())
 
+    # ---- training-time forward (model_building.py:141-157) through the reference's own modules -------------
+    # model_building.SynergyNet needs CUDA at construction; synergy3DMM.SynergyNet owns the same sub-modules
+    # (I2P, forwardDirection, reverseDirection, LMKLoss_3D, ParamLoss), so the statements of forward() are executed
+    # on them one by one (I2P.forward's `.type(torch.cuda.FloatTensor)` becomes `.float()`), eval-mode BatchNorm.
+    g = torch.Generator().manual_seed(3)
+    target = params + 0.3 * torch.randn(params.shape, generator=g)
+    with torch.no_grad():
+        _3D_attr, avgpool = ref.I2P.backbone(x)
+        _3D_attr_GT = target.float()
+        vertex_lmk = ref.reconstruct_vertex_62(_3D_attr, dense=False)
+        vertex_GT_lmk = ref.reconstruct_vertex_62(_3D_attr_GT, dense=False)
+        fwd = {'loss_LMK_f0': 0.05 * ref.LMKLoss_3D(vertex_lmk, vertex_GT_lmk, kp=True),
+               'loss_Param_In': 0.02 * ref.ParamLoss(_3D_attr, _3D_attr_GT)}
+        point_residual = ref.forwardDirection(vertex_lmk, avgpool, _3D_attr[:, 12:52], _3D_attr[:, 52:62])
+        vertex_lmk_ref = vertex_lmk + 0.05 * point_residual
+        fwd['loss_LMK_pointNet'] = 0.05 * ref.LMKLoss_3D(vertex_lmk_ref, vertex_GT_lmk, kp=True)
+        _3D_attr_S2 = ref.reverseDirection(vertex_lmk_ref)
+        fwd['loss_Param_S2'] = 0.02 * ref.ParamLoss(_3D_attr_S2, _3D_attr_GT, mode='only_3dmm')
+        fwd['loss_Param_S1S2'] = 0.001 * ref.ParamLoss(_3D_attr_S2, _3D_attr, mode='only_3dmm')
+    out['fwd_target'] = target.numpy()
+    for k, v in fwd.items():
+        out['fwd_' + k] = v.numpy()
+    out['fwd_point_residual'] = point_residual.numpy()
+    out['fwd_vertex_lmk_refined'] = vertex_lmk_ref.numpy()
+    out['fwd_3D_attr_S2'] = _3D_attr_S2.numpy()
+    assert float(point_residual.abs().max()) > 0.1 and float((_3D_attr_S2 != 0).float().mean()) > 0.2, 'dead PointNet heads'
+
+    # ---- ResNet-50 backbone variant (BASELINE.json configs[4]): the reference module itself ------------------
+    from backbone_nets import resnet_backbone as ref_resnet
+    rn = ref_resnet.resnet50(pretrained=False)
+    rn_sd = synth_model.build_resnet50_state_dict(0)
+    res = rn.load_state_dict(rn_sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    rn.eval()
+    with torch.no_grad():
+        rn_out = rn(x[:4])                                  # (4,102) = ori | shape | exp | tex (resnet_backbone.py:242-246)
+        lmk_rn = ref.reconstruct_vertex_62(rn_out[:, :62].contiguous(), dense=False)   # the adapter: first 62 = ori|shape|exp
+    out['resnet50_out102'] = rn_out.numpy()
+    out['resnet50_lmk'] = lmk_rn.numpy()
+
     # ---- numpy per-face path (utils/inference.py) and crop_img ------------------------------------
     p0 = params[0].numpy().astype(np.float32)
     roi = [30.2, 41.7, 211.4, 222.9, 0.99]

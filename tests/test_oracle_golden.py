@@ -94,3 +94,25 @@ def test_per_face_numpy_api(gold, basis):
 def test_crop_img_bit_exact(gold):
     for i, box in enumerate(gold['crop_boxes']):
         assert np.array_equal(rp.crop_img(gold['crop_img'], list(box)), gold[f'crop_out{i}'])
+
+
+def test_training_forward_losses_and_pointnet_heads(gold, sd, basis):
+    """SynergyNet.forward (model_building.py:141-157): the oracle's MLP_for / MLP_rev / WingLoss / ParamLoss against the
+    values recorded from the reference's own modules."""
+    x = synthetic.normalize_crops(torch.from_numpy(gold['x_u8']))
+    loss, t = rp.synergy_forward(sd, basis, x, torch.from_numpy(gold['fwd_target']))
+    for k in ('loss_LMK_f0', 'loss_LMK_pointNet', 'loss_Param_In', 'loss_Param_S2', 'loss_Param_S1S2'):
+        assert rp.max_rel_err(loss[k].numpy(), gold['fwd_' + k]) < TOL, k
+    assert rp.max_rel_err(t['point_residual'].numpy(), gold['fwd_point_residual']) < TOL
+    assert rp.max_rel_err(t['vertex_lmk_refined'].numpy(), gold['fwd_vertex_lmk_refined']) < TOL
+    assert rp.max_rel_err(t['_3D_attr_S2'].numpy(), gold['fwd_3D_attr_S2']) < TOL
+    assert float(np.abs(gold['fwd_point_residual']).max()) > 0.1          # the heads are alive in the synthetic checkpoint
+
+
+def test_resnet50_variant(gold):
+    """BASELINE.json configs[4]: the oracle's ResNet-50 against the reference's resnet_backbone.resnet50() module."""
+    sd = {'I2P.backbone.' + k: v for k, v in synth_model.build_resnet50_state_dict(0).items()}
+    x = synthetic.normalize_crops(torch.from_numpy(gold['x_u8']))[:4]
+    out, pooled = rp.resnet50_forward(sd, x)
+    assert out.shape == (4, 102) and pooled.shape == (4, 2048)
+    assert rp.max_rel_err(out.numpy(), gold['resnet50_out102']) < TOL
