@@ -301,6 +301,40 @@ def gpu_reference_comparator(dev, B):
     return out
 
 
+def config5_measurement(dev, peaks, B=512):
+    """BASELINE.json configs[4]: ResNet-50 backbone variant (resnet_backbone.py:227-249) at batch 512 and the PointNet
+    heads MLP_for / MLP_rev (pointnet_backbone.py:31-106) on 512 faces.  The reference cannot chain the two (I2P unpacks
+    two values from a backbone that returns one, MLP_for.conv6 wants a 1280-d feature), so they are
+    timed separately: ResNet-50 forward -> (B,102) + 68 landmarks from its first 62 outputs; MLP_for + MLP_rev fed with
+    MobileNetV2 features.  Random-init weights of the reference architecture, synthetic crops."""
+    from synergynet_b200 import model_building, synthetic
+    rn = model_building.SynergyNet(types.SimpleNamespace(arch='resnet50', img_size=120, devices_id=[dev.index]), _device=str(dev))
+    synthetic.seeded_init_(rn, 1)
+    synthetic.randomize_batchnorm_(rn, 1)
+    rn.eval()
+    x = synthetic.make_inputs(B, seed=3).to(dev)
+    eng = rn._engine(dev)
+    ms_rn = _time_cuda(lambda: rn.reconstruct_vertex_62(rn.forward_test(x)), iters=5, warmup=2)
+    flop_rn = 2.0 * 1_259_011_072 * B
+    mb = build_model(str(dev))
+    e2 = mb._engine(dev)
+    params, pool = e2.forward(x, want_pool=True)
+    lmk = e2.reconstruct(params)
+    ef = mb._pointnet_engine(x, 0)
+    mb._pointnet_engine(x, 1)
+    ms_for = _time_cuda(lambda: ef.mlp_for(lmk, pool, params), iters=10, warmup=2)
+    ms_rev = _time_cuda(lambda: ef.mlp_rev(lmk), iters=10, warmup=2)
+    mac_for = 68 * (192 + 4096 + 4096 + 8192 + 131072 + 32768 + 131072 + 32768 + 384) + 2354 * 512
+    mac_rev = 68 * (192 + 4096 + 4096 + 8192 + 131072) + 1024 * 62
+    return {'workload': 'configs[4]: ResNet-50 backbone variant, batch 512 -> (B,102) + 68 landmarks; PointNet heads on 512 faces',
+            'resnet50_ms': ms_rn, 'resnet50_faces_per_s': B / ms_rn * 1e3, 'resnet50_tflops': flop_rn / (ms_rn * 1e-3) / 1e12,
+            'resnet50_frac_tensor': flop_rn / (ms_rn * 1e-3) / 1e12 / peaks['bf16_sustained'],
+            'mlp_for_ms': ms_for, 'mlp_for_tflops': 2.0 * mac_for * B / (ms_for * 1e-3) / 1e12,
+            'mlp_rev_ms': ms_rev, 'mlp_rev_tflops': 2.0 * mac_rev * B / (ms_rev * 1e-3) / 1e12,
+            'note': 'general split-fp16 GEMM kernel (tc_gemm_kernel), not tuned: parity-grade coverage of the variant, '
+                    'algorithmic FLOP (2 x MAC; the shared per-face part of conv6 counted once) / CUDA-event time'}
+
+
 def run_b200(args):
     import torch.distributed as dist
     from synergynet_b200 import distributed as sdist
@@ -319,16 +353,20 @@ def run_b200(args):
     from synergynet_b200 import synthetic
     n_rot = 3                                   # rotate 3 x 177 MB inputs: every step misses the 126 MB L2
     xs = [synthetic.make_inputs(B, seed=10 * rank + i).to(dev) for i in range(n_rot)]
-    lmk_all = torch.empty((world * B, 3, 68), device=dev, dtype=torch.float32)
+    # two gather targets: the all-gather of step i runs on a side stream under the backbone of step i+1
+    lmk_alls = [torch.empty((world * B, 3, 68), device=dev, dtype=torch.float32) for _ in range(2)]
+    lmk_all = lmk_alls[0]
+    og = sdist.OverlappedGather(dev) if world > 1 else None
 
     def step(i):
         lmk = eng.forward_landmarks(xs[i % n_rot])
         if world > 1:
-            sdist.gather_landmarks(lmk, lmk_all)
+            og.gather(lmk, lmk_alls[i & 1])
         return lmk
 
     def barrier():
         if world > 1:
+            og.wait()                                   # every gather issued so far is part of the timed region
             dist.barrier()
         torch.cuda.synchronize(dev)
 
@@ -341,6 +379,8 @@ def run_b200(args):
     e0.record()
     for i in range(args.steps):
         step(i)
+    if world > 1:
+        og.wait()
     e1.record()
     barrier()
     probe_ms = max(e0.elapsed_time(e1), 1e-3)
@@ -360,6 +400,8 @@ def run_b200(args):
     ev0.record()
     for i in range(rounds * args.steps):
         step(i)
+    if world > 1:
+        og.wait()                                       # the last gather ends inside the CUDA-event region
     ev1.record()
     barrier()
     t_wall1 = time.time()
@@ -491,6 +533,12 @@ def run_b200(args):
                 extra['gpu_reference'] = gpu_reference_comparator(dev, B)
             except Exception as e:
                 extra['gpu_reference'] = {'unavailable': f'{type(e).__name__}: {e}'}
+        if not args.no_config5:
+            # ---- configs[4]: ResNet-50 backbone variant + PointNet refinement heads, batch 512 ---------------
+            try:
+                extra['config5'] = config5_measurement(dev, peaks)
+            except Exception as e:
+                extra['config5'] = {'unavailable': f'{type(e).__name__}: {e}'}
         if args.engine is None and not args.no_single_pass:
             # ---- single-pass fp16 engine (NOT parity grade): how much of the step is the 3x precision tax ----
             ref_l, ref_p = eng.forward_landmarks(xs[0][:256], want_params=True)
@@ -526,6 +574,9 @@ def run_b200(args):
                        'engine': {0: 'simt_fp32', 1: 'tcgen05_f16x3_unfused', 2: 'tcgen05_f16x3_fused',
                                   3: 'tcgen05_f16x1_fused (not parity grade)'}.get(eng.engine, eng.engine),
                        'parallelism': f'dp{world}',
+                       'collective': ('one all_gather_into_tensor of the (B,3,68) landmarks per step (NCCL), issued on a side '
+                                      'stream under the next step\'s backbone; the last one completes inside the timed region'
+                                      if world > 1 else None),
                        'timed_region': f'{rounds} x {args.steps} steps in one CUDA-event region ({ms / 1e3:.2f} s)',
                        'rounds': rounds, 'timed_steps': n_timed,
                        'l2': f'{n_rot} rotating device-resident input batches of {B * X_BYTES_PER_FACE / 1e6:.0f} MB '
@@ -587,6 +638,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile', action='store_true', help='device-resident steps only (for ncu runs)')
     ap.add_argument('--no-gpu-reference', action='store_true', help='skip the same-box PyTorch GPU comparator')
+    ap.add_argument('--no-config5', action='store_true', help='skip the ResNet-50 / PointNet heads measurement')
     ap.add_argument('--no-single-pass', action='store_true', help='skip the single-pass fp16 engine measurement')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -214,6 +214,9 @@ int syn_poll_saturation(syn_handle_t* h, int* flag_out);
 int syn_debug_forward_until(syn_handle_t* h, const float* x_dev, int batch, int layer,
                             float* out_dev, void* stream);
 
+/* Debug only: one workspace buffer of the PointNet heads after syn_mlp_for / syn_mlp_rev (synchronises). */
+int syn_debug_heads_buffer(syn_handle_t* h, int which, float* out_host, int64_t n);
+
 /* Host-only: the face-group plan the fused engine uses for a launch over `batch` faces on a GPU with
  * `sms` SMs and `faces_per_tile` (1, 2 or 8) faces per full tile.  Groups [0, *split) hold
  * faces_per_tile faces each; for two-face tiles the groups [*split, *face_groups) hold ONE face each

@@ -68,6 +68,7 @@ SIGNATURES = {
     'syn_resnet_set_heads': (_I, [_P, _F, _F]),
     'syn_resnet_commit': (_I, [_P]),
     'syn_resnet50_forward': (_I, [_P, _F, _I, _F, _F, _P]),
+    'syn_debug_heads_buffer': (_I, [_P, _I, _F, _L]),
     'syn_launch_count': (_L, [_P]),
     'syn_set_timing': (_I, [_P, _I]),
     'syn_get_timings': (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_char_p), _I, C.POINTER(C.c_int)]),
@@ -83,7 +84,7 @@ SIGNATURES = {
 _CORE = {n for n in SIGNATURES if n not in ('syn_peek_error', 'syn_poll_saturation', 'syn_pointnet_set_layer',
                                              'syn_pointnet_commit', 'syn_mlp_for', 'syn_mlp_rev', 'syn_wing_loss',
                                              'syn_param_loss', 'syn_reconstruct_image', 'syn_pose_decode', 'syn_set_center_crop', 'syn_resnet_num_convs', 'syn_resnet_conv_desc',
-                                             'syn_resnet_set_conv', 'syn_resnet_set_heads', 'syn_resnet_commit', 'syn_resnet50_forward')}
+                                             'syn_resnet_set_conv', 'syn_resnet_set_heads', 'syn_resnet_commit', 'syn_resnet50_forward', 'syn_debug_heads_buffer')}
 
 
 def declared_symbols(header: str = HEADER_PATH):

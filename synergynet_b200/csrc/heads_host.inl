@@ -365,6 +365,20 @@ int syn_mlp_rev(syn_handle_t* h, const float* lmk_dev, int batch, float* params6
   return launch_gemm(h, s->lr[5], io, st, "pointnet_rev_heads");
 }
 
+// Debug only: copy one workspace buffer of the PointNet heads to the host after a call (0 = point_features (B*68,64),
+// 1 = face vector (B,2360), 2 = conv6 face part (B,512), 3 = bufA, 4 = bufB, 5 = max-pooled conv5 as floats (B,1024)).
+int syn_debug_heads_buffer(syn_handle_t* h, int which, float* out_host, int64_t n) {
+  if (h == nullptr || h->heads == nullptr || out_host == nullptr || n <= 0) return fail(SYN_ERR_INVALID, "syn_debug_heads_buffer: bad argument");
+  DeviceGuard g(h->device);
+  SYN_CUDA(cudaDeviceSynchronize());
+  syn_heads* s = h->heads;
+  const void* src = which == 0 ? (const void*)s->pf : which == 1 ? (const void*)s->facevec : which == 2 ? (const void*)s->addend
+                    : which == 3 ? (const void*)s->bufA : which == 4 ? (const void*)s->bufB : (const void*)s->gmax;
+  if (src == nullptr) return fail(SYN_ERR_STATE, "syn_debug_heads_buffer: workspace not allocated");
+  SYN_CUDA(cudaMemcpy(out_host, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  return SYN_OK;
+}
+
 int syn_wing_loss(syn_handle_t* h, const float* pred_dev, const float* target_dev, int batch, int n_pts, float* out_dev,
                   void* stream) {
   if (h == nullptr || pred_dev == nullptr || target_dev == nullptr || out_dev == nullptr || batch <= 0 || n_pts <= 0)

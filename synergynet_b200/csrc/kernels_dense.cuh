@@ -372,6 +372,10 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
     const uint32_t d_hi = smem_desc_hi(128);
     const int n_planes = 3 * n_items;
     int next_plane = 0;                                               // next plane to request
+    // the basis image (40 MB) is read once per 64-face tile while ~650 MB of write-once output stream through L2:
+    // without a hint a quarter of the plane loads came back from DRAM (ncu: 180 MB read) and their latency, two
+    // planes of look-ahead deep, was what the epilogue warps waited for
+    const uint64_t keep = l2_policy_evict_last();
     auto dfree_wait = [&](int j) { mbar_wait(smem_u32(&bar_dfree[j & 1]), (uint32_t)(j >> 1) & 1, p.err); };
     // Request planes up to (and including) `upto`.  Plane q reuses the slot of plane q - 4, whose MMAs must be complete
     // (bar_pempty, consumed strictly in order).  The meta rows of item i go to slot i % 4, last read by the epilogue
@@ -385,12 +389,13 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
           const int it = it0 + i;
           const int ft = it / p.n_vtiles, vt = it - ft * p.n_vtiles;
           mbar_expect_tx(smem_u32(&bar_pfull[slot]), kFmPlane);
-          bulk_g2s(smem_u32(sP + slot * kFmPlane), p.basis_img + (size_t)vt * kDnATile + (size_t)c * kFmPlane, kFmPlane,
-                   smem_u32(&bar_pfull[slot]));
+          bulk_g2s_hint(smem_u32(sP + slot * kFmPlane), p.basis_img + (size_t)vt * kDnATile + (size_t)c * kFmPlane, kFmPlane,
+                        smem_u32(&bar_pfull[slot]), keep);
           if (c == 0) {
             const int ms = i % kFmMetaSlots;
             mbar_expect_tx(smem_u32(&bar_mfull[ms]), kDnMetaTile);
-            bulk_g2s(smem_u32(sMeta + ms * (kDnMetaTile / 4)), p.meta + (size_t)vt * 6 * 128, kDnMetaTile, smem_u32(&bar_mfull[ms]));
+            bulk_g2s_hint(smem_u32(sMeta + ms * (kDnMetaTile / 4)), p.meta + (size_t)vt * 6 * 128, kDnMetaTile,
+                          smem_u32(&bar_mfull[ms]), keep);
           }
         }
         __syncwarp();

@@ -30,9 +30,6 @@ namespace syn {
 constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 // tile shapes / chunk widths / batching depths worth re-measuring when the kernel changes: build variants
 // with -D... and compare them on one box with scripts/ab_variants.sh
-#ifndef SYN_OCC2
-#define SYN_OCC2 0
-#endif
 #ifndef SYN_RO_STEM
 #define SYN_RO_STEM 6
 #endif
@@ -66,7 +63,7 @@ constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 #define SYN_DW3_S 3
 #endif
 #ifndef SYN_DW2_MAXW
-#define SYN_DW2_MAXW (SYN_OCC2 ? 60 : 30)
+#define SYN_DW2_MAXW 30
 #endif
 #ifndef SYN_NC_B56
 #define SYN_NC_B56 64
@@ -82,11 +79,6 @@ constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 #endif
 #ifndef SYN_NC_B17
 #define SYN_NC_B17 32
-#endif
-// SYN_OCC2: two co-resident CTAs per SM (8 worker warps each, <= 112 KB smem, <= 256 TMEM columns) for the
-// stem ... block 13, so that one CTA's EPI1 / GEMM waits / EPI2 overlap the other's depthwise phase
-#ifndef SYN_OCC2
-#define SYN_OCC2 0
 #endif
 #ifndef SYN_EB_STEM
 #define SYN_EB_STEM 1
@@ -104,9 +96,8 @@ constexpr int round_up_c(int a, int b) { return ceil_div_c(a, b) * b; }
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 template <int CIN_, int CHID_, int NC_, int COUT_, int W_, int STRIDE_, int RO_, int FACES_, bool RES_, bool STEM_,
-          int WSTREAM_, int OCC_ = 1>
+          int WSTREAM_>
 struct FusedCfg {
-  static constexpr int OCC = OCC_;               // co-resident CTAs per SM this configuration is sized for (1 or 2)
   static constexpr bool STEM = STEM_;            // GEMM1 = im2col(3x3 s2 stem conv), CIN = 27 taps
   static constexpr bool RES = RES_;
   static constexpr bool WSTREAM = WSTREAM_ > 0;  // weights streamed per chunk (ring of WSTREAM_ slots) instead of resident
@@ -170,8 +161,6 @@ struct FusedCfg {
   static_assert(FACES_ == 1 || RO_ == WO, "multi-face tiles hold whole faces");
   static_assert(XA_COL + MT1 * CIN_P <= 512, "TMEM columns");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
-  // two CTAs per SM: 228 KB minus 1 KB reserved per CTA minus the static barriers; both CTAs allocate TM_COLS columns
-  static_assert(OCC_ == 1 || (OCC_ == 2 && SMEM_BYTES <= 112 * 1024 && TM_COLS <= 256), "occupancy-2 budget");
   static_assert(N2 % 16 == 0 && N2 <= 256, "MMA N");
   static_assert(WSTREAM_ == 0 || (WSTREAM_ >= 2 && WSTREAM_ <= 4 && NCHUNK >= WSTREAM_), "weight ring");
   // DW3 bank-conflict conditions.  Window loads: lane (s, r) of a quarter-warp reads 16 bytes at group offset
@@ -212,8 +201,7 @@ __device__ long long g_fused_trace[18 * 2 * 64 * 8];
 #define SYN_TRACE(role, chunk, ev) do { } while (0)
 #endif
 
-// Named barrier of a worker group with an IMMEDIATE id: with a register id ptxas reserves all 16 hardware barriers for
-// the CTA, and a second CTA cannot become resident on the SM (measured: occupancy 1 for the SYN_OCC2 shapes).
+// Named barrier of a worker group with an IMMEDIATE id (a register id makes ptxas reserve all 16 hardware barriers).
 template <int THREADS>
 __device__ __forceinline__ void group_bar_sync(int grp) {
   switch (grp) {
@@ -226,7 +214,7 @@ __device__ __forceinline__ void group_bar_sync(int grp) {
 
 // NWW = worker warps (multiple of 4: TMEM lane quarter = warp % 4); the issuer is warp NWW.
 template <class C, int NWW>
-__global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(const FusedArgs p) {
+__global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const FusedArgs p) {
   constexpr int NWT = NWW * 32;          // worker threads
   constexpr int NWG = NWW / 4;           // worker groups: group g owns every NWG-th (tile, column-chunk) pair
   static_assert(NWW % 4 == 0 && NWW >= 4 && NWW <= 16, "worker warps");
@@ -1103,7 +1091,6 @@ __global__ void __launch_bounds__((NWW + 1) * 32, C::OCC) fused_mbconv_kernel(co
 // CTAs; the remainder becomes single-face groups when those still fit in one wave.
 template <class C>
 inline void fused_tile_plan(int batch, int sms, int& split, int& face_groups) {
-  sms *= C::OCC;                                            // CTAs of one wave
   if constexpr (C::FACES == 2) {
     const int full = batch / 2, odd = batch & 1, rem = full % sms;
     split = (2 * rem + odd <= sms) ? full - rem : full;
@@ -1116,30 +1103,32 @@ inline void fused_tile_plan(int batch, int sms, int& split, int& face_groups) {
 
 // ---- the instantiations used by the backbone (SURVEY.md section 8(a) shape table) -------------------
 //                          CIN CHID NC COUT  W  S  RO FACES RES    STEM   weight ring slots (0 = resident)
-#if SYN_OCC2
-// occupancy-2 shapes: smaller strips / chunks so that two CTAs (8 worker warps each) share an SM
-using FusedStemB1 = FusedCfg<27, 32, 32, 16, 60, 1, 4, 1, false, true, 0, 2>;         // features[0] + features[1]
-using FusedB2 = FusedCfg<16, 96, 32, 24, 60, 2, 3, 1, false, false, 0, 2>;            // features[2]
-using FusedB3 = FusedCfg<24, 144, 16, 24, 30, 1, 10, 1, true, false, 0, 2>;           // features[3]
-using FusedB4 = FusedCfg<24, 144, 16, 32, 30, 2, 5, 1, false, false, 0, 2>;           // features[4]
-using FusedB56 = FusedCfg<32, 192, 32, 32, 15, 1, 15, 1, true, false, 3, 2>;          // features[5], [6]
-using FusedB7 = FusedCfg<32, 192, 32, 64, 15, 2, 8, 1, false, false, 3, 2>;           // features[7]
-using FusedB8 = FusedCfg<64, 384, 32, 64, 8, 1, 8, 2, true, false, 3, 2>;             // features[8..10]
-using FusedB11 = FusedCfg<64, 384, 32, 96, 8, 1, 8, 2, false, false, 2, 2>;           // features[11]
-using FusedB12 = FusedCfg<96, 576, 32, 96, 8, 1, 8, 2, true, false, 2, 2>;            // features[12], [13]
-#else
 using FusedStemB1 = FusedCfg<27, 32, 32, 16, 60, 1, SYN_RO_STEM, 1, false, true, 0>;    // features[0] + features[1]
 using FusedB2 = FusedCfg<16, 96, 32, 24, 60, 2, SYN_RO_B2, 1, false, false, 0>;       // features[2]
 using FusedB3 = FusedCfg<24, 144, 16, 24, 30, 1, 15, 1, true, false, 0>;      // features[3]
 using FusedB4 = FusedCfg<24, 144, SYN_NC_B4, 32, 30, 2, SYN_RO_B4, 1, false, false, 0>;      // features[4]
 using FusedB56 = FusedCfg<32, 192, SYN_NC_B56, 32, 15, 1, 15, 1, true, false, 0>;     // features[5], [6]
 using FusedB7 = FusedCfg<32, 192, SYN_NC_B7, 64, 15, 2, 8, 1, false, false, 0>;      // features[7]
+// Weight ring depth of the streamed blocks (SYN_DEEP_RING): the late blocks wait for their weight chunks -- a bulk copy of a
+// 25-60 KB chunk takes microseconds under load and a 2-slot ring gives it one chunk period -- so narrower chunks in
+// a 3-4-slot ring can win although they add chunk synchronisations.
+#ifndef SYN_DEEP_RING
+#define SYN_DEEP_RING 0
+#endif
+#if SYN_DEEP_RING
+using FusedB8 = FusedCfg<64, 384, 32, 64, 8, 1, 8, 2, true, false, 4>;         // features[8..10]
+using FusedB11 = FusedCfg<64, 384, 32, 96, 8, 1, 8, 2, false, false, 4>;       // features[11]
+using FusedB12 = FusedCfg<96, 576, 32, 96, 8, 1, 8, 2, true, false, 4>;        // features[12], [13]
+using FusedB14 = FusedCfg<96, 576, 32, 160, 8, 2, 4, 2, false, false, 4>;      // features[14]
+using FusedB15 = FusedCfg<160, 960, 32, 160, 4, 1, 4, 8, true, false, 3>;      // features[15], [16]
+using FusedB17 = FusedCfg<160, 960, 16, 320, 4, 1, 4, 8, false, false, 4>;     // features[17]
+#else
 using FusedB8 = FusedCfg<64, 384, 64, 64, 8, 1, 8, 2, true, false, 3>;         // features[8..10]
 using FusedB11 = FusedCfg<64, 384, 64, 96, 8, 1, 8, 2, false, false, 2>;       // features[11]
 using FusedB12 = FusedCfg<96, 576, SYN_NC_B12, 96, 8, 1, 8, 2, true, false, SYN_NC_B12 == 32 ? 3 : 2>;        // features[12], [13]
-#endif
 using FusedB14 = FusedCfg<96, 576, SYN_NC_B14, 160, 8, 2, 4, 2, false, false, SYN_NC_B14 == 32 ? 3 : 2>;      // features[14]
 using FusedB15 = FusedCfg<160, 960, 32, 160, 4, 1, 4, 8, true, false, 2>;      // features[15], [16]
 using FusedB17 = FusedCfg<160, 960, SYN_NC_B17, 320, 4, 1, 4, 8, false, false, SYN_NC_B17 == 16 ? 3 : 2>;     // features[17]
+#endif
 
 }  // namespace syn

@@ -510,15 +510,12 @@ int launch_fused_nww(syn_handle* h, const FusedArgs& a, int grid, cudaStream_t s
   static bool attr_set[16] = {};
   if (!attr_set[h->device & 15]) {
     SYN_CUDA(cudaFuncSetAttribute(fused_mbconv_kernel<C, NWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    if (C::OCC > 1)   // two CTAs per SM only fit with the largest shared-memory carve-out: ask for it explicitly
-      SYN_CUDA(cudaFuncSetAttribute(fused_mbconv_kernel<C, NWW>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    cudaSharedmemCarveoutMaxShared));
     attr_set[h->device & 15] = true;
     if (getenv("SYN_DEBUG_OCC") != nullptr) {
       int nb = -1;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_mbconv_kernel<C, NWW>, (NWW + 1) * 32, C::SMEM_BYTES);
-      fprintf(stderr, "[syn] fused CIN=%d CHID=%d W=%d: %d worker warps, %d B smem, %d TMEM cols -> %d CTA(s)/SM (sized for %d)\n",
-              C::CIN, C::CHID, C::W, NWW, C::SMEM_BYTES, C::TM_COLS, nb, C::OCC);
+      fprintf(stderr, "[syn] fused CIN=%d CHID=%d W=%d: %d worker warps, %d B smem, %d TMEM cols -> %d CTA(s)/SM\n",
+              C::CIN, C::CHID, C::W, NWW, C::SMEM_BYTES, C::TM_COLS, nb);
     }
   }
 #if SYN_PDL
@@ -551,16 +548,12 @@ int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, 
 #endif
   fused_tile_plan<C>(batch, h->sm_count, a.split, a.face_groups);
   const int ntiles = a.face_groups * C::STRIPS;
-  const int grid = std::min(ntiles, C::OCC * h->sm_count);
+  const int grid = std::min(ntiles, h->sm_count);
   int rc;
-  if constexpr (C::OCC == 2) {
-    rc = launch_fused_nww<C, 8>(h, a, grid, st);            // two co-resident CTAs per SM, 8 worker warps each
-  } else {
-    switch (fused_worker_warps()) {
-      case 8: rc = launch_fused_nww<C, 8>(h, a, grid, st); break;
-      case 12: rc = launch_fused_nww<C, 12>(h, a, grid, st); break;
-      default: rc = launch_fused_nww<C, 16>(h, a, grid, st); break;
-    }
+  switch (fused_worker_warps()) {
+    case 8: rc = launch_fused_nww<C, 8>(h, a, grid, st); break;
+    case 12: rc = launch_fused_nww<C, 12>(h, a, grid, st); break;
+    default: rc = launch_fused_nww<C, 16>(h, a, grid, st); break;
   }
   if (rc != SYN_OK) return rc;
   SYN_LAUNCH_CHECK("fused_mbconv_kernel");
@@ -1022,13 +1015,22 @@ int syn_forward_landmarks_u8(syn_handle_t* h, const uint8_t* x_u8, int batch, fl
   return run_reconstruct(h, p, batch, 0, 1, 1, lmk, (cudaStream_t)stream);
 }
 
-// Faces per pipeline chunk: large enough that the 8x8 / 4x4 blocks still fill the 148 SMs, small enough
-// that the first copy does not sit exposed.  SYN_HOST_CHUNK overrides it for measurements.
+// Faces per pipeline chunk: large enough that the 8x8 / 4x4 blocks still fill the 148 SMs, small enough that the copies
+// hide behind compute.  The FIRST chunk is small: its host->device copy is the only one nothing can overlap.
+// SYN_HOST_CHUNK / SYN_HOST_CHUNK0 override both for measurements.
 static int host_chunk_faces() {
   static const int v = [] {
     const char* e = getenv("SYN_HOST_CHUNK");
     const int c = e ? atoi(e) : 0;
     return c > 0 ? c : 512;
+  }();
+  return v;
+}
+static int host_first_chunk_faces() {
+  static const int v = [] {
+    const char* e = getenv("SYN_HOST_CHUNK0");
+    const int c = e ? atoi(e) : 0;
+    return c > 0 ? c : 512;   // measured: [512, 512] beats [128, 448, 448] and [256, 448, 320] (round 2)
   }();
   return v;
 }
@@ -1078,8 +1080,8 @@ static int forward_landmarks_host_impl(syn_handle_t* h, const void* x_host, int 
   int rc = ensure_workspace(h, chunk);
   if (rc != SYN_OK) return rc;
   int slot = 0, issued = 0;
-  for (int b0 = 0; b0 < batch; b0 += chunk, slot ^= 1, ++issued) {
-    const int nb = std::min(chunk, batch - b0);
+  for (int b0 = 0, nb = 0; b0 < batch; b0 += nb, slot ^= 1, ++issued) {
+    nb = std::min(issued == 0 ? std::min(chunk, host_first_chunk_faces()) : chunk, batch - b0);
     if (issued >= 2) SYN_CUDA(cudaStreamWaitEvent(h->s_copy, h->ev_done[slot], 0));
     SYN_CUDA(cudaMemcpyAsync(stage[slot], (const uint8_t*)x_host + (size_t)b0 * x_face * elt, nb * x_face * elt,
                              cudaMemcpyHostToDevice, h->s_copy));

@@ -241,6 +241,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+// Same copy with an L2 eviction-priority hint.  evict_last keeps a re-read working set (the 40 MB dense basis image,
+// read once per 64-face tile) resident in the 126 MB L2 while a write-once stream several times its size flows through.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
+
 // ---- packed fp32 arithmetic (sm_100: FFMA2 / FMUL2, two IEEE fp32 lanes per instruction) -----------------
 // Bit-identical to two scalar fmaf / multiplies; halves the FMA-pipe issue slots of the depthwise phase.
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {

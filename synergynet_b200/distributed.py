@@ -37,3 +37,27 @@ def gather_landmarks(local: torch.Tensor, out: torch.Tensor = None, group=None) 
         out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local.contiguous(), group=group)
     return out
+
+
+class OverlappedGather:
+    """The same single all-gather per step, issued on a side stream so that it runs under the NEXT step's backbone
+    instead of at the tail of its own step (the gather moves 835 KB per rank after ~2 ms of compute; un-overlapped it is
+    the whole 1 -> 8 GPU efficiency loss).  ``gather`` returns immediately; ``wait`` makes the current stream (and hence
+    a later ``.cpu()`` / synchronize) see every gather issued so far."""
+
+    def __init__(self, device: torch.device, group=None):
+        self.device, self.group = device, group
+        self.side = torch.cuda.Stream(device)
+
+    def gather(self, local: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        cur = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(cur)                       # landmarks of this step are complete
+        local = local.contiguous()
+        local.record_stream(self.side)                   # allocated on the compute stream, read on the side stream
+        out.record_stream(self.side)
+        with torch.cuda.stream(self.side):
+            dist.all_gather_into_tensor(out, local, group=self.group)
+        return out
+
+    def wait(self) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
