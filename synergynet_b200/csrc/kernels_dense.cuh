@@ -298,6 +298,21 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
   const int per = (items + gridDim.x - 1) / gridDim.x;
   const int it0 = min((int)blockIdx.x * per, items), it1 = min(it0 + per, items);
   const int n_items = it1 - it0;
+  // Item order: face tiles in PAIRS (outer), vertex tiles (middle), the two face tiles of the pair (inner).  Consecutive
+  // items with the same vertex tile form a VISIT and share its three basis planes, which halves the basis stream
+  // (96 KB per 128 x 64 x 3 outputs otherwise -- as many bytes read as written), while every (face, coordinate) row of a
+  // CTA still grows by 512 contiguous bytes per visit.  An odd last face tile walks the vertex tiles alone.
+  const int full_pairs = p.n_ftiles / 2, per_pair = 2 * p.n_vtiles;
+  auto decode = [&](int it, int& vt, int& ft) {
+    if (it < full_pairs * per_pair) {
+      const int ftp = it / per_pair, r = it - ftp * per_pair;
+      vt = r >> 1;
+      ft = 2 * ftp + (r & 1);
+    } else {
+      vt = it - full_pairs * per_pair;
+      ft = p.n_ftiles - 1;
+    }
+  };
 
   if (tid == 0) {
     for (int i = 0; i < kFmPSlots; ++i) { mbar_init(smem_u32(&bar_pfull[i]), 1); mbar_init(smem_u32(&bar_pempty[i]), 1); }
@@ -317,17 +332,21 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
 
   if (warp < kDnEpiWarps) {
     // ------------------------------ epilogue (two groups of 8 warps, alternate items) -----------------------------
+    // both groups walk the whole item list so that they agree on the visit numbering (meta slot = visit % 4)
     const int grp = warp >> 3, half = (warp >> 2) & 1;
     const int lane_v = tid & 127;
-    for (int i = grp; i < n_items; i += 2) {
-      const int it = it0 + i;
-      const int ft = it / p.n_vtiles, vt = it - ft * p.n_vtiles;
+    int visit = -1, cur_vt = -1;
+    for (int i = 0; i < n_items; ++i) {
+      int vt, ft;
+      decode(it0 + i, vt, ft);
+      if (vt != cur_vt) { cur_vt = vt; ++visit; }
+      if ((i & 1) != grp) continue;
       const int sb = i % kDnBSlots;
       mbar_wait(smem_u32(&bar_bfull[sb]), (uint32_t)(i / kDnBSlots) & 1, p.err);      // pose tile visible to this thread
-      mbar_wait(smem_u32(&bar_mfull[i % kFmMetaSlots]), (uint32_t)(i / kFmMetaSlots) & 1, p.err);   // meta rows visible
+      mbar_wait(smem_u32(&bar_mfull[visit % kFmMetaSlots]), (uint32_t)(visit / kFmMetaSlots) & 1, p.err);   // meta rows visible
       mbar_wait(smem_u32(&bar_dfull[grp]), (uint32_t)(i >> 1) & 1, p.err);
       tc_fence_after_sync();
-      const float* m = sMeta + (i % kFmMetaSlots) * (kDnMetaTile / 4);
+      const float* m = sMeta + (visit % kFmMetaSlots) * (kDnMetaTile / 4);
       const float ux = m[0 * 128 + lane_v], uy = m[1 * 128 + lane_v], uz = m[2 * 128 + lane_v];
       const float ox = m[3 * 128 + lane_v], oy = m[4 * 128 + lane_v], oz = m[5 * 128 + lane_v];
       const int v = vt * 128 + lane_v;
@@ -370,31 +389,37 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
     // ------------------------------ loader + MMA issuer (converged warp, elect.sync) ------------------------------
     const uint32_t idesc = make_idesc_f16(128, kDnFaces);
     const uint32_t d_hi = smem_desc_hi(128);
-    const int n_planes = 3 * n_items;
+    // planes are numbered per VISIT (q = 3 * visit + coordinate); the prefetcher scans the item list on its own
     int next_plane = 0;                                               // next plane to request
-    // the basis image (40 MB) is read once per 64-face tile while ~650 MB of write-once output stream through L2:
-    // without a hint a quarter of the plane loads came back from DRAM (ncu: 180 MB read) and their latency, two
-    // planes of look-ahead deep, was what the epilogue warps waited for
-    const uint64_t keep = l2_policy_evict_last();
+    int pre_i = 0, pre_vt = -1;                                       // prefetcher: next unscanned item, vertex tile of the visit being requested
+    const uint64_t keep = l2_policy_evict_last();                     // the basis image is re-read once per face-tile pair
     auto dfree_wait = [&](int j) { mbar_wait(smem_u32(&bar_dfree[j & 1]), (uint32_t)(j >> 1) & 1, p.err); };
     // Request planes up to (and including) `upto`.  Plane q reuses the slot of plane q - 4, whose MMAs must be complete
-    // (bar_pempty, consumed strictly in order).  The meta rows of item i go to slot i % 4, last read by the epilogue
-    // of item i - 4: plane 0 of item i is never requested before the MMAs of item i - 2 were issued, and those waited
-    // for dfree(i - 4), so that slot is known to be free without another wait.
+    // (bar_pempty, consumed strictly in order).  The meta rows of visit v go to slot v % 4, last read by the epilogue of
+    // an item at least three items back, which the TMEM hand-over (dfree of item i - 2) has already waited for.
     auto request_planes = [&](int upto) {
-      for (; next_plane <= upto && next_plane < n_planes; ++next_plane) {
-        const int q = next_plane, slot = q % kFmPSlots, i = q / 3, c = q - 3 * i;
+      for (; next_plane <= upto; ++next_plane) {
+        const int q = next_plane, slot = q % kFmPSlots, v = q / 3, c = q - 3 * v;
+        if (c == 0) {                                                // first plane of a new visit: find its vertex tile
+          if (pre_i >= n_items) return;                               // no more visits
+          int vt, ft;
+          decode(it0 + pre_i, vt, ft);
+          pre_vt = vt;
+          for (++pre_i; pre_i < n_items; ++pre_i) {                   // skip the other items of this visit
+            int vt2, ft2;
+            decode(it0 + pre_i, vt2, ft2);
+            if (vt2 != vt) break;
+          }
+        }
         if (q >= kFmPSlots) mbar_wait(smem_u32(&bar_pempty[slot]), (uint32_t)(q / kFmPSlots - 1) & 1, p.err);
         if (elect_one()) {
-          const int it = it0 + i;
-          const int ft = it / p.n_vtiles, vt = it - ft * p.n_vtiles;
           mbar_expect_tx(smem_u32(&bar_pfull[slot]), kFmPlane);
-          bulk_g2s_hint(smem_u32(sP + slot * kFmPlane), p.basis_img + (size_t)vt * kDnATile + (size_t)c * kFmPlane, kFmPlane,
+          bulk_g2s_hint(smem_u32(sP + slot * kFmPlane), p.basis_img + (size_t)pre_vt * kDnATile + (size_t)c * kFmPlane, kFmPlane,
                         smem_u32(&bar_pfull[slot]), keep);
           if (c == 0) {
-            const int ms = i % kFmMetaSlots;
+            const int ms = v % kFmMetaSlots;
             mbar_expect_tx(smem_u32(&bar_mfull[ms]), kDnMetaTile);
-            bulk_g2s_hint(smem_u32(sMeta + ms * (kDnMetaTile / 4)), p.meta + (size_t)vt * 6 * 128, kDnMetaTile,
+            bulk_g2s_hint(smem_u32(sMeta + ms * (kDnMetaTile / 4)), p.meta + (size_t)pre_vt * 6 * 128, kDnMetaTile,
                           smem_u32(&bar_mfull[ms]), keep);
           }
         }
@@ -402,8 +427,9 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
       }
     };
     auto load_b = [&](int i, int s) {
+      int vt, ft;
+      decode(it0 + i, vt, ft);
       if (elect_one()) {
-        const int ft = (it0 + i) / p.n_vtiles;
         uint8_t* dst = sB + s * kDnBSlot;
         mbar_expect_tx(smem_u32(&bar_bfull[s]), kDnBSlot);
         bulk_g2s(smem_u32(dst), p.alpha_img + (size_t)ft * kDnBTile, kDnBTile, smem_u32(&bar_bfull[s]));
@@ -414,15 +440,29 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
     for (int k = 0; k < kDnBSlots - 1; ++k)
       if (k < n_items) load_b(k, k);
     request_planes(kFmPSlots - 2);                                   // planes 0..2 in flight before the first MMA
+    int visit = -1, cur_vt = -1;
     for (int i = 0; i < n_items; ++i) {
+      int vt, ft;
+      decode(it0 + i, vt, ft);
+      const bool new_visit = vt != cur_vt;
+      if (new_visit) { cur_vt = vt; ++visit; }
+      bool last_of_visit = true;
+      if (i + 1 < n_items) {
+        int vt2, ft2;
+        decode(it0 + i + 1, vt2, ft2);
+        last_of_visit = vt2 != vt;
+      }
       const int s = i & 1, sb = i % kDnBSlots;
       mbar_wait(smem_u32(&bar_bfull[sb]), (uint32_t)(i / kDnBSlots) & 1, p.err);
       if (i >= 2) dfree_wait(i - 2);                                 // TMEM buffer s drained
       const uint32_t b_lo = smem_desc_lo(smem_u32(sB + sb * kDnBSlot), 1024);
       for (int c = 0; c < 3; ++c) {
-        const int q = 3 * i + c, slot = q % kFmPSlots;
-        request_planes(q + 2);                                       // keep two planes ahead of the MMAs in flight
-        mbar_wait(smem_u32(&bar_pfull[slot]), (uint32_t)(q / kFmPSlots) & 1, p.err);
+        const int q = 3 * visit + c, slot = q % kFmPSlots;
+        // keep up to two planes ahead of the MMAs in flight -- but never ask for a slot whose current plane this visit
+        // still needs (plane q+2 reuses the slot of plane q-2, which belongs to THIS visit when c == 2 and the visit has
+        // a second item to come: its release is committed by that item)
+        request_planes(last_of_visit ? q + 2 : min(q + 2, 3 * visit + 3));
+        if (new_visit) mbar_wait(smem_u32(&bar_pfull[slot]), (uint32_t)(q / kFmPSlots) & 1, p.err);
         tc_fence_after_sync();
         const uint32_t a_lo = smem_desc_lo(smem_u32(sP + slot * kFmPlane), 2048);
         if (elect_one()) {
@@ -435,7 +475,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
               umma_f16(tmem + s * 192 + c * 64, desc64(d_hi, a_lo + ((a_off + ks * 4096) >> 4)),
                        desc64(d_hi, b_lo + ((b_off + ks * 2048) >> 4)), idesc, (pass > 0 || ks > 0) ? 1u : 0u);
           }
-          umma_commit(smem_u32(&bar_pempty[slot]));                  // the plane may be overwritten once these MMAs are done
+          if (last_of_visit) umma_commit(smem_u32(&bar_pempty[slot]));   // the plane may be overwritten once these MMAs are done
           if (c == 2) umma_commit(smem_u32(&bar_dfull[s]));
         }
         __syncwarp();

@@ -1109,26 +1109,12 @@ using FusedB3 = FusedCfg<24, 144, 16, 24, 30, 1, 15, 1, true, false, 0>;      //
 using FusedB4 = FusedCfg<24, 144, SYN_NC_B4, 32, 30, 2, SYN_RO_B4, 1, false, false, 0>;      // features[4]
 using FusedB56 = FusedCfg<32, 192, SYN_NC_B56, 32, 15, 1, 15, 1, true, false, 0>;     // features[5], [6]
 using FusedB7 = FusedCfg<32, 192, SYN_NC_B7, 64, 15, 2, 8, 1, false, false, 0>;      // features[7]
-// Weight ring depth of the streamed blocks (SYN_DEEP_RING): the late blocks wait for their weight chunks -- a bulk copy of a
-// 25-60 KB chunk takes microseconds under load and a 2-slot ring gives it one chunk period -- so narrower chunks in
-// a 3-4-slot ring can win although they add chunk synchronisations.
-#ifndef SYN_DEEP_RING
-#define SYN_DEEP_RING 0
-#endif
-#if SYN_DEEP_RING
-using FusedB8 = FusedCfg<64, 384, 32, 64, 8, 1, 8, 2, true, false, 4>;         // features[8..10]
-using FusedB11 = FusedCfg<64, 384, 32, 96, 8, 1, 8, 2, false, false, 4>;       // features[11]
-using FusedB12 = FusedCfg<96, 576, 32, 96, 8, 1, 8, 2, true, false, 4>;        // features[12], [13]
-using FusedB14 = FusedCfg<96, 576, 32, 160, 8, 2, 4, 2, false, false, 4>;      // features[14]
-using FusedB15 = FusedCfg<160, 960, 32, 160, 4, 1, 4, 8, true, false, 3>;      // features[15], [16]
-using FusedB17 = FusedCfg<160, 960, 16, 320, 4, 1, 4, 8, false, false, 4>;     // features[17]
-#else
 using FusedB8 = FusedCfg<64, 384, 64, 64, 8, 1, 8, 2, true, false, 3>;         // features[8..10]
 using FusedB11 = FusedCfg<64, 384, 64, 96, 8, 1, 8, 2, false, false, 2>;       // features[11]
 using FusedB12 = FusedCfg<96, 576, SYN_NC_B12, 96, 8, 1, 8, 2, true, false, SYN_NC_B12 == 32 ? 3 : 2>;        // features[12], [13]
 using FusedB14 = FusedCfg<96, 576, SYN_NC_B14, 160, 8, 2, 4, 2, false, false, SYN_NC_B14 == 32 ? 3 : 2>;      // features[14]
-using FusedB15 = FusedCfg<160, 960, 32, 160, 4, 1, 4, 8, true, false, 2>;      // features[15], [16]
+// three ring slots for blocks 15/16 (measured -6 %); narrower chunks in deeper rings were slower everywhere else
+using FusedB15 = FusedCfg<160, 960, 32, 160, 4, 1, 4, 8, true, false, 3>;      // features[15], [16]
 using FusedB17 = FusedCfg<160, 960, SYN_NC_B17, 320, 4, 1, 4, 8, false, false, SYN_NC_B17 == 16 ? 3 : 2>;     // features[17]
-#endif
 
 }  // namespace syn
