@@ -87,6 +87,7 @@ struct DenseArgs {
   float* out;                 // (B,3,nver)
   int batch, nver, n_vtiles, n_ftiles, transform;
   int affine;                 // apply the per-face crop -> image affine stored behind the pose rows
+  int stream_stores;          // 1: st.global.cs (evict-first), 0: plain write-back stores (L2 merges neighbouring 512-byte runs)
   int* err;
 };
 
@@ -298,20 +299,13 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
   const int per = (items + gridDim.x - 1) / gridDim.x;
   const int it0 = min((int)blockIdx.x * per, items), it1 = min(it0 + per, items);
   const int n_items = it1 - it0;
-  // Item order: face tiles in PAIRS (outer), vertex tiles (middle), the two face tiles of the pair (inner).  Consecutive
-  // items with the same vertex tile form a VISIT and share its three basis planes, which halves the basis stream
-  // (96 KB per 128 x 64 x 3 outputs otherwise -- as many bytes read as written), while every (face, coordinate) row of a
-  // CTA still grows by 512 contiguous bytes per visit.  An odd last face tile walks the vertex tiles alone.
-  const int full_pairs = p.n_ftiles / 2, per_pair = 2 * p.n_vtiles;
+  // Item order: face tile (outer), vertex tile (inner).  Consecutive items with the same vertex tile would form a VISIT
+  // and share its three basis planes (the machinery below handles runs of any length); walking the face tiles in
+  // pairs to halve the basis stream was measured SLOWER (0.246 vs 0.226 ms: the held planes cost a slot of look-ahead),
+  // so every item is its own visit unless the mesh has a single vertex tile.
   auto decode = [&](int it, int& vt, int& ft) {
-    if (it < full_pairs * per_pair) {
-      const int ftp = it / per_pair, r = it - ftp * per_pair;
-      vt = r >> 1;
-      ft = 2 * ftp + (r & 1);
-    } else {
-      vt = it - full_pairs * per_pair;
-      ft = p.n_ftiles - 1;
-    }
+    ft = it / p.n_vtiles;
+    vt = it - ft * p.n_vtiles;
   };
 
   if (tid == 0) {
@@ -377,7 +371,8 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
                 vz = __fmul_rn(vz, pose[f * kDnPoseStride + 16]);
               }
               float* o = p.out + (size_t)(b0 + f) * 3 * p.nver + v;
-              __stcs(o, vx); __stcs(o + p.nver, vy); __stcs(o + 2 * (size_t)p.nver, vz);
+              if (p.stream_stores) { __stcs(o, vx); __stcs(o + p.nver, vy); __stcs(o + 2 * (size_t)p.nver, vz); }
+              else { o[0] = vx; o[p.nver] = vy; o[2 * (size_t)p.nver] = vz; }
             }
           }
         }

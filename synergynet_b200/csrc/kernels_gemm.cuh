@@ -11,10 +11,11 @@
 // the hi/lo split -- exact, undone by one multiply in the epilogue, and immune to the |x| < ~937 range limit of
 // the fixed scale (ReLU outputs of these layers are unbounded).
 //
-// Roles: warps 0-3 = producers (thread = GEMM row: gathers the fp32 row -- or, in conv mode, the k x k x C patch of
-// an NHWC pixel -- splits it and stores the canonical K-major operand), then the epilogue; warp 4 = bulk-copy of the
-// pre-packed weight chunks + MMA issue (converged warp, elect.sync).  K streams in chunks of 32 through a 2-stage
-// ring; two CTAs share an SM (96 KB smem, 256 TMEM columns each) so one tile's loads overlap the other's MMAs.
+// Roles: warps 0-7 = producers (thread = GEMM row x half of a chunk's k groups: gathers the fp32 row -- or, in conv
+// mode, the k x k x C patch of an NHWC pixel -- splits it and stores the canonical K-major operand), then the epilogue
+// (lane quarter = warp & 3, column half = warp >> 2); warp 8 = bulk-copy of the
+// pre-packed weight chunks + MMA issue (converged warp, elect.sync).  K streams in chunks of 32 through a 4-stage
+// ring (193 KB smem): the fp32 rows come from global memory / L2 and three chunks of look-ahead cover their latency.
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -22,12 +23,14 @@
 namespace syn {
 
 constexpr int kGmKC = 32;                                 // K chunk
-constexpr int kGmThreads = 160;
+constexpr int kGmStages = 4;                              // chunk ring: global-load latency of three chunks hidden
+constexpr int kGmProducerWarps = 8;                       // thread = (GEMM row, half of the chunk's k groups)
+constexpr int kGmThreads = (kGmProducerWarps + 1) * 32;
 constexpr int kGmMaxNr = 256;
 constexpr int kGmStageA = 128 * kGmKC * 2;                // 8 KB: one plane (hi or lo) of the A tile
 constexpr int kGmStageB = kGmMaxNr * kGmKC * 2;           // 16 KB
 constexpr int kGmStage = 2 * kGmStageA + 2 * kGmStageB;   // 48 KB
-constexpr int kGmSmem = 2 * kGmStage + 1024;
+constexpr int kGmSmem = kGmStages * kGmStage + 1024;
 
 enum { kActNone = 0, kActRelu6 = 1, kActRelu = 2 };
 
@@ -57,10 +60,10 @@ __device__ __forceinline__ int gemm_row_exp(unsigned maxbits) {
 }
 __device__ __forceinline__ float exp2i(int e) { return __uint_as_float((unsigned)(e + 127) << 23); }   // |e| <= 126
 
-__global__ void __launch_bounds__(kGmThreads, 2) tc_gemm_kernel(const GemmArgs p) {
+__global__ void __launch_bounds__(kGmThreads, 1) tc_gemm_kernel(const GemmArgs p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_acc;
+  __shared__ __align__(8) uint64_t bar_full[kGmStages], bar_empty[kGmStages], bar_acc;
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -70,14 +73,14 @@ __global__ void __launch_bounds__(kGmThreads, 2) tc_gemm_kernel(const GemmArgs p
   const uint8_t* wimg = p.Wimg + (size_t)blockIdx.y * (size_t)p.nr * p.Kp * 4;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bar_full[i]), 129);      // 128 producer arrivals + the weight copy's expect_tx arrival
+    for (int i = 0; i < kGmStages; ++i) {
+      mbar_init(smem_u32(&bar_full[i]), kGmProducerWarps * 32 + 1);   // producer arrivals + the weight copy's expect_tx arrival
       mbar_init(smem_u32(&bar_empty[i]), 1);
     }
     mbar_init(smem_u32(&bar_acc), 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc<256>(smem_u32(&tmem_base_s));
+  if (warp == kGmProducerWarps) tmem_alloc<256>(smem_u32(&tmem_base_s));
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -85,9 +88,9 @@ __global__ void __launch_bounds__(kGmThreads, 2) tc_gemm_kernel(const GemmArgs p
   auto stage_a = [&](int s, int plane) { return smem + s * kGmStage + plane * kGmStageA; };
   auto stage_b = [&](int s, int plane) { return smem + s * kGmStage + 2 * kGmStageA + plane * kGmStageB; };
 
-  if (warp < 4) {
+  if (warp < kGmProducerWarps) {
     // ------------------------------ producers ---------------------------------------------------
-    const int row = tid, m = m0 + row;
+    const int row = tid & 127, kh = tid >> 7, m = m0 + row;        // kh: which two of the chunk's four 8-element k groups
     const bool row_ok = m < p.M;
     int b = 0, oy = 0, ox = 0;
     unsigned mx = 0;
@@ -109,17 +112,16 @@ __global__ void __launch_bounds__(kGmThreads, 2) tc_gemm_kernel(const GemmArgs p
     const float a_scale = exp2i(e_row);
     const float* arow = p.A + (size_t)m * p.lda;
     for (int c = 0; c < nchunks; ++c) {
-      const int s = c & 1, use = c >> 1;
+      const int s = c % kGmStages, use = c / kGmStages;
       const int k0 = c * kGmKC;
       const int kc = min(kGmKC, p.Kp - k0);
-      mbar_wait(smem_u32(&bar_empty[s]), (use & 1) ^ 1, p.err);
-      uint8_t* ah = stage_a(s, 0) + (row >> 3) * 128 + (row & 7) * 16;
-      uint8_t* al = stage_a(s, 1) + (row >> 3) * 128 + (row & 7) * 16;
-#pragma unroll 2
-      for (int kg = 0; kg < kc / 8; ++kg) {
-        const int k = k0 + kg * 8;
+      // gather first (the loads do not depend on the slot), then wait for the slot: the global latency overlaps the wait
+      float4 va[2], ve[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int kg = kh * 2 + q, k = k0 + kg * 8;
         const float* src = nullptr;
-        if (row_ok && k < p.K) {
+        if (row_ok && kg * 8 < kc && k < p.K) {
           if (p.ksize > 0) {
             const int tap = k / p.C, cc = k - tap * p.C;
             const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
@@ -129,18 +131,27 @@ __global__ void __launch_bounds__(kGmThreads, 2) tc_gemm_kernel(const GemmArgs p
             src = arow + k;
           }
         }
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), e = a;
+        va[q] = make_float4(0.f, 0.f, 0.f, 0.f); ve[q] = va[q];
         if (src != nullptr) {                                 // K and C are multiples of 8, rows 16-byte aligned
-          a = __ldg(reinterpret_cast<const float4*>(src));
-          e = __ldg(reinterpret_cast<const float4*>(src + 4));
+          va[q] = __ldg(reinterpret_cast<const float4*>(src));
+          ve[q] = __ldg(reinterpret_cast<const float4*>(src + 4));
         }
-        uint32_t h[4], l[4];
-        split2_f16(a.x * a_scale, a.y * a_scale, h[0], l[0]);
-        split2_f16(a.z * a_scale, a.w * a_scale, h[1], l[1]);
-        split2_f16(e.x * a_scale, e.y * a_scale, h[2], l[2]);
-        split2_f16(e.z * a_scale, e.w * a_scale, h[3], l[3]);
-        *reinterpret_cast<uint4*>(ah + kg * 2048) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(al + kg * 2048) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      mbar_wait(smem_u32(&bar_empty[s]), (use & 1) ^ 1, p.err);
+      uint8_t* ah = stage_a(s, 0) + (row >> 3) * 128 + (row & 7) * 16;
+      uint8_t* al = stage_a(s, 1) + (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int kg = kh * 2 + q;
+        if (kg * 8 < kc) {
+          uint32_t h[4], l[4];
+          split2_f16(va[q].x * a_scale, va[q].y * a_scale, h[0], l[0]);
+          split2_f16(va[q].z * a_scale, va[q].w * a_scale, h[1], l[1]);
+          split2_f16(ve[q].x * a_scale, ve[q].y * a_scale, h[2], l[2]);
+          split2_f16(ve[q].z * a_scale, ve[q].w * a_scale, h[3], l[3]);
+          *reinterpret_cast<uint4*>(ah + kg * 2048) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(al + kg * 2048) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&bar_full[s]));
@@ -148,7 +159,7 @@ __global__ void __launch_bounds__(kGmThreads, 2) tc_gemm_kernel(const GemmArgs p
     // ------------------------------ epilogue ----------------------------------------------------
     mbar_wait(smem_u32(&bar_acc), 0, p.err);
     tc_fence_after_sync();
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int ncols = min(p.nr, p.N - n0);
     const float inv_a = exp2i(-e_row);
     float* orow = p.out ? p.out + (size_t)m * p.N + n0 : nullptr;
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(kGmThreads, 2) tc_gemm_kernel(const GemmArgs p
     const float* arow2 = p.addend ? p.addend + (size_t)(m / p.addend_group) * p.N + n0 : nullptr;
     unsigned* crow = p.colmax_out ? p.colmax_out + (size_t)(m / p.colmax_group) * p.N + n0 : nullptr;
     float rmax = 0.f;
-    for (int c0 = 0; c0 < ncols; c0 += 16) {
+    for (int c0 = kh * 16; c0 < ncols; c0 += 32) {          // the two warps of a lane quarter interleave 16-column blocks
       float v[16];
       tmem_ld16(trow + c0, v);                              // warp-collective: no divergence above
       if (!row_ok) continue;
@@ -179,11 +190,9 @@ __global__ void __launch_bounds__(kGmThreads, 2) tc_gemm_kernel(const GemmArgs p
     const uint32_t idesc = make_idesc_f16(128, p.nr);
     const uint32_t lbo_b = (uint32_t)(p.nr >> 3) * 128;
     const uint32_t d_hi = smem_desc_hi(128);
-    for (int c = 0; c < nchunks; ++c) {
-      const int s = c & 1, use = c >> 1;
-      const int k0 = c * kGmKC;
+    auto load_w = [&](int c) {                                // weight chunk c -> its ring slot (slot known to be free)
+      const int s = c % kGmStages, k0 = c * kGmKC;
       const int kc = min(kGmKC, p.Kp - k0);
-      mbar_wait(smem_u32(&bar_empty[s]), (use & 1) ^ 1, p.err);
       if (elect_one()) {
         const uint32_t plane_bytes = (uint32_t)p.nr * kc * 2;
         const uint8_t* src = wimg + (size_t)p.nr * k0 * 4;    // chunks of this range are consecutive
@@ -192,6 +201,11 @@ __global__ void __launch_bounds__(kGmThreads, 2) tc_gemm_kernel(const GemmArgs p
         bulk_g2s(smem_u32(stage_b(s, 1)), src + plane_bytes, plane_bytes, smem_u32(&bar_full[s]));
       }
       __syncwarp();
+    };
+    for (int c = 0; c < min(nchunks, kGmStages); ++c) load_w(c);      // the first use of every slot needs no wait
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % kGmStages, use = c / kGmStages;
+      const int kc = min(kGmKC, p.Kp - c * kGmKC);
       mbar_wait(smem_u32(&bar_full[s]), use & 1, p.err);
       tc_fence_after_sync();
       const uint32_t a_lo = smem_desc_lo(smem_u32(stage_a(s, 0)), 2048);
@@ -208,11 +222,17 @@ __global__ void __launch_bounds__(kGmThreads, 2) tc_gemm_kernel(const GemmArgs p
         if (c == nchunks - 1) umma_commit(smem_u32(&bar_acc));
       }
       __syncwarp();
+      // refill the slot of chunk c - 1 (its MMAs were committed one iteration ago) with chunk c - 1 + stages
+      if (c >= 1 && c - 1 + kGmStages < nchunks) {
+        const int cp = c - 1, sp = cp % kGmStages;
+        mbar_wait(smem_u32(&bar_empty[sp]), (uint32_t)(cp / kGmStages) & 1, p.err);
+        load_w(cp + kGmStages);
+      }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kGmProducerWarps) {
     __syncwarp();
     tmem_dealloc<256>(tmem);
   }

@@ -365,7 +365,9 @@ int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense,
   const int items = a.n_vtiles * a.n_ftiles;
   // dense mesh: face-major walk with streamed basis planes (long contiguous output runs per CTA); the 68-landmark
   // basis is one vertex tile, where the two kernels do the same work -- keep the simpler one there.
-  static const bool fm_off = getenv("SYN_DENSE_VERTEX_MAJOR") != nullptr;      // A/B switch for measurements
+  static const bool fm_off = getenv("SYN_DENSE_VERTEX_MAJOR") != nullptr;      // A/B switches for measurements
+  static const bool wb_stores = getenv("SYN_DENSE_WB_STORES") != nullptr;
+  a.stream_stores = wb_stores ? 0 : 1;
   if (dense && !fm_off) {
     dense_recon_fm_kernel<<<std::min(items, h->sm_count), kDnThreads, kFmSmem, st>>>(a);
     SYN_LAUNCH_CHECK("dense_recon_fm_kernel");
