@@ -308,6 +308,8 @@ def config5_measurement(dev, peaks, B=512):
     timed separately: ResNet-50 forward -> (B,102) + 68 landmarks from its first 62 outputs; MLP_for + MLP_rev fed with
     MobileNetV2 features.  Random-init weights of the reference architecture, synthetic crops."""
     from synergynet_b200 import model_building, synthetic
+    from synergynet_b200.params import ParamsPack, set_param_pack
+    set_param_pack(ParamsPack(arrays=synthetic.make_3dmm(seed=0)))
     rn = model_building.SynergyNet(types.SimpleNamespace(arch='resnet50', img_size=120, devices_id=[dev.index]), _device=str(dev))
     synthetic.seeded_init_(rn, 1)
     synthetic.randomize_batchnorm_(rn, 1)

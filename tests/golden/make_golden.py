@@ -99,6 +99,14 @@ def main():
         out[f'feat{i:02d}_sub'] = f[0, :, ::FEAT_STRIDE, ::FEAT_STRIDE].numpy()
         out[f'feat{i:02d}_absmean'] = np.float64(f.abs().double().mean().item())
 
+    # ---- BASELINE.json configs[1] size: 1024 DISTINCT faces through the reference, end to end ----------------------
+    x1024 = synthetic.normalize_crops(synthetic.make_structured_crops_u8(1024, seed=77))
+    with torch.no_grad():
+        p1024 = torch.cat([ref.forward_test(x1024[i:i + 64]) for i in range(0, 1024, 64)])
+        l1024 = ref.reconstruct_vertex_62(p1024, dense=False)
+    out['params1024'] = p1024.numpy()
+    out['lmk1024'] = l1024.numpy()
+
     # ---- training-time forward (model_building.py:141-157) through the reference's own modules -------------
     # model_building.SynergyNet needs CUDA at construction; synergy3DMM.SynergyNet owns the same sub-modules
     # (I2P, forwardDirection, reverseDirection, LMKLoss_3D, ParamLoss), so the statements of forward() are executed

@@ -16,10 +16,10 @@ pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'ref_vectors.npz')
 TOL = 1e-4            # north_star: 1e-4 relative fp32 on params / landmarks / vertices
-# Intermediate activations are a diagnostic, not a north_star output: the calibrated synthetic
-# network amplifies fp32 ordering noise to ~3e-5 per layer already (engine 0 vs the oneDNN oracle),
-# and the split-fp16 tensor-core engines sit ~4x above that at the deepest layers.
-LAYER_TOL = {0: 1e-4, 1: 3e-4, 2: 3e-4}
+# Intermediate activations are a diagnostic, not a north_star output: the calibrated synthetic network amplifies fp32
+# ordering noise to ~3e-5 per layer already (engine 0 vs the oneDNN oracle); the split-fp16 tensor-core engines measure
+# 7.9e-5 at the deepest layers.  DESIGN.md section 2 quotes the bound asserted here.
+LAYER_TOL = {0: 1e-4, 1: 1.5e-4, 2: 1.5e-4}
 ENGINES = [_lib.ENGINE_SIMT_FP32, _lib.ENGINE_TC_BF16X3, _lib.ENGINE_TC_FUSED]
 
 
@@ -176,9 +176,13 @@ def test_full_size_batch_properties(model, sd, gold, basis, engine_kind):
     assert rp.max_rel_err(params.view(128, 8, 62).cpu().numpy(),
                           ref8.cpu().numpy()[None].repeat(128, 0)) < 1e-6
     assert rp.max_rel_err(lmk[:8].cpu().numpy(), gold['lmk']) < TOL
-    # distinct faces too: oracle on a 24-face sample drawn from a 1024-face batch
+    # 1024 DISTINCT faces end to end against the values the reference itself produced for them (make_golden.py)
     xs = synthetic.normalize_crops(synthetic.make_structured_crops_u8(1024, seed=77))
-    p_big = model.forward_test(xs.cuda()).cpu()
+    l_big, p_dev = model._engine(big.device).forward_landmarks(xs.cuda(), want_params=True)
+    p_big = p_dev.cpu()
+    assert rp.max_rel_err(p_big.numpy(), gold['params1024']) < TOL
+    assert rp.max_rel_err(l_big.cpu().numpy(), gold['lmk1024']) < TOL
+    assert rp.nme_vs_reference(l_big.cpu().numpy(), gold['lmk1024']).max() < TOL
     idx = torch.arange(0, 1024, 43)
     want, _ = rp.mobilenetv2_forward(sd, xs[idx])
     assert rp.max_rel_err(p_big[idx].numpy(), want.numpy()) < TOL

@@ -116,3 +116,12 @@ def test_resnet50_variant(gold):
     out, pooled = rp.resnet50_forward(sd, x)
     assert out.shape == (4, 102) and pooled.shape == (4, 2048)
     assert rp.max_rel_err(out.numpy(), gold['resnet50_out102']) < TOL
+
+
+def test_thousand_face_batch_sample(gold, sd, basis):
+    """The 1024 distinct faces of the configs[1]-size golden batch: the oracle on a 16-face sample."""
+    xs = synthetic.normalize_crops(synthetic.make_structured_crops_u8(1024, seed=77))
+    idx = torch.arange(0, 1024, 64)
+    p, _ = rp.mobilenetv2_forward(sd, xs[idx])
+    assert rp.max_rel_err(p.numpy(), gold['params1024'][idx.numpy()]) < TOL
+    assert rp.max_rel_err(rp.reconstruct_vertex_62(p.numpy(), basis), gold['lmk1024'][idx.numpy()]) < TOL
