@@ -88,6 +88,7 @@ struct DenseArgs {
   int batch, nver, n_vtiles, n_ftiles, transform;
   int affine;                 // apply the per-face crop -> image affine stored behind the pose rows
   int stream_stores;          // 1: st.global.cs (evict-first), 0: plain write-back stores (L2 merges neighbouring 512-byte runs)
+  long long* trace;           // debug (SYN_DENSE_TRACE): clock64 stamps of CTA 0, 8 events x 64 items x {group 0, group 1, issuer}
   int* err;
 };
 
@@ -278,40 +279,50 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
 //   bar_mfull[slot]   meta rows of item i (slot i % 4) landed                         loader -> epilogue
 //   bar_bfull / bar_dfull / bar_dfree as above
 constexpr int kFmPlane = 2 * kDnAPlane;                   // 32 KB: [hi|lo] of one coordinate of one vertex tile
-constexpr int kFmPSlots = 4, kFmMetaSlots = 4;
-constexpr int kFmSmem = kFmPSlots * kFmPlane + kFmMetaSlots * kDnMetaTile + kDnBSlots * kDnBSlot + 1024;
+#ifndef SYN_FM_SPLIT
+#define SYN_FM_SPLIT 1                                    // bulk copies per plane
+#endif
+// Six plane slots: a 32 KB plane takes ~4 us from request to completion while the output stream saturates the memory
+// system (measured timeline, scripts/dense_trace.py), so the bytes in flight pace the kernel.  A CTA works on ONE face
+// tile, so its alpha / pose tile is loaded once instead of through a ring -- that is where the two extra slots come from.
+constexpr int kFmPSlots = 6, kFmMetaSlots = 4;
+constexpr int kFmSmem = kFmPSlots * kFmPlane + kFmMetaSlots * kDnMetaTile + kDnBSlot + 1024;
 static_assert(kDnATile == 3 * kFmPlane, "basis tile = three coordinate planes");
 static_assert(kFmSmem <= 227 * 1024, "shared memory");
 
 __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const DenseArgs p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_pfull[kFmPSlots], bar_pempty[kFmPSlots], bar_mfull[kFmMetaSlots], bar_bfull[kDnBSlots],
+  __shared__ __align__(8) uint64_t bar_pfull[kFmPSlots], bar_pempty[kFmPSlots], bar_mfull[kFmMetaSlots], bar_bfull,
       bar_dfull[2], bar_dfree[2];
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sP = smem;                                                                      // plane ring
   float* sMeta = reinterpret_cast<float*>(smem + kFmPSlots * kFmPlane);                   // kFmMetaSlots meta tiles
-  uint8_t* sB = smem + kFmPSlots * kFmPlane + kFmMetaSlots * kDnMetaTile;                 // alpha + pose ring
+  uint8_t* sB = smem + kFmPSlots * kFmPlane + kFmMetaSlots * kDnMetaTile;                 // alpha + pose tile of this CTA's face tile
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int items = p.n_vtiles * p.n_ftiles;
-  const int per = (items + gridDim.x - 1) / gridDim.x;
-  const int it0 = min((int)blockIdx.x * per, items), it1 = min(it0 + per, items);
-  const int n_items = it1 - it0;
-  // Item order: face tile (outer), vertex tile (inner).  Consecutive items with the same vertex tile would form a VISIT
-  // and share its three basis planes (the machinery below handles runs of any length); walking the face tiles in
-  // pairs to halve the basis stream was measured SLOWER (0.246 vs 0.226 ms: the held planes cost a slot of look-ahead),
-  // so every item is its own visit unless the mesh has a single vertex tile.
+  // Work split: CTA = (face tile ft, BAND of consecutive vertex tiles); the bands are the same for every face tile and the
+  // CTAs of one band are neighbours in the grid, so the n_ftiles CTAs that need a given basis tile ask for it at about the
+  // same time and all but the first hit in L2.  (A plain contiguous split of the item list gives every face tile its own
+  // band boundaries: ncu showed the 40 MB basis image read 4.4x from DRAM, and the plane loads -- two planes of look-ahead
+  // deep -- were what the epilogue warps waited for.)  Consecutive items with the same vertex tile would form a VISIT and
+  // share its planes (the machinery below handles runs of any length; walking face tiles in pairs to halve the basis
+  // stream was measured slower: the held planes cost a slot of look-ahead), so here every item is its own visit.
+  const int n_bands = max(1, (int)gridDim.x / p.n_ftiles);
+  const int band_len = (p.n_vtiles + n_bands - 1) / n_bands;
+  const int my_ft = (int)blockIdx.x % p.n_ftiles, my_band = (int)blockIdx.x / p.n_ftiles;
+  const int vt_lo = min(my_band * band_len, p.n_vtiles), vt_hi = (my_band < n_bands) ? min(vt_lo + band_len, p.n_vtiles) : vt_lo;
+  const int it0 = 0, n_items = vt_hi - vt_lo;
   auto decode = [&](int it, int& vt, int& ft) {
-    ft = it / p.n_vtiles;
-    vt = it - ft * p.n_vtiles;
+    vt = vt_lo + it;
+    ft = my_ft;
   };
 
   if (tid == 0) {
     for (int i = 0; i < kFmPSlots; ++i) { mbar_init(smem_u32(&bar_pfull[i]), 1); mbar_init(smem_u32(&bar_pempty[i]), 1); }
     for (int i = 0; i < kFmMetaSlots; ++i) mbar_init(smem_u32(&bar_mfull[i]), 1);
-    for (int i = 0; i < kDnBSlots; ++i) mbar_init(smem_u32(&bar_bfull[i]), 1);
+    mbar_init(smem_u32(&bar_bfull), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar_dfull[i]), 1);
       mbar_init(smem_u32(&bar_dfree[i]), kDnEpiWarps * 16);
@@ -335,11 +346,14 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
       decode(it0 + i, vt, ft);
       if (vt != cur_vt) { cur_vt = vt; ++visit; }
       if ((i & 1) != grp) continue;
-      const int sb = i % kDnBSlots;
-      mbar_wait(smem_u32(&bar_bfull[sb]), (uint32_t)(i / kDnBSlots) & 1, p.err);      // pose tile visible to this thread
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && (tid & 255) == 0 && i < 64;
+      if (tr) p.trace[(grp * 64 + i) * 8 + 0] = clock64();
+      mbar_wait(smem_u32(&bar_bfull), 0, p.err);                                       // pose tile visible to this thread
       mbar_wait(smem_u32(&bar_mfull[visit % kFmMetaSlots]), (uint32_t)(visit / kFmMetaSlots) & 1, p.err);   // meta rows visible
+      if (tr) p.trace[(grp * 64 + i) * 8 + 1] = clock64();
       mbar_wait(smem_u32(&bar_dfull[grp]), (uint32_t)(i >> 1) & 1, p.err);
       tc_fence_after_sync();
+      if (tr) p.trace[(grp * 64 + i) * 8 + 2] = clock64();
       const float* m = sMeta + (visit % kFmMetaSlots) * (kDnMetaTile / 4);
       const float ux = m[0 * 128 + lane_v], uy = m[1 * 128 + lane_v], uz = m[2 * 128 + lane_v];
       const float ox = m[3 * 128 + lane_v], oy = m[4 * 128 + lane_v], oz = m[5 * 128 + lane_v];
@@ -347,10 +361,11 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
 #pragma unroll
       for (int rnd = 0; rnd < 2; ++rnd) {                            // 2 x 16 faces per thread
         const int fofs = half * 32 + rnd * 16;
-        const float* pose = reinterpret_cast<const float*>(sB + sb * kDnBSlot + kDnBTile) + fofs * kDnPoseStride;
+        const float* pose = reinterpret_cast<const float*>(sB + kDnBTile) + fofs * kDnPoseStride;
         const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + grp * 192 + fofs;
         float sx[16], sy[16], sz[16];
         tmem_ld16x3(trow, trow + 64, trow + 128, sx, sy, sz);
+        if (tr) p.trace[(grp * 64 + i) * 8 + 3 + rnd] = clock64();
         const int b0 = ft * kDnFaces + fofs;
         if (v < p.nver) {
 #pragma unroll
@@ -377,6 +392,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
           }
         }
       }
+      if (tr) p.trace[(grp * 64 + i) * 8 + 5] = clock64();
       tc_fence_before_sync();
       mbar_arrive(smem_u32(&bar_dfree[grp]));
     }
@@ -389,7 +405,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
     int pre_i = 0, pre_vt = -1;                                       // prefetcher: next unscanned item, vertex tile of the visit being requested
     const uint64_t keep = l2_policy_evict_last();                     // the basis image is re-read once per face-tile pair
     auto dfree_wait = [&](int j) { mbar_wait(smem_u32(&bar_dfree[j & 1]), (uint32_t)(j >> 1) & 1, p.err); };
-    // Request planes up to (and including) `upto`.  Plane q reuses the slot of plane q - 4, whose MMAs must be complete
+    // Request planes up to (and including) `upto`.  Plane q reuses the slot of plane q - kFmPSlots, whose MMAs must be complete
     // (bar_pempty, consumed strictly in order).  The meta rows of visit v go to slot v % 4, last read by the epilogue of
     // an item at least three items back, which the TMEM hand-over (dfree of item i - 2) has already waited for.
     auto request_planes = [&](int upto) {
@@ -409,8 +425,14 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
         if (q >= kFmPSlots) mbar_wait(smem_u32(&bar_pempty[slot]), (uint32_t)(q / kFmPSlots - 1) & 1, p.err);
         if (elect_one()) {
           mbar_expect_tx(smem_u32(&bar_pfull[slot]), kFmPlane);
-          bulk_g2s_hint(smem_u32(sP + slot * kFmPlane), p.basis_img + (size_t)pre_vt * kDnATile + (size_t)c * kFmPlane, kFmPlane,
-                        smem_u32(&bar_pfull[slot]), keep);
+          // SYN_FM_SPLIT bulk copies per plane on the same barrier (measured: a single 32 KB copy takes ~4 us from request
+          // to completion while the output stream saturates the memory system, and that latency -- three planes in
+          // flight -- is what paces the kernel)
+#pragma unroll
+          for (int part = 0; part < SYN_FM_SPLIT; ++part)
+            bulk_g2s_hint(smem_u32(sP + slot * kFmPlane + part * (kFmPlane / SYN_FM_SPLIT)),
+                          p.basis_img + (size_t)pre_vt * kDnATile + (size_t)c * kFmPlane + part * (kFmPlane / SYN_FM_SPLIT),
+                          kFmPlane / SYN_FM_SPLIT, smem_u32(&bar_pfull[slot]), keep);
           if (c == 0) {
             const int ms = v % kFmMetaSlots;
             mbar_expect_tx(smem_u32(&bar_mfull[ms]), kDnMetaTile);
@@ -421,20 +443,15 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
         __syncwarp();
       }
     };
-    auto load_b = [&](int i, int s) {
-      int vt, ft;
-      decode(it0 + i, vt, ft);
+    if (n_items > 0) {                                               // alpha + pose of this CTA's face tile: once
       if (elect_one()) {
-        uint8_t* dst = sB + s * kDnBSlot;
-        mbar_expect_tx(smem_u32(&bar_bfull[s]), kDnBSlot);
-        bulk_g2s(smem_u32(dst), p.alpha_img + (size_t)ft * kDnBTile, kDnBTile, smem_u32(&bar_bfull[s]));
-        bulk_g2s(smem_u32(dst + kDnBTile), p.pose + (size_t)ft * kDnFaces * kDnPoseStride, kDnPoseTile, smem_u32(&bar_bfull[s]));
+        mbar_expect_tx(smem_u32(&bar_bfull), kDnBSlot);
+        bulk_g2s(smem_u32(sB), p.alpha_img + (size_t)my_ft * kDnBTile, kDnBTile, smem_u32(&bar_bfull));
+        bulk_g2s(smem_u32(sB + kDnBTile), p.pose + (size_t)my_ft * kDnFaces * kDnPoseStride, kDnPoseTile, smem_u32(&bar_bfull));
       }
       __syncwarp();
-    };
-    for (int k = 0; k < kDnBSlots - 1; ++k)
-      if (k < n_items) load_b(k, k);
-    request_planes(kFmPSlots - 2);                                   // planes 0..2 in flight before the first MMA
+    }
+    request_planes(kFmPSlots - 2);                                   // planes 0..4 in flight before the first MMA
     int visit = -1, cur_vt = -1;
     for (int i = 0; i < n_items; ++i) {
       int vt, ft;
@@ -447,17 +464,21 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
         decode(it0 + i + 1, vt2, ft2);
         last_of_visit = vt2 != vt;
       }
-      const int s = i & 1, sb = i % kDnBSlots;
-      mbar_wait(smem_u32(&bar_bfull[sb]), (uint32_t)(i / kDnBSlots) & 1, p.err);
+      const int s = i & 1;
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && (tid & 31) == 0 && i < 64;
+      if (tr) p.trace[(128 + i) * 8 + 0] = clock64();
+      mbar_wait(smem_u32(&bar_bfull), 0, p.err);
+      if (tr) p.trace[(128 + i) * 8 + 1] = clock64();
       if (i >= 2) dfree_wait(i - 2);                                 // TMEM buffer s drained
-      const uint32_t b_lo = smem_desc_lo(smem_u32(sB + sb * kDnBSlot), 1024);
+      if (tr) p.trace[(128 + i) * 8 + 2] = clock64();
+      const uint32_t b_lo = smem_desc_lo(smem_u32(sB), 1024);
       for (int c = 0; c < 3; ++c) {
         const int q = 3 * visit + c, slot = q % kFmPSlots;
-        // keep up to two planes ahead of the MMAs in flight -- but never ask for a slot whose current plane this visit
-        // still needs (plane q+2 reuses the slot of plane q-2, which belongs to THIS visit when c == 2 and the visit has
-        // a second item to come: its release is committed by that item)
-        request_planes(last_of_visit ? q + 2 : min(q + 2, 3 * visit + 3));
+        // keep up to four planes ahead of the MMAs in flight -- but never ask for a slot whose current plane this visit
+        // still needs (a multi-item visit releases its planes with its last item)
+        request_planes(last_of_visit ? q + kFmPSlots - 2 : min(q + kFmPSlots - 2, 3 * visit + kFmPSlots - 1));
         if (new_visit) mbar_wait(smem_u32(&bar_pfull[slot]), (uint32_t)(q / kFmPSlots) & 1, p.err);
+        if (tr) p.trace[(128 + i) * 8 + 3 + c] = clock64();            // plane c landed (and requests up to q+2 issued)
         tc_fence_after_sync();
         const uint32_t a_lo = smem_desc_lo(smem_u32(sP + slot * kFmPlane), 2048);
         if (elect_one()) {
@@ -475,11 +496,8 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
         }
         __syncwarp();
       }
-      // alpha/pose three items ahead, into the slot last used by item i-1 (its MMAs and epilogue are done)
-      if (i + kDnBSlots - 1 < n_items) {
-        if (i >= 1) dfree_wait(i - 1);
-        load_b(i + kDnBSlots - 1, (i + kDnBSlots - 1) % kDnBSlots);
-      }
+      if (tr) p.trace[(128 + i) * 8 + 6] = clock64();                  // MMAs of the item issued
+      if (tr) p.trace[(128 + i) * 8 + 7] = clock64();
     }
   }
   tc_fence_before_sync();

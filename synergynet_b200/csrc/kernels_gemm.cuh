@@ -65,10 +65,15 @@ __global__ void __launch_bounds__(kGmThreads, 1) tc_gemm_kernel(const GemmArgs p
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[kGmStages], bar_empty[kGmStages], bar_acc;
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[kGmMaxNr], s_osc[kGmMaxNr];       // epilogue constants of this n-range
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int m0 = blockIdx.x * 128;
   const int n0 = blockIdx.y * p.nr;
+  for (int i = tid; i < p.nr; i += kGmThreads) {              // the packed arrays are padded to nranges * nr entries
+    s_bias[i] = p.bias[n0 + i];
+    s_osc[i] = p.oscale[n0 + i];
+  }
   const int nchunks = (p.Kp + kGmKC - 1) / kGmKC;
   const uint8_t* wimg = p.Wimg + (size_t)blockIdx.y * (size_t)p.nr * p.Kp * 4;
 
@@ -167,21 +172,57 @@ __global__ void __launch_bounds__(kGmThreads, 1) tc_gemm_kernel(const GemmArgs p
     const float* arow2 = p.addend ? p.addend + (size_t)(m / p.addend_group) * p.N + n0 : nullptr;
     unsigned* crow = p.colmax_out ? p.colmax_out + (size_t)(m / p.colmax_group) * p.N + n0 : nullptr;
     float rmax = 0.f;
+    const bool vec = (p.N & 3) == 0;                           // rows of out / residual / addend are 16-byte aligned
+    // max-pool over the rows of a group (PointNet): the 32 rows of a warp almost always belong to one group (68 points
+    // per face), so the warp reduces first (redux.sync) and issues ONE atomic per column instead of 32 on one address
+    const int cgrp = crow ? m / p.colmax_group : 0;
+    const bool warp_one_group = crow != nullptr && __all_sync(0xffffffffu, cgrp == __shfl_sync(0xffffffffu, cgrp, 0) && row_ok);
+    auto pool_max = [&](int col, float o) {                    // warp-uniform call sites only
+      const unsigned bits = row_ok ? __float_as_uint(o) : 0u;  // o >= 0 (ReLU): the bit pattern orders like the value
+      if (warp_one_group) {
+        const unsigned mx = __reduce_max_sync(0xffffffffu, bits);
+        if ((tid & 31) == 0) atomicMax(crow + col, mx);
+      } else if (row_ok) {
+        atomicMax(crow + col, bits);
+      }
+    };
     for (int c0 = kh * 16; c0 < ncols; c0 += 32) {          // the two warps of a lane quarter interleave 16-column blocks
       float v[16];
-      tmem_ld16(trow + c0, v);                              // warp-collective: no divergence above
-      if (!row_ok) continue;
+      tmem_ld16(trow + c0, v);                              // warp-collective: the control flow below stays warp-uniform
+      if (vec && c0 + 16 <= ncols) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_osc + c0 + j), bb = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+          float4 o = make_float4(fmaf(v[j] * inv_a, sc.x, bb.x), fmaf(v[j + 1] * inv_a, sc.y, bb.y),
+                                 fmaf(v[j + 2] * inv_a, sc.z, bb.z), fmaf(v[j + 3] * inv_a, sc.w, bb.w));
+          if (row_ok) {
+            if (arow2) { const float4 a = *reinterpret_cast<const float4*>(arow2 + c0 + j); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+            if (rrow) { const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + c0 + j)); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+          }
+          if (p.act == kActRelu6) { o.x = relu6f(o.x); o.y = relu6f(o.y); o.z = relu6f(o.z); o.w = relu6f(o.w); }
+          else if (p.act == kActRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (row_ok) {
+            rmax = fmaxf(rmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+            if (orow) *reinterpret_cast<float4*>(orow + c0 + j) = o;
+          }
+          if (crow) { pool_max(c0 + j, o.x); pool_max(c0 + j + 1, o.y); pool_max(c0 + j + 2, o.z); pool_max(c0 + j + 3, o.w); }
+        }
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        if (c0 + j >= ncols) break;
-        const int n = n0 + c0 + j;
-        float o = fmaf(v[j] * inv_a, p.oscale[n], p.bias[n]);
-        if (arow2) o += arow2[c0 + j];
-        if (rrow) o += rrow[c0 + j];
+        if (c0 + j >= ncols) break;                          // warp-uniform
+        float o = fmaf(v[j] * inv_a, s_osc[c0 + j], s_bias[c0 + j]);
+        if (row_ok) {
+          if (arow2) o += arow2[c0 + j];
+          if (rrow) o += rrow[c0 + j];
+        }
         if (p.act == kActRelu6) o = relu6f(o); else if (p.act == kActRelu) o = fmaxf(o, 0.f);
-        rmax = fmaxf(rmax, fabsf(o));
-        if (orow) orow[c0 + j] = o;
-        if (crow) atomicMax(crow + c0 + j, __float_as_uint(o));      // o >= 0 (ReLU): the bit pattern orders like the value
+        if (row_ok) {
+          rmax = fmaxf(rmax, fabsf(o));
+          if (orow) orow[c0 + j] = o;
+        }
+        if (crow) pool_max(c0 + j, o);
       }
     }
     if (row_ok && p.rowmax_out != nullptr) atomicMax(p.rowmax_out + m, __float_as_uint(rmax));

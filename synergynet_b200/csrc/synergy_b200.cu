@@ -368,10 +368,33 @@ int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense,
   static const bool fm_off = getenv("SYN_DENSE_VERTEX_MAJOR") != nullptr;      // A/B switches for measurements
   static const bool wb_stores = getenv("SYN_DENSE_WB_STORES") != nullptr;
   a.stream_stores = wb_stores ? 0 : 1;
+  a.trace = nullptr;
+  static long long* d_dense_trace = nullptr;                                   // debug: SYN_DENSE_TRACE=file dumps CTA 0's timeline
+  static const char* trace_fp = getenv("SYN_DENSE_TRACE");
+  if (trace_fp != nullptr && dense) {
+    if (d_dense_trace == nullptr) cudaMalloc(&d_dense_trace, 192 * 8 * sizeof(long long));
+    cudaMemsetAsync(d_dense_trace, 0, 192 * 8 * sizeof(long long), st);
+    a.trace = d_dense_trace;
+  }
   if (dense && !fm_off) {
-    dense_recon_fm_kernel<<<std::min(items, h->sm_count), kDnThreads, kFmSmem, st>>>(a);
+    // grid = face tiles x vertex bands (see the kernel): as many whole bands as fit the SMs
+    const int n_bands = std::max(1, h->sm_count / a.n_ftiles);
+    dense_recon_fm_kernel<<<a.n_ftiles * std::min(n_bands, a.n_vtiles), kDnThreads, kFmSmem, st>>>(a);
     SYN_LAUNCH_CHECK("dense_recon_fm_kernel");
     mark(h, st, "dense_recon_fm_kernel");
+    if (a.trace != nullptr) {                                                  // debug only: synchronous dump
+      std::vector<long long> t(192 * 8);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(t.data(), a.trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      if (FILE* f = fopen(trace_fp, "w")) {
+        for (int r = 0; r < 192; ++r) {
+          fprintf(f, "%s %d", r < 64 ? "epi0" : r < 128 ? "epi1" : "issuer", r & 63);
+          for (int e = 0; e < 8; ++e) fprintf(f, " %lld", t[r * 8 + e]);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+    }
     return SYN_OK;
   }
   dense_recon_tc_kernel<<<std::min(items, h->sm_count), kDnThreads, kDnSmem, st>>>(a);
