@@ -271,25 +271,68 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
 // Face-major variant for the dense mesh (configs[2]).  The kernel above walks vertex-tile major: a CTA writes 512 B
 // to each of 64 faces x 3 rows and moves on to OTHER faces, so every DRAM page is touched once per visit (measured:
 // 2.1 TB/s of 6.5).  Here a CTA keeps one 64-face tile and walks over consecutive vertex tiles: each of its 192
-// output rows grows by 512 contiguous bytes per item, which L2 write-back turns into long DRAM bursts.  The price is
-// a new basis tile per item; it streams from L2 (40 MB image, resident) coordinate plane by coordinate plane (32 KB =
-// hi + lo of one coordinate) through a 4-slot ring, two planes ahead of the MMAs.
+// output rows grows by 512 contiguous bytes per item.  The price is a new basis tile per item; it streams from L2
+// (40 MB image, resident) coordinate plane by coordinate plane (32 KB = hi + lo of one coordinate) through a 4-slot
+// ring, two planes ahead of the MMAs.
+//
+// WHOLE-SECTOR STORES.  The output rows of the reference layout (B,3,53215) fp32 start on every 4-byte phase, so a warp
+// that stores "lane = vertex" always writes two partial 32-byte sectors per 128 bytes.  Measured with the store stream
+// alone (tools/dense_store_probe.cu): that pattern tops out at 2.95 TB/s -- exactly what the previous version of this
+// kernel reached -- while the same bytes written as whole aligned sectors go at 5.1 TB/s.  So the epilogue does not
+// store from the TMEM lane mapping: a TEAM of four warps (the four lane quarters = 128 vertices, 16 faces) stages
+// 12 output rows at a time in shared memory and writes them back out with the lane -> address mapping shifted by each
+// row's own phase (address / 4 mod 8), so that every warp store covers whole aligned sectors.  The <= 7 floats that
+// fall off the end of a row piece are carried (sCarry) into the next item's piece of the same row; only the two ends of
+// a CTA's band are written with bounds-checked stores.
 //   bar_pfull[slot]   plane landed                                                    loader -> issuer
 //   bar_pempty[slot]  the 12 MMAs that read the plane are complete (tcgen05.commit)  -> loader
 //   bar_mfull[slot]   meta rows of item i (slot i % 4) landed                         loader -> epilogue
-//   bar_bfull / bar_dfull / bar_dfree as above
+//   bar_bfull         alpha + pose tile of the CTA's face tile landed (once)
+//   bar_dfull[s]      accumulator buffer s complete                                   issuer -> epilogue
+//   bar_dfree[s]      all 512 epilogue threads have read buffer s into registers (before they stage / store the second half)
 constexpr int kFmPlane = 2 * kDnAPlane;                   // 32 KB: [hi|lo] of one coordinate of one vertex tile
 #ifndef SYN_FM_SPLIT
-#define SYN_FM_SPLIT 1                                    // bulk copies per plane
+#define SYN_FM_SPLIT 1                                    // bulk copies per plane (1, 2, 4, 8: measured no difference)
 #endif
-// Six plane slots: a 32 KB plane takes ~4 us from request to completion while the output stream saturates the memory
-// system (measured timeline, scripts/dense_trace.py), so the bytes in flight pace the kernel.  A CTA works on ONE face
-// tile, so its alpha / pose tile is loaded once instead of through a ring -- that is where the two extra slots come from.
-constexpr int kFmPSlots = 6, kFmMetaSlots = 4;
-constexpr int kFmSmem = kFmPSlots * kFmPlane + kFmMetaSlots * kDnMetaTile + kDnBSlot + 1024;
+constexpr int kFmPSlots = 4, kFmMetaSlots = 4;
+constexpr int kFmTeams = 4;                               // 4 warps each: faces 16t .. 16t+15 of the item
+constexpr int kFmSubFaces = 4;                            // faces staged per sub-round -> 12 rows
+constexpr int kFmRows = 3 * kFmSubFaces;
+constexpr int kFmPitch = 128;                             // floats per staged row (position = vertex within the tile)
+constexpr int kFmStage = 2 * kFmRows * kFmPitch * 4;      // per team, double buffered: 12 KB
+constexpr int kFmCarry = 16 * 3 * 8 * 4;                  // per team: 48 rows x 8 floats
+constexpr int kFmSmem = kFmPSlots * kFmPlane + kFmMetaSlots * kDnMetaTile + kDnBSlot + kFmTeams * (kFmStage + kFmCarry) + 1024;
 static_assert(kDnATile == 3 * kFmPlane, "basis tile = three coordinate planes");
-static_assert(kFmSmem <= 227 * 1024, "shared memory");
+static_assert(kFmSmem + 512 <= 227 * 1024, "shared memory");
+static_assert(kDnEpiWarps == 4 * kFmTeams && kDnFaces == 16 * kFmTeams, "team shape");
 
+// Bounds-checked write-out of dense_recon_fm_kernel for the first / last item of a CTA's band and for ragged face tiles
+// (kept out of line: the hot path then needs no predicates).  Same mapping as the fast path in the kernel.
+__device__ __forceinline__ void fm_write_edge(const DenseArgs& p, const float* Tw, float* crw, float* piece, int bq, int wq, int lane,
+                                           bool first, bool last, int nvalid) {
+#pragma unroll 1
+  for (int k = 0; k < kFmRows / 4; ++k, piece += 4 * (size_t)p.nver) {
+    if (bq + (wq + 4 * k) / 3 >= p.batch) continue;
+    const int phase = (int)((reinterpret_cast<uintptr_t>(piece) >> 2) & 7u);
+    const float* src = Tw + 4 * k * kFmPitch - phase;
+    float* cr = crw + 4 * k * 8;
+    const bool low = lane < phase;
+    const float v0 = *(low ? cr : src);                              // `first`: garbage below phase, not stored
+    const float v1 = src[32], v2 = src[64], v3 = src[96];
+    float ov = 0.f;
+    if (low) { ov = src[128]; *cr = ov; }
+    float* win = piece - phase + lane;
+    const int lo = first ? phase : 0;                                // floats below belong to the previous band's CTA
+    const int hi = last ? phase + nvalid : 128;                      // the last item also flushes what it would carry
+    if (lane >= lo && lane < hi) win[0] = v0;
+    if (32 + lane < hi) win[32] = v1;
+    if (64 + lane < hi) win[64] = v2;
+    if (96 + lane < hi) win[96] = v3;
+    if (low && 128 + lane < hi) win[128] = ov;
+  }
+}
+
+template <bool kTrace>
 __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const DenseArgs p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -300,24 +343,19 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
   uint8_t* sP = smem;                                                                      // plane ring
   float* sMeta = reinterpret_cast<float*>(smem + kFmPSlots * kFmPlane);                   // kFmMetaSlots meta tiles
   uint8_t* sB = smem + kFmPSlots * kFmPlane + kFmMetaSlots * kDnMetaTile;                 // alpha + pose tile of this CTA's face tile
+  float* sStage = reinterpret_cast<float*>(sB + kDnBSlot);                                // [team][buf][row][kFmPitch]
+  float* sCarry = sStage + kFmTeams * (kFmStage / 4);                                     // [team][48 rows][8]
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  // Work split: CTA = (face tile ft, BAND of consecutive vertex tiles); the bands are the same for every face tile and the
-  // CTAs of one band are neighbours in the grid, so the n_ftiles CTAs that need a given basis tile ask for it at about the
-  // same time and all but the first hit in L2.  (A plain contiguous split of the item list gives every face tile its own
-  // band boundaries: ncu showed the 40 MB basis image read 4.4x from DRAM, and the plane loads -- two planes of look-ahead
-  // deep -- were what the epilogue warps waited for.)  Consecutive items with the same vertex tile would form a VISIT and
-  // share its planes (the machinery below handles runs of any length; walking face tiles in pairs to halve the basis
-  // stream was measured slower: the held planes cost a slot of look-ahead), so here every item is its own visit.
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // Work split: CTA = (face tile ft, BAND of consecutive vertex tiles); the bands are the same for every face tile and
+  // the CTAs of one band are neighbours in the grid, so the CTAs that need a given basis tile ask for it at about the
+  // same time and all but the first hit in L2 (a plain contiguous split of the item list gives every face tile its own
+  // band boundaries: ncu showed the 40 MB basis image read 4.4x from DRAM).
   const int n_bands = max(1, (int)gridDim.x / p.n_ftiles);
   const int band_len = (p.n_vtiles + n_bands - 1) / n_bands;
-  const int my_ft = (int)blockIdx.x % p.n_ftiles, my_band = (int)blockIdx.x / p.n_ftiles;
+  const int ft = (int)blockIdx.x % p.n_ftiles, my_band = (int)blockIdx.x / p.n_ftiles;
   const int vt_lo = min(my_band * band_len, p.n_vtiles), vt_hi = (my_band < n_bands) ? min(vt_lo + band_len, p.n_vtiles) : vt_lo;
-  const int it0 = 0, n_items = vt_hi - vt_lo;
-  auto decode = [&](int it, int& vt, int& ft) {
-    vt = vt_lo + it;
-    ft = my_ft;
-  };
+  const int n_items = vt_hi - vt_lo;                                 // item i = vertex tile vt_lo + i
 
   if (tid == 0) {
     for (int i = 0; i < kFmPSlots; ++i) { mbar_init(smem_u32(&bar_pfull[i]), 1); mbar_init(smem_u32(&bar_pempty[i]), 1); }
@@ -325,7 +363,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
     mbar_init(smem_u32(&bar_bfull), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar_dfull[i]), 1);
-      mbar_init(smem_u32(&bar_dfree[i]), kDnEpiWarps * 16);
+      mbar_init(smem_u32(&bar_dfree[i]), kDnEpiWarps * 32);
     }
     fence_mbar_init();
   }
@@ -336,107 +374,124 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
   const uint32_t tmem = tmem_base_s;
 
   if (warp < kDnEpiWarps) {
-    // ------------------------------ epilogue (two groups of 8 warps, alternate items) -----------------------------
-    // both groups walk the whole item list so that they agree on the visit numbering (meta slot = visit % 4)
-    const int grp = warp >> 3, half = (warp >> 2) & 1;
-    const int lane_v = tid & 127;
-    int visit = -1, cur_vt = -1;
+    // ------------------------------ epilogue: 4 teams x 4 warps, every team works on every item ------------------------
+    const int team = warp >> 2, tt = tid & 127, wq = warp & 3;       // tt = TMEM lane = vertex within the tile
+    const int f0 = team * 16;                                        // first face (within the tile) of this team
+    float* stage = sStage + team * (kFmStage / 4);
+    float* carry = sCarry + team * (kFmCarry / 4);
+    const float* pose_tile = reinterpret_cast<const float*>(sB + kDnBTile);
     for (int i = 0; i < n_items; ++i) {
-      int vt, ft;
-      decode(it0 + i, vt, ft);
-      if (vt != cur_vt) { cur_vt = vt; ++visit; }
-      if ((i & 1) != grp) continue;
-      const bool tr = p.trace != nullptr && blockIdx.x == 0 && (tid & 255) == 0 && i < 64;
-      if (tr) p.trace[(grp * 64 + i) * 8 + 0] = clock64();
-      mbar_wait(smem_u32(&bar_bfull), 0, p.err);                                       // pose tile visible to this thread
-      mbar_wait(smem_u32(&bar_mfull[visit % kFmMetaSlots]), (uint32_t)(visit / kFmMetaSlots) & 1, p.err);   // meta rows visible
-      if (tr) p.trace[(grp * 64 + i) * 8 + 1] = clock64();
-      mbar_wait(smem_u32(&bar_dfull[grp]), (uint32_t)(i >> 1) & 1, p.err);
+      const int vt = vt_lo + i, s = i & 1;
+      const bool tr = kTrace && blockIdx.x == 0 && tid == 0 && i < 64;
+      if (tr) p.trace[i * 8 + 0] = clock64();
+      mbar_wait_inl(smem_u32(&bar_bfull), 0, p.err);                                       // pose tile visible to this thread
+      mbar_wait_inl(smem_u32(&bar_mfull[i % kFmMetaSlots]), (uint32_t)(i / kFmMetaSlots) & 1, p.err);   // meta rows visible
+      const float* m = sMeta + (i % kFmMetaSlots) * (kDnMetaTile / 4);
+      const float ux = m[0 * 128 + tt], uy = m[1 * 128 + tt], uz = m[2 * 128 + tt];
+      const float ox = m[3 * 128 + tt], oy = m[4 * 128 + tt], oz = m[5 * 128 + tt];
+      if (tr) p.trace[i * 8 + 1] = clock64();
+      mbar_wait_inl(smem_u32(&bar_dfull[s]), (uint32_t)(i >> 1) & 1, p.err);
       tc_fence_after_sync();
-      if (tr) p.trace[(grp * 64 + i) * 8 + 2] = clock64();
-      const float* m = sMeta + (visit % kFmMetaSlots) * (kDnMetaTile / 4);
-      const float ux = m[0 * 128 + lane_v], uy = m[1 * 128 + lane_v], uz = m[2 * 128 + lane_v];
-      const float ox = m[3 * 128 + lane_v], oy = m[4 * 128 + lane_v], oz = m[5 * 128 + lane_v];
-      const int v = vt * 128 + lane_v;
+      if (tr) p.trace[i * 8 + 2] = clock64();
+      const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + s * 192 + f0;
+      const bool first = i == 0, last = i == n_items - 1;
+      const bool edge = first || last || (ft + 1) * kDnFaces > p.batch;     // CTA-uniform
+      const int nvalid = min(128, p.nver - vt * 128);
+      float* item_row0 = p.out + ((size_t)(ft * kDnFaces + f0) * 3 + wq) * p.nver + (size_t)vt * 128;   // face f0, row wq
+      uint32_t sx[8], sy[8], sz[8];                                  // 8 faces x 3 coordinates at a time (96-register budget)
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        tmem_ld8_async(trow + h * 8, sx);
+        tmem_ld8_async(trow + 64 + h * 8, sy);
+        tmem_ld8_async(trow + 128 + h * 8, sz);
+        tmem_wait_ld();
+        if (h == 1) {                                                // accumulators are in registers: the buffer is free
+          tc_fence_before_sync();
+          mbar_arrive(smem_u32(&bar_dfree[s]));
+          if (tr) p.trace[i * 8 + 3] = clock64();
+        }
 #pragma unroll
-      for (int rnd = 0; rnd < 2; ++rnd) {                            // 2 x 16 faces per thread
-        const int fofs = half * 32 + rnd * 16;
-        const float* pose = reinterpret_cast<const float*>(sB + kDnBTile) + fofs * kDnPoseStride;
-        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + grp * 192 + fofs;
-        float sx[16], sy[16], sz[16];
-        tmem_ld16x3(trow, trow + 64, trow + 128, sx, sy, sz);
-        if (tr) p.trace[(grp * 64 + i) * 8 + 3 + rnd] = clock64();
-        const int b0 = ft * kDnFaces + fofs;
-        if (v < p.nver) {
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const int sr = 2 * h + s2;
+          float* T = stage + s2 * (kFmRows * kFmPitch);
+          const int bq = ft * kDnFaces + f0 + sr * kFmSubFaces;      // first face (batch index) of the sub-round
+          // ---- stage: row (face, coordinate), position = this thread's vertex (no shift: the reader applies the phase)
 #pragma unroll
-          for (int f = 0; f < 16; ++f) {
-            if (b0 + f < p.batch) {
-              const float4 r0 = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride);
-              const float4 r1 = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride + 4);
-              const float4 r2 = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride + 8);
-              const float X = fmaf(sx[f], ox, ux), Y = fmaf(sy[f], oy, uy), Z = fmaf(sz[f], oz, uz);
-              float vx = fmaf(r0.x, X, fmaf(r0.y, Y, r0.z * Z)) + r0.w;
-              float vy = fmaf(r1.x, X, fmaf(r1.y, Y, r1.z * Z)) + r1.w;
-              float vz = fmaf(r2.x, X, fmaf(r2.y, Y, r2.z * Z)) + r2.w;
-              if (p.transform) vy = (float)(kImg + 1) - vy;          // model_building.py:129,137
-              if (p.affine) {                                        // utils/inference.py:131-136, numpy's fp32 mul then add
-                const float4 q = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride + 12);
-                vx = __fadd_rn(__fmul_rn(vx, q.x), q.y);
-                vy = __fadd_rn(__fmul_rn(vy, q.z), q.w);
-                vz = __fmul_rn(vz, pose[f * kDnPoseStride + 16]);
-              }
-              float* o = p.out + (size_t)(b0 + f) * 3 * p.nver + v;
-              if (p.stream_stores) { __stcs(o, vx); __stcs(o + p.nver, vy); __stcs(o + 2 * (size_t)p.nver, vz); }
-              else { o[0] = vx; o[p.nver] = vy; o[2 * (size_t)p.nver] = vz; }
+          for (int fl = 0; fl < kFmSubFaces; ++fl) {
+            const int f8 = s2 * kFmSubFaces + fl;
+            const float* pose = pose_tile + (f0 + sr * kFmSubFaces + fl) * kDnPoseStride;
+            const float4 r0 = *reinterpret_cast<const float4*>(pose);
+            const float4 r1 = *reinterpret_cast<const float4*>(pose + 4);
+            const float4 r2 = *reinterpret_cast<const float4*>(pose + 8);
+            const float X = fmaf(__uint_as_float(sx[f8]), ox, ux), Y = fmaf(__uint_as_float(sy[f8]), oy, uy),
+                        Z = fmaf(__uint_as_float(sz[f8]), oz, uz);
+            float vx = fmaf(r0.x, X, fmaf(r0.y, Y, r0.z * Z)) + r0.w;
+            float vy = fmaf(r1.x, X, fmaf(r1.y, Y, r1.z * Z)) + r1.w;
+            float vz = fmaf(r2.x, X, fmaf(r2.y, Y, r2.z * Z)) + r2.w;
+            if (p.transform) vy = (float)(kImg + 1) - vy;            // model_building.py:129,137
+            if (p.affine) {                                          // utils/inference.py:131-136, numpy's fp32 mul then add
+              const float4 q = *reinterpret_cast<const float4*>(pose + 12);
+              vx = __fadd_rn(__fmul_rn(vx, q.x), q.y);
+              vy = __fadd_rn(__fmul_rn(vy, q.z), q.w);
+              vz = __fmul_rn(vz, pose[16]);
             }
+            T[(fl * 3 + 0) * kFmPitch + tt] = vx;
+            T[(fl * 3 + 1) * kFmPitch + tt] = vy;
+            T[(fl * 3 + 2) * kFmPitch + tt] = vz;
           }
+          asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory");
+          // ---- write out: warp wq takes rows wq + 4k.  Window position pos (0 = the sector boundary at or below the row
+          // piece) holds vertex pos - phase of this item, or, below phase, the previous item's overhang.  Lane j stores
+          // positions j, 32 + j, 64 + j, 96 + j: every warp store is four whole aligned sectors.
+          const float* Tw = T + wq * kFmPitch + lane;
+          float* crw = carry + (sr * kFmRows + wq) * 8 + lane;
+          float* piece = item_row0 + (size_t)(sr * kFmRows) * p.nver;   // row wq of the sub-round, first float of the piece
+          if (!edge) {
+#pragma unroll
+            for (int k = 0; k < kFmRows / 4; ++k, piece += 4 * (size_t)p.nver) {
+              const int phase = (int)((reinterpret_cast<uintptr_t>(piece) >> 2) & 7u);
+              const float* src = Tw + 4 * k * kFmPitch - phase;
+              float* cr = crw + 4 * k * 8;
+              const bool low = lane < phase;
+              const float v0 = *(low ? cr : src);
+              const float v1 = src[32], v2 = src[64], v3 = src[96];
+              if (low) *cr = src[128];                               // this item's overhang (vertices 128 - phase .. 127)
+              float* win = piece - phase + lane;                     // plain stores: .cs needs a policy descriptor per store
+              win[0] = v0; win[32] = v1; win[64] = v2; win[96] = v3;
+            }
+          } else {                                                   // first / last item of the band, ragged face tile
+            fm_write_edge(p, Tw, crw, piece, bq, wq, lane, first, last, nvalid);
+          }
+          // the other staging buffer is written next; this one again two sub-rounds later, after the next team barrier
         }
       }
-      if (tr) p.trace[(grp * 64 + i) * 8 + 5] = clock64();
-      tc_fence_before_sync();
-      mbar_arrive(smem_u32(&bar_dfree[grp]));
+      if (tr) p.trace[i * 8 + 4] = clock64();
     }
   } else if (warp == kDnEpiWarps) {
     // ------------------------------ loader + MMA issuer (converged warp, elect.sync) ------------------------------
     const uint32_t idesc = make_idesc_f16(128, kDnFaces);
     const uint32_t d_hi = smem_desc_hi(128);
-    // planes are numbered per VISIT (q = 3 * visit + coordinate); the prefetcher scans the item list on its own
-    int next_plane = 0;                                               // next plane to request
-    int pre_i = 0, pre_vt = -1;                                       // prefetcher: next unscanned item, vertex tile of the visit being requested
-    const uint64_t keep = l2_policy_evict_last();                     // the basis image is re-read once per face-tile pair
-    auto dfree_wait = [&](int j) { mbar_wait(smem_u32(&bar_dfree[j & 1]), (uint32_t)(j >> 1) & 1, p.err); };
-    // Request planes up to (and including) `upto`.  Plane q reuses the slot of plane q - kFmPSlots, whose MMAs must be complete
-    // (bar_pempty, consumed strictly in order).  The meta rows of visit v go to slot v % 4, last read by the epilogue of
-    // an item at least three items back, which the TMEM hand-over (dfree of item i - 2) has already waited for.
+    int next_plane = 0;                                               // next plane to request (plane q = 3 * item + coordinate)
+    const uint64_t keep = l2_policy_evict_last();                     // the basis image is re-read once per face tile
+    // Request planes up to (and including) `upto`.  Plane q reuses the slot of plane q - kFmPSlots, whose MMAs must be
+    // complete (bar_pempty, consumed strictly in order).  The meta rows of item v go to slot v % 4, last read by the
+    // epilogue of item v - 4 BEFORE it released its accumulator buffer, which the issuer has waited for by then.
     auto request_planes = [&](int upto) {
+      upto = min(upto, 3 * n_items - 1);
       for (; next_plane <= upto; ++next_plane) {
         const int q = next_plane, slot = q % kFmPSlots, v = q / 3, c = q - 3 * v;
-        if (c == 0) {                                                // first plane of a new visit: find its vertex tile
-          if (pre_i >= n_items) return;                               // no more visits
-          int vt, ft;
-          decode(it0 + pre_i, vt, ft);
-          pre_vt = vt;
-          for (++pre_i; pre_i < n_items; ++pre_i) {                   // skip the other items of this visit
-            int vt2, ft2;
-            decode(it0 + pre_i, vt2, ft2);
-            if (vt2 != vt) break;
-          }
-        }
-        if (q >= kFmPSlots) mbar_wait(smem_u32(&bar_pempty[slot]), (uint32_t)(q / kFmPSlots - 1) & 1, p.err);
+        if (q >= kFmPSlots) mbar_wait_inl(smem_u32(&bar_pempty[slot]), (uint32_t)(q / kFmPSlots - 1) & 1, p.err);
         if (elect_one()) {
           mbar_expect_tx(smem_u32(&bar_pfull[slot]), kFmPlane);
-          // SYN_FM_SPLIT bulk copies per plane on the same barrier (measured: a single 32 KB copy takes ~4 us from request
-          // to completion while the output stream saturates the memory system, and that latency -- three planes in
-          // flight -- is what paces the kernel)
 #pragma unroll
           for (int part = 0; part < SYN_FM_SPLIT; ++part)
             bulk_g2s_hint(smem_u32(sP + slot * kFmPlane + part * (kFmPlane / SYN_FM_SPLIT)),
-                          p.basis_img + (size_t)pre_vt * kDnATile + (size_t)c * kFmPlane + part * (kFmPlane / SYN_FM_SPLIT),
+                          p.basis_img + (size_t)(vt_lo + v) * kDnATile + (size_t)c * kFmPlane + part * (kFmPlane / SYN_FM_SPLIT),
                           kFmPlane / SYN_FM_SPLIT, smem_u32(&bar_pfull[slot]), keep);
           if (c == 0) {
             const int ms = v % kFmMetaSlots;
             mbar_expect_tx(smem_u32(&bar_mfull[ms]), kDnMetaTile);
-            bulk_g2s_hint(smem_u32(sMeta + ms * (kDnMetaTile / 4)), p.meta + (size_t)pre_vt * 6 * 128, kDnMetaTile,
+            bulk_g2s_hint(smem_u32(sMeta + ms * (kDnMetaTile / 4)), p.meta + (size_t)(vt_lo + v) * 6 * 128, kDnMetaTile,
                           smem_u32(&bar_mfull[ms]), keep);
           }
         }
@@ -446,39 +501,25 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
     if (n_items > 0) {                                               // alpha + pose of this CTA's face tile: once
       if (elect_one()) {
         mbar_expect_tx(smem_u32(&bar_bfull), kDnBSlot);
-        bulk_g2s(smem_u32(sB), p.alpha_img + (size_t)my_ft * kDnBTile, kDnBTile, smem_u32(&bar_bfull));
-        bulk_g2s(smem_u32(sB + kDnBTile), p.pose + (size_t)my_ft * kDnFaces * kDnPoseStride, kDnPoseTile, smem_u32(&bar_bfull));
+        bulk_g2s(smem_u32(sB), p.alpha_img + (size_t)ft * kDnBTile, kDnBTile, smem_u32(&bar_bfull));
+        bulk_g2s(smem_u32(sB + kDnBTile), p.pose + (size_t)ft * kDnFaces * kDnPoseStride, kDnPoseTile, smem_u32(&bar_bfull));
       }
       __syncwarp();
     }
-    request_planes(kFmPSlots - 2);                                   // planes 0..4 in flight before the first MMA
-    int visit = -1, cur_vt = -1;
+    request_planes(kFmPSlots - 1);                                   // planes 0..3 in flight before the first MMA
+    const uint32_t b_lo = smem_desc_lo(smem_u32(sB), 1024);
     for (int i = 0; i < n_items; ++i) {
-      int vt, ft;
-      decode(it0 + i, vt, ft);
-      const bool new_visit = vt != cur_vt;
-      if (new_visit) { cur_vt = vt; ++visit; }
-      bool last_of_visit = true;
-      if (i + 1 < n_items) {
-        int vt2, ft2;
-        decode(it0 + i + 1, vt2, ft2);
-        last_of_visit = vt2 != vt;
-      }
       const int s = i & 1;
-      const bool tr = p.trace != nullptr && blockIdx.x == 0 && (tid & 31) == 0 && i < 64;
+      const bool tr = kTrace && blockIdx.x == 0 && lane == 0 && i < 64;
       if (tr) p.trace[(128 + i) * 8 + 0] = clock64();
-      mbar_wait(smem_u32(&bar_bfull), 0, p.err);
+      if (i == 0) mbar_wait_inl(smem_u32(&bar_bfull), 0, p.err);
+      if (i >= 2) mbar_wait_inl(smem_u32(&bar_dfree[s]), (uint32_t)((i - 2) >> 1) & 1, p.err);   // buffer s read out
       if (tr) p.trace[(128 + i) * 8 + 1] = clock64();
-      if (i >= 2) dfree_wait(i - 2);                                 // TMEM buffer s drained
-      if (tr) p.trace[(128 + i) * 8 + 2] = clock64();
-      const uint32_t b_lo = smem_desc_lo(smem_u32(sB), 1024);
       for (int c = 0; c < 3; ++c) {
-        const int q = 3 * visit + c, slot = q % kFmPSlots;
-        // keep up to four planes ahead of the MMAs in flight -- but never ask for a slot whose current plane this visit
-        // still needs (a multi-item visit releases its planes with its last item)
-        request_planes(last_of_visit ? q + kFmPSlots - 2 : min(q + kFmPSlots - 2, 3 * visit + kFmPSlots - 1));
-        if (new_visit) mbar_wait(smem_u32(&bar_pfull[slot]), (uint32_t)(q / kFmPSlots) & 1, p.err);
-        if (tr) p.trace[(128 + i) * 8 + 3 + c] = clock64();            // plane c landed (and requests up to q+2 issued)
+        const int q = 3 * i + c, slot = q % kFmPSlots;
+        request_planes(q + kFmPSlots - 2);                           // the slot freed by the previous plane's MMAs
+        mbar_wait_inl(smem_u32(&bar_pfull[slot]), (uint32_t)(q / kFmPSlots) & 1, p.err);
+        if (tr) p.trace[(128 + i) * 8 + 2 + c] = clock64();            // plane c landed
         tc_fence_after_sync();
         const uint32_t a_lo = smem_desc_lo(smem_u32(sP + slot * kFmPlane), 2048);
         if (elect_one()) {
@@ -491,13 +532,12 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
               umma_f16(tmem + s * 192 + c * 64, desc64(d_hi, a_lo + ((a_off + ks * 4096) >> 4)),
                        desc64(d_hi, b_lo + ((b_off + ks * 2048) >> 4)), idesc, (pass > 0 || ks > 0) ? 1u : 0u);
           }
-          if (last_of_visit) umma_commit(smem_u32(&bar_pempty[slot]));   // the plane may be overwritten once these MMAs are done
+          umma_commit(smem_u32(&bar_pempty[slot]));                  // the plane may be overwritten once these MMAs are done
           if (c == 2) umma_commit(smem_u32(&bar_dfull[s]));
         }
         __syncwarp();
       }
-      if (tr) p.trace[(128 + i) * 8 + 6] = clock64();                  // MMAs of the item issued
-      if (tr) p.trace[(128 + i) * 8 + 7] = clock64();
+      if (tr) p.trace[(128 + i) * 8 + 5] = clock64();                  // MMAs of the item issued
     }
   }
   tc_fence_before_sync();

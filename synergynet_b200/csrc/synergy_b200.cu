@@ -379,7 +379,9 @@ int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense,
   if (dense && !fm_off) {
     // grid = face tiles x vertex bands (see the kernel): as many whole bands as fit the SMs
     const int n_bands = std::max(1, h->sm_count / a.n_ftiles);
-    dense_recon_fm_kernel<<<a.n_ftiles * std::min(n_bands, a.n_vtiles), kDnThreads, kFmSmem, st>>>(a);
+    const int grid = a.n_ftiles * std::min(n_bands, a.n_vtiles);
+    if (a.trace != nullptr) dense_recon_fm_kernel<true><<<grid, kDnThreads, kFmSmem, st>>>(a);
+    else dense_recon_fm_kernel<false><<<grid, kDnThreads, kFmSmem, st>>>(a);
     SYN_LAUNCH_CHECK("dense_recon_fm_kernel");
     mark(h, st, "dense_recon_fm_kernel");
     if (a.trace != nullptr) {                                                  // debug only: synchronous dump
@@ -949,7 +951,8 @@ int syn_commit(syn_handle_t* h) {
       if ((rc = upload(&h->d_dn_meta, meta)) != SYN_OK) return rc;
     }
     SYN_CUDA(cudaFuncSetAttribute(dense_recon_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDnSmem));
-    SYN_CUDA(cudaFuncSetAttribute(dense_recon_fm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmSmem));
+    SYN_CUDA(cudaFuncSetAttribute(dense_recon_fm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmSmem));
+    SYN_CUDA(cudaFuncSetAttribute(dense_recon_fm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmSmem));
   }
   h->committed = true;
   return SYN_OK;

@@ -85,7 +85,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // Slow path: plain try_wait polling (a suspend-time hint was tried and measured ~6 % slower end to end:
 // wake-up latency matters more than the issue slots the polling warps take).  The sticky flag (a global
 // load) and the wall clock are only looked at every 256 polls.
-__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* err_flag) {
+__device__ __forceinline__ bool mbar_wait_spin(uint32_t bar, uint32_t parity, int* err_flag) {
   const uint64_t t0 = globaltimer_ns();
   for (uint32_t it = 1;; ++it) {
     if (mbar_try_wait(bar, parity)) return true;
@@ -99,9 +99,26 @@ __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* 
     }
   }
 }
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* err_flag) {
+  return mbar_wait_spin(bar, parity, err_flag);
+}
+// SYN_MBAR_INLINE: a real call in a kernel makes ptxas keep the global-memory descriptor in a vector register and copy it
+// to a uniform register pair (2 x R2UR) in front of every LDG / STG; the spin loop inlined costs less code than that.
+#ifndef SYN_MBAR_INLINE
+#define SYN_MBAR_INLINE 0
+#endif
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err_flag) {
   if (mbar_try_wait(bar, parity)) return true;
+#if SYN_MBAR_INLINE
+  return mbar_wait_spin(bar, parity, err_flag);
+#else
   return mbar_wait_slow(bar, parity, err_flag);
+#endif
+}
+// always-inline flavour for kernels whose hot loop is made of global stores (dense_recon_fm_kernel)
+__device__ __forceinline__ bool mbar_wait_inl(uint32_t bar, uint32_t parity, int* err_flag) {
+  if (mbar_try_wait(bar, parity)) return true;
+  return mbar_wait_spin(bar, parity, err_flag);
 }
 
 // ---- proxies / fences ----------------------------------------------------------------------------
