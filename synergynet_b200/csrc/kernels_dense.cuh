@@ -38,45 +38,54 @@ constexpr int kDnThreads = (kDnEpiWarps + 1) * 32;
 
 // ---- pre-pass -----------------------------------------------------------------------------------------
 // alpha image: per face tile [hi plane 64 faces x 64 k][lo plane], canonical K-major (SBO 128, LBO 1024);
-// pose: (tiles*64, 12) fp32 rows [R|t] (model_building.py:27-29), zero rows past the batch.
-__global__ void __launch_bounds__(64) dense_alpha_kernel(const float* __restrict__ params, const float* __restrict__ mean,
-                                                         const float* __restrict__ stdv, const float* __restrict__ ascale,
-                                                         uint8_t* __restrict__ aimg, float* __restrict__ pose, int batch,
-                                                         int whitening, const float* __restrict__ roi5) {
-  const int f = threadIdx.x, tile = blockIdx.x;
+// pose: (tiles*64, kDnPoseStride) fp32 rows [R|t] (model_building.py:27-29) + crop -> image affine, identity / zero
+// rows past the batch.  One thread per (face, group of 8 coefficients): a 512-thread CTA per face tile, every uint4 of
+// the image and every float4 of the pose rows is produced by its own thread (the first version -- one thread per face
+// walking all 62 parameters -- took as long as a tenth of the dense reconstruction it feeds).
+constexpr int kDnAlphaThreads = kDnFaces * (kDnK / 8);
+__global__ void __launch_bounds__(kDnAlphaThreads) dense_alpha_kernel(const float* __restrict__ params, const float* __restrict__ mean,
+                                                                      const float* __restrict__ stdv, const float* __restrict__ ascale,
+                                                                      uint8_t* __restrict__ aimg, float* __restrict__ pose, int batch,
+                                                                      int whitening, const float* __restrict__ roi5) {
+  // the reconstruction kernel may start its prologue (barriers, TMEM, basis planes) now; it waits for this grid
+  // (griddepcontrol.wait) before it touches the alpha image or the pose rows
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int f = threadIdx.x & (kDnFaces - 1), kg = threadIdx.x / kDnFaces, tile = blockIdx.x;
   const int b = tile * kDnFaces + f;
-  float pr[kNumParams];
-#pragma unroll
-  for (int j = 0; j < kNumParams; ++j) {
+  const bool live = b < batch;
+  auto param = [&](int j) {                                  // de-whitened parameter j of face b (model_building.py:117)
     float v = 0.f;
-    if (b < batch) {
+    if (live) {
       v = params[(size_t)b * kNumParams + j];
-      if (whitening) v = v * stdv[j] + mean[j];          // model_building.py:117
+      if (whitening) v = v * stdv[j] + mean[j];
     }
-    pr[j] = v;
-  }
-  float* prow = pose + (size_t)(tile * kDnFaces + f) * kDnPoseStride;
-#pragma unroll
-  for (int j = 0; j < 12; ++j) prow[j] = pr[j];
-  // crop -> image affine of _predict_vertices (utils/inference.py:127-138): x*kx+sx, y*ky+sy, z*kz (identity if absent)
-  const bool has = roi5 != nullptr && b < batch;
-  prow[12] = has ? roi5[(size_t)b * 5 + 0] : 1.f; prow[13] = has ? roi5[(size_t)b * 5 + 1] : 0.f;
-  prow[14] = has ? roi5[(size_t)b * 5 + 2] : 1.f; prow[15] = has ? roi5[(size_t)b * 5 + 3] : 0.f;
-  prow[16] = has ? roi5[(size_t)b * 5 + 4] : 1.f; prow[17] = prow[18] = prow[19] = 0.f;
-  uint8_t* hi = aimg + (size_t)tile * kDnBTile + (f >> 3) * 128 + (f & 7) * 16;
-#pragma unroll
-  for (int kg = 0; kg < kDnK / 8; ++kg) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k0 = kg * 8 + 2 * j, k1 = k0 + 1;
-      const float a0 = (k0 < kNumAlpha) ? pr[12 + k0] * ascale[k0] : 0.f;
-      const float a1 = (k1 < kNumAlpha) ? pr[12 + k1] * ascale[k1] : 0.f;
-      tc::split2_f16(a0, a1, h[j], l[j]);
+    return v;
+  };
+  // pose row: float4 #kg of [R|t] (kg 0..2), crop -> image affine kx,sx,ky,sy (3), kz,0,0,0 (4)
+  // (utils/inference.py:127-138: x*kx+sx, y*ky+sy, z*kz; identity if absent)
+  if (kg < kDnPoseStride / 4) {
+    float4 v;
+    if (kg < 3) {
+      v = make_float4(param(4 * kg), param(4 * kg + 1), param(4 * kg + 2), param(4 * kg + 3));
+    } else {
+      const bool has = roi5 != nullptr && live;
+      const float* r = roi5 + (size_t)b * 5;
+      if (kg == 3) v = make_float4(has ? r[0] : 1.f, has ? r[1] : 0.f, has ? r[2] : 1.f, has ? r[3] : 0.f);
+      else v = make_float4(has ? r[4] : 1.f, 0.f, 0.f, 0.f);
     }
-    *reinterpret_cast<uint4*>(hi + kg * 1024) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(hi + kDnBPlane + kg * 1024) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<float4*>(pose + (size_t)(tile * kDnFaces + f) * kDnPoseStride + 4 * kg) = v;
   }
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k0 = kg * 8 + 2 * j, k1 = k0 + 1;
+    const float a0 = (k0 < kNumAlpha) ? param(12 + k0) * ascale[k0] : 0.f;
+    const float a1 = (k1 < kNumAlpha) ? param(12 + k1) * ascale[k1] : 0.f;
+    tc::split2_f16(a0, a1, h[j], l[j]);
+  }
+  uint8_t* hi = aimg + (size_t)tile * kDnBTile + kg * 1024 + f * 16;   // (f >> 3) * 128 + (f & 7) * 16 = f * 16
+  *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(hi + kDnBPlane) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 struct DenseArgs {
@@ -169,9 +178,9 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
               const float4 r1 = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride + 4);
               const float4 r2 = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride + 8);
               const float X = fmaf(sx[f], ox, ux), Y = fmaf(sy[f], oy, uy), Z = fmaf(sz[f], oz, uz);
-              float vx = fmaf(r0.x, X, fmaf(r0.y, Y, r0.z * Z)) + r0.w;
-              float vy = fmaf(r1.x, X, fmaf(r1.y, Y, r1.z * Z)) + r1.w;
-              float vz = fmaf(r2.x, X, fmaf(r2.y, Y, r2.z * Z)) + r2.w;
+              float vx = fmaf(r0.x, X, fmaf(r0.y, Y, fmaf(r0.z, Z, r0.w)));
+              float vy = fmaf(r1.x, X, fmaf(r1.y, Y, fmaf(r1.z, Z, r1.w)));
+              float vz = fmaf(r2.x, X, fmaf(r2.y, Y, fmaf(r2.z, Z, r2.w)));
               if (p.transform) vy = (float)(kImg + 1) - vy;          // model_building.py:129,137
               if (p.affine) {                                        // utils/inference.py:131-136, numpy's fp32 mul then add
                 const float4 q = *reinterpret_cast<const float4*>(pose + f * kDnPoseStride + 12);
@@ -211,6 +220,7 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_tc_kernel(const Den
     };
     int cur_vt = -1;
     const int vt0 = it0 / p.n_ftiles;
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // alpha image / pose rows come from the pre-pass
     for (int k = 0; k < kDnBSlots - 1; ++k)
       if (it0 + k < it1) load_b(it0 + k, k);
     for (int it = it0, i = 0; it < it1; ++it, ++i) {
@@ -332,7 +342,7 @@ __device__ __forceinline__ void fm_write_edge(const DenseArgs& p, const float* T
   }
 }
 
-template <bool kTrace>
+template <bool kTrace, bool kAffine>
 __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const DenseArgs p) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -416,20 +426,26 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
           float* T = stage + s2 * (kFmRows * kFmPitch);
           const int bq = ft * kDnFaces + f0 + sr * kFmSubFaces;      // first face (batch index) of the sub-round
           // ---- stage: row (face, coordinate), position = this thread's vertex (no shift: the reader applies the phase)
+          const float* pose = pose_tile + (f0 + sr * kFmSubFaces) * kDnPoseStride;
+          float4 n0 = *reinterpret_cast<const float4*>(pose);       // [R|t] rows, loaded one face ahead of their use
+          float4 n1 = *reinterpret_cast<const float4*>(pose + 4);
+          float4 n2 = *reinterpret_cast<const float4*>(pose + 8);
 #pragma unroll
-          for (int fl = 0; fl < kFmSubFaces; ++fl) {
+          for (int fl = 0; fl < kFmSubFaces; ++fl, pose += kDnPoseStride) {
             const int f8 = s2 * kFmSubFaces + fl;
-            const float* pose = pose_tile + (f0 + sr * kFmSubFaces + fl) * kDnPoseStride;
-            const float4 r0 = *reinterpret_cast<const float4*>(pose);
-            const float4 r1 = *reinterpret_cast<const float4*>(pose + 4);
-            const float4 r2 = *reinterpret_cast<const float4*>(pose + 8);
+            const float4 r0 = n0, r1 = n1, r2 = n2;
+            if (fl + 1 < kFmSubFaces) {
+              n0 = *reinterpret_cast<const float4*>(pose + kDnPoseStride);
+              n1 = *reinterpret_cast<const float4*>(pose + kDnPoseStride + 4);
+              n2 = *reinterpret_cast<const float4*>(pose + kDnPoseStride + 8);
+            }
             const float X = fmaf(__uint_as_float(sx[f8]), ox, ux), Y = fmaf(__uint_as_float(sy[f8]), oy, uy),
                         Z = fmaf(__uint_as_float(sz[f8]), oz, uz);
-            float vx = fmaf(r0.x, X, fmaf(r0.y, Y, r0.z * Z)) + r0.w;
-            float vy = fmaf(r1.x, X, fmaf(r1.y, Y, r1.z * Z)) + r1.w;
-            float vz = fmaf(r2.x, X, fmaf(r2.y, Y, r2.z * Z)) + r2.w;
+            float vx = fmaf(r0.x, X, fmaf(r0.y, Y, fmaf(r0.z, Z, r0.w)));
+            float vy = fmaf(r1.x, X, fmaf(r1.y, Y, fmaf(r1.z, Z, r1.w)));
+            float vz = fmaf(r2.x, X, fmaf(r2.y, Y, fmaf(r2.z, Z, r2.w)));
             if (p.transform) vy = (float)(kImg + 1) - vy;            // model_building.py:129,137
-            if (p.affine) {                                          // utils/inference.py:131-136, numpy's fp32 mul then add
+            if (kAffine) {                                           // utils/inference.py:131-136, numpy's fp32 mul then add
               const float4 q = *reinterpret_cast<const float4*>(pose + 12);
               vx = __fadd_rn(__fmul_rn(vx, q.x), q.y);
               vy = __fadd_rn(__fmul_rn(vy, q.z), q.w);
@@ -498,6 +514,9 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
         __syncwarp();
       }
     };
+    request_planes(kFmPSlots - 1);                                   // planes 0..3 in flight before the first MMA
+    // programmatic dependent launch: everything above overlaps the pre-pass; its output is first touched here
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (n_items > 0) {                                               // alpha + pose of this CTA's face tile: once
       if (elect_one()) {
         mbar_expect_tx(smem_u32(&bar_bfull), kDnBSlot);
@@ -506,7 +525,6 @@ __global__ void __launch_bounds__(kDnThreads, 1) dense_recon_fm_kernel(const Den
       }
       __syncwarp();
     }
-    request_planes(kFmPSlots - 1);                                   // planes 0..3 in flight before the first MMA
     const uint32_t b_lo = smem_desc_lo(smem_u32(sB), 1024);
     for (int i = 0; i < n_items; ++i) {
       const int s = i & 1;

@@ -340,6 +340,23 @@ int run_backbone(syn_handle* h, const float* x, int batch, float* params, float*
   return SYN_OK;
 }
 
+// Reconstruction kernels are launched with programmatic stream serialization: they start while dense_alpha_kernel
+// (which signals griddepcontrol.launch_dependents at its top) is still running, set up barriers / TMEM, stream in
+// basis data, and execute griddepcontrol.wait before the first access to the pre-pass' output.
+static cudaError_t launch_after_prepass(void (*kernel)(DenseArgs), int grid, int smem, cudaStream_t st, const DenseArgs& a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kDnThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense, int whitening, int transform,
                        float* out, cudaStream_t st, const float* roi5 = nullptr) {
   const int n_ftiles = (batch + kDnFaces - 1) / kDnFaces;
@@ -351,7 +368,7 @@ int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense,
     SYN_CUDA(cudaMalloc(&h->d_pose, (size_t)n_ftiles * kDnPoseTile));
     h->recon_ftiles = n_ftiles;
   }
-  dense_alpha_kernel<<<n_ftiles, 64, 0, st>>>(params, h->d_mean, h->d_std, h->d_ascale, h->d_alpha_img, h->d_pose, batch,
+  dense_alpha_kernel<<<n_ftiles, kDnAlphaThreads, 0, st>>>(params, h->d_mean, h->d_std, h->d_ascale, h->d_alpha_img, h->d_pose, batch,
                                              whitening, roi5);
   SYN_LAUNCH_CHECK("dense_alpha_kernel");
   mark(h, st, "dense_alpha_kernel");
@@ -380,8 +397,9 @@ int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense,
     // grid = face tiles x vertex bands (see the kernel): as many whole bands as fit the SMs
     const int n_bands = std::max(1, h->sm_count / a.n_ftiles);
     const int grid = a.n_ftiles * std::min(n_bands, a.n_vtiles);
-    if (a.trace != nullptr) dense_recon_fm_kernel<true><<<grid, kDnThreads, kFmSmem, st>>>(a);
-    else dense_recon_fm_kernel<false><<<grid, kDnThreads, kFmSmem, st>>>(a);
+    if (a.trace != nullptr) SYN_CUDA(launch_after_prepass(dense_recon_fm_kernel<true, true>, grid, kFmSmem, st, a));
+    else if (a.affine) SYN_CUDA(launch_after_prepass(dense_recon_fm_kernel<false, true>, grid, kFmSmem, st, a));
+    else SYN_CUDA(launch_after_prepass(dense_recon_fm_kernel<false, false>, grid, kFmSmem, st, a));
     SYN_LAUNCH_CHECK("dense_recon_fm_kernel");
     mark(h, st, "dense_recon_fm_kernel");
     if (a.trace != nullptr) {                                                  // debug only: synchronous dump
@@ -399,7 +417,7 @@ int run_reconstruct_tc(syn_handle* h, const float* params, int batch, int dense,
     }
     return SYN_OK;
   }
-  dense_recon_tc_kernel<<<std::min(items, h->sm_count), kDnThreads, kDnSmem, st>>>(a);
+  SYN_CUDA(launch_after_prepass(dense_recon_tc_kernel, std::min(items, h->sm_count), kDnSmem, st, a));
   SYN_LAUNCH_CHECK("dense_recon_tc_kernel");
   mark(h, st, "dense_recon_tc_kernel");
   return SYN_OK;
@@ -951,8 +969,9 @@ int syn_commit(syn_handle_t* h) {
       if ((rc = upload(&h->d_dn_meta, meta)) != SYN_OK) return rc;
     }
     SYN_CUDA(cudaFuncSetAttribute(dense_recon_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDnSmem));
-    SYN_CUDA(cudaFuncSetAttribute(dense_recon_fm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmSmem));
-    SYN_CUDA(cudaFuncSetAttribute(dense_recon_fm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmSmem));
+    SYN_CUDA(cudaFuncSetAttribute(dense_recon_fm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmSmem));
+    SYN_CUDA(cudaFuncSetAttribute(dense_recon_fm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmSmem));
+    SYN_CUDA(cudaFuncSetAttribute(dense_recon_fm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmSmem));
   }
   h->committed = true;
   return SYN_OK;
