@@ -146,6 +146,14 @@ int syn_forward_landmarks_u8(syn_handle_t* h, const uint8_t* x_u8_dev, int batch
                              float* lmk_dev, void* stream);
 int syn_forward_landmarks_host_u8(syn_handle_t* h, const uint8_t* x_u8_host, int batch,
                                   float* params62_host, float* lmk_host);
+/* The same call split in two, for a loader loop that keeps the GPU busy (benchmark.py:119-132 iterates a DataLoader
+ * with pinned memory and non_blocking copies): submit enqueues H2D + forward + landmarks + D2H and returns a ticket;
+ * syn_host_wait(ticket) returns once lmk_host / params62_host of that call are filled.  Up to two calls may be in flight
+ * (the second one's copies run under the first one's kernels); a third submit waits for the oldest.  The host buffers
+ * (pinned) must stay valid until their ticket has been waited for.  x_is_u8: 0 = fp32 normalised crops, 1 = raw uint8. */
+int syn_forward_landmarks_host_submit(syn_handle_t* h, const void* x_host, int x_is_u8, int batch, float* params62_host,
+                                      float* lmk_host, int* ticket);
+int syn_host_wait(syn_handle_t* h, int ticket);
 
 /* ---- PointNet refinement heads and the training-forward losses -------------
  * net 0 = MLP_for (backbone_nets/pointnet_backbone.py:7-64): layer 0..8 = conv1..conv9 (+bn1..bn9);

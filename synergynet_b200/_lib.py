@@ -53,6 +53,8 @@ SIGNATURES = {
     'syn_forward_landmarks_host': (_I, [_P, _F, _I, _F, _F]),
     'syn_forward_landmarks_u8': (_I, [_P, _F, _I, _F, _F, _P]),
     'syn_forward_landmarks_host_u8': (_I, [_P, _F, _I, _F, _F]),
+    'syn_forward_landmarks_host_submit': (_I, [_P, _F, _I, _I, _F, _F, C.POINTER(C.c_int)]),
+    'syn_host_wait': (_I, [_P, _I]),
     'syn_pointnet_set_layer': (_I, [_P, _I, _I, _F, _I, _I, _F, _F, _F, _F, _F, C.c_float]),
     'syn_pointnet_commit': (_I, [_P, _I]),
     'syn_mlp_for': (_I, [_P, _F, _F, _F, _I, _F, _F, _P]),

@@ -44,6 +44,7 @@ class Engine:
         # (nn.DataParallel replicas use one engine per device, but user threads may share a model) and order
         # consecutive calls that arrive on different CUDA streams with an event.
         self._lock = threading.RLock()
+        self._host_inflight: Dict[int, tuple] = {}     # ticket -> tensors of a submitted host call (kept alive)
         self._last_stream = None
         self._last_event = None
 
@@ -130,6 +131,8 @@ class Engine:
         st = torch.cuda.current_stream(self.device)
         if torch.cuda.is_current_stream_capturing():
             return st.cuda_stream            # CUDA-graph capture: no cross-stream events (they would join the graph)
+        for ticket in list(self._host_inflight):     # submitted host calls run on the library's own streams and use the
+            _lib.check(self._lib.syn_host_wait(self._h, ticket))   # same workspace: let them finish (tickets stay valid)
         if self._last_stream is not None and self._last_stream != st.cuda_stream and self._last_event is not None:
             st.wait_event(self._last_event)
         return st.cuda_stream
@@ -267,7 +270,14 @@ class Engine:
 
     def forward_landmarks_host(self, x_host: torch.Tensor, lmk_host: Optional[torch.Tensor] = None,
                                params_host: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """End-to-end call on HOST tensors (pinned recommended): H2D, forward, landmarks, D2H."""
+        """End-to-end call on HOST tensors (pinned recommended): H2D, forward, landmarks, D2H.  Synchronous."""
+        return self.host_wait(self.forward_landmarks_host_submit(x_host, lmk_host, params_host))
+
+    def forward_landmarks_host_submit(self, x_host: torch.Tensor, lmk_host: Optional[torch.Tensor] = None,
+                                      params_host: Optional[torch.Tensor] = None) -> int:
+        """Enqueue the end-to-end call and return a ticket for :meth:`host_wait`.  Up to two calls may be in flight: the
+        second one's host->device copies run under the first one's kernels (a loader loop: submit batch k+1, then wait
+        for batch k).  The tensors are kept alive here until their ticket has been waited for."""
         if x_host.is_cuda or x_host.dtype not in (torch.float32, torch.uint8) or not x_host.is_contiguous():
             raise RuntimeError('x_host must be a contiguous fp32 (normalised) or uint8 (raw) CPU tensor')
         if x_host.dim() != 4 or tuple(x_host.shape[1:]) != (3, 120, 120):
@@ -281,11 +291,25 @@ class Engine:
                 continue
             if buf.is_cuda or buf.dtype != torch.float32 or not buf.is_contiguous() or buf.numel() < need:
                 raise RuntimeError(f'{name} must be a contiguous CPU float32 tensor with at least {need} elements')
-        fn = self._lib.syn_forward_landmarks_host_u8 if x_host.dtype == torch.uint8 else self._lib.syn_forward_landmarks_host
+        ticket = C.c_int(0)
         with self._lock:
-            _lib.check(fn(
-                self._h, x_host.data_ptr(), b, params_host.data_ptr() if params_host is not None else None,
-                lmk_host.data_ptr()))
+            if self._last_event is not None:         # stream-ordered calls share the workspace with the host pipeline
+                self._last_event.synchronize()
+            _lib.check(self._lib.syn_forward_landmarks_host_submit(
+                self._h, x_host.data_ptr(), 1 if x_host.dtype == torch.uint8 else 0, b,
+                params_host.data_ptr() if params_host is not None else None, lmk_host.data_ptr(), C.byref(ticket)))
+            self._host_inflight[ticket.value] = (x_host, lmk_host, params_host)
+        return ticket.value
+
+    def host_wait(self, ticket: int) -> torch.Tensor:
+        """Block until the call behind ``ticket`` has written its host outputs; returns its landmark tensor."""
+        with self._lock:
+            if ticket not in self._host_inflight:
+                raise RuntimeError(f'unknown or already collected ticket {ticket}')
+            try:
+                _lib.check(self._lib.syn_host_wait(self._h, ticket))
+            finally:
+                _, lmk_host, _ = self._host_inflight.pop(ticket)
         return lmk_host
 
     # ---- PointNet refinement heads + losses (training-forward surface, model_building.py:141-157) --------------

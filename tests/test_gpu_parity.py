@@ -217,6 +217,38 @@ def test_host_buffer_call_matches_device_call(model, gold, engine_kind):
     assert rp.max_rel_err(par.numpy(), model.forward_test(x.cuda()).cpu().numpy()) < 1e-6
 
 
+def test_pipelined_host_calls_match_blocking_calls(model, engine_kind):
+    """submit / wait with two calls in flight (the loader-loop form of the host call): every ticket returns exactly what
+    the blocking call returns for its batch, whatever the interleaving, batch sizes and input types; a stream-ordered
+    call in between sees a consistent workspace; a ticket cannot be collected twice."""
+    eng = model._engine(torch.device('cuda', 0))
+    batches = [synthetic.normalize_crops(synthetic.make_structured_crops_u8(n, seed=40 + i)).pin_memory()
+               for i, n in enumerate((600, 130, 1024, 7))]
+    batches.append(synthetic.make_structured_crops_u8(257, seed=77).pin_memory())          # uint8 batch in the mix
+    want = [eng.forward_landmarks_host(b).clone() for b in batches]
+    outs = [torch.empty((b.shape[0], 3, 68), dtype=torch.float32).pin_memory() for b in batches]
+    pars = [torch.empty((b.shape[0], 62), dtype=torch.float32).pin_memory() for b in batches]
+    prev = None
+    for i, b in enumerate(batches):
+        tk = eng.forward_landmarks_host_submit(b, outs[i], pars[i])
+        if prev is not None:
+            got = eng.host_wait(prev[0])
+            assert got is outs[prev[1]] and torch.equal(got, want[prev[1]])
+        prev = (tk, i)
+    mid = eng.forward_landmarks(batches[1].cuda()).cpu()          # stream call while the last ticket is still open
+    assert torch.equal(mid, want[1])
+    assert torch.equal(eng.host_wait(prev[0]), want[prev[1]])
+    with pytest.raises(RuntimeError):
+        eng.host_wait(prev[0])
+    for i, b in enumerate(batches):
+        x = b.cuda() if b.dtype == torch.float32 else synthetic.normalize_crops(b).cuda()
+        assert rp.max_rel_err(pars[i].numpy(), model.forward_test(x).cpu().numpy()) < 1e-6
+    three = [eng.forward_landmarks_host_submit(batches[i], outs[i]) for i in (0, 1, 3)]   # third submit waits for the first
+    for tk, i in zip(three, (0, 1, 3)):
+        assert torch.equal(eng.host_wait(tk), want[i])
+    assert eng.poll_error() == 0
+
+
 def test_uint8_crops_match_host_normalised_floats(model, engine_kind):
     """`(img - 127.5) / 128` applied on the device (uint8 entry points) is the same fp32 arithmetic as
     the reference's host-side normalisation (synergy3DMM.py:192): outputs must be bit-identical."""
