@@ -504,7 +504,7 @@ def run_b200(args):
         fp = os.path.join(ROOT, 'profiles', 'kernel_traffic.json')
         if os.path.exists(fp):
             with open(fp) as f:
-                traffic = json.load(f).get('dense_recon_tc_kernel_dense')
+                traffic = json.load(f).get('dense_recon_fm_kernel')
         extra['dense'] = {
             'workload': 'configs[2]: batch=1024 params -> dense (B,3,53215) vertices', 'ms': d_ms,
             'faces_per_s': B / d_ms * 1e3, 'image_to_dense_ms': img_dense_ms, 'image_to_dense_faces_per_s': B / img_dense_ms * 1e3,
