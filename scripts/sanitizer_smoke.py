@@ -30,6 +30,10 @@ def main():
     eng.forward_landmarks(u8.cuda())
     eng.forward_landmarks_host(u8)
     dense = eng.reconstruct(params, dense=True)
+    eng.reconstruct(params.repeat(24, 1)[:70], dense=True)          # two face tiles, the second one ragged; band edges
+    tk = [eng.forward_landmarks_host_submit(u8.pin_memory()) for _ in range(3)]   # third submit waits for the first
+    for t in tk:
+        eng.host_wait(t)
     roi5 = torch.from_numpy(inference.roi_affine([[1.0, 2.0, 100.0, 110.0]] * 3)).cuda()
     eng.reconstruct_image(params, roi5, dense=True)
     eng.reconstruct_image(params, roi5, dense=False)
