@@ -196,6 +196,64 @@ int syn_resnet_commit(syn_handle_t* h);                      /* after syn_commit
 int syn_resnet50_forward(syn_handle_t* h, const float* x_dev, int batch, float* out102_dev, float* pool2048_dev,
                          void* stream);
 
+/* ---- Sim3DR: vertex normals, lighting, z-buffer rasterisation -------------------------
+ * Handle-free; every pointer is caller-owned device memory unless it says _host.  B meshes share one triangle list
+ * tri_dev (ntri,3) int32, 0-based (utils/render.py:32-33).  Vertices are read in place through element strides:
+ * coordinate k of vertex i of mesh b = vertices_dev[b*stride_mesh + i*stride_vertex + k*stride_coord], i.e.
+ * (nver, 1) for the dense output (B,3,nver) of syn_reconstruct / syn_reconstruct_image (stride_mesh = 3*nver) and
+ * (3, 1) for the (nver,3) arrays the reference passes (Sim3DR/Sim3DR.py:8-29).  normals / colours are (B,nver,3).
+ * Normals and rasterisation return the reference's bits (csrc/render_math.h explains how); lighting is its float32
+ * arithmetic except x**5, where numpy's powf has no portable bit pattern (<= 1 ulp). */
+typedef struct {        /* Sim3DR/lighting.py:24-32 (RenderPipeline.__init__) */
+  float intensity_ambient, intensity_directional, intensity_specular;
+  float color_ambient[3], color_directional[3], light_pos[3], view_pos[3];
+  int32_t specular_exp;
+} syn_light_cfg_t;
+
+/* One-time index work per topology: the triangles incident to each vertex, ascending (start_out: nver+1 entries,
+ * list_out: 3*ntri), so that vertex normals add up in the reference's order (rasterize_kernel.cpp:189-199).
+ * SYN_ERR_SHAPE if a triangle references a vertex outside [0, nver). */
+int syn_mesh_incidence_host(const int32_t* tri_host, int ntri, int nver, int32_t* start_out, int32_t* list_out);
+/* Sim3DR.get_normal (Sim3DR/Sim3DR.py:8-11 -> rasterize_kernel.cpp:158-213).  tri_normals_ws_dev: B*ntri*3 floats. */
+int syn_mesh_normals(const float* vertices_dev, int64_t stride_mesh, int stride_vertex, int stride_coord, int batch, int nver,
+                     const int32_t* tri_dev, int ntri, const int32_t* inc_start_dev, const int32_t* inc_tri_dev,
+                     float* tri_normals_ws_dev, float* normals_dev, void* stream);
+/* RenderPipeline.__call__ up to the rasterize call (Sim3DR/lighting.py:37-75): colours = clip(ambient + diffuse +
+ * specular, 0, 1), times texture_dev (nver,3) when that is not NULL.  stats_ws_dev: 6*B uint32. */
+int syn_mesh_lighting(const float* vertices_dev, int64_t stride_mesh, int stride_vertex, int stride_coord, int batch, int nver,
+                      const float* normals_dev, const syn_light_cfg_t* cfg, const float* texture_dev, uint32_t* stats_ws_dev,
+                      float* colors_dev, void* stream);
+/* Sim3DR.rasterize (Sim3DR/Sim3DR.py:14-29 -> rasterize_kernel.cpp:217-287): draws the B meshes, in order, onto
+ * image_dev (height,width,channels) uint8, each with its own depth buffer as the reference's per-face calls have
+ * (utils/render.py:41-45).  colors_dev (B,nver,channels).  alpha must be 1 (the only value the reference's Python
+ * API can pass; SYN_ERR_UNSUPPORTED otherwise).  keys_ws_dev: B*height*width uint64.  depth_out_dev: NULL, or
+ * (B,height,width) floats that receive each mesh's final depth buffer (-1e8 where nothing was drawn). */
+int syn_rasterize(uint8_t* image_dev, int height, int width, int channels, const float* vertices_dev, int64_t stride_mesh,
+                  int stride_vertex, int stride_coord, int batch, int nver, const int32_t* tri_dev, int ntri,
+                  const float* colors_dev, float alpha, int reverse, uint64_t* keys_ws_dev, float* depth_out_dev, void* stream);
+
+/* ---- FaceBoxes post-processing -----------------------------------------------------------
+ * The detector's CNN (FaceBoxes/models/faceboxes.py) is not part of this library; these entries take its outputs. */
+enum {
+  SYN_NMS_CPU_NMS = 0,     /* FaceBoxes/utils/nms/cpu_nms.pyx:17-68, the path nms_wrapper.py:13-18 takes: suppress on   */
+                           /* ovr >= thresh, compared in double                                                       */
+  SYN_NMS_PY_CPU_NMS = 1   /* FaceBoxes/utils/nms/py_cpu_nms.py:10-38: keep on ovr <= thresh, compared in float32     */
+};
+/* Greedy NMS of dets_dev (n,5) fp32 rows [x1 y1 x2 y2 score] ALREADY in descending score order (FaceBoxes.py:116-121
+ * sorts before it calls nms).  keep_dev (n) int32 receives the kept row indices in order, *n_keep_dev their count:
+ * the index list either reference function returns, bit for bit.  mask_ws_dev: n * ceil(n/64) uint64. */
+int syn_nms(const float* dets_dev, int n, double thresh, int mode, uint64_t* mask_ws_dev, int32_t* keep_dev, int32_t* n_keep_dev,
+            void* stream);
+/* Number of prior boxes for an im_height x im_width network input (utils/prior_box.py:19-43); -1 on bad sizes. */
+int syn_faceboxes_num_priors(int im_height, int im_width);
+/* FaceBoxes.__call__ between the network and the NMS (FaceBoxes/FaceBoxes.py:98-121): priors, decode
+ * (utils/box_utils.py:177-195, variances 0.1 / 0.2), `boxes * scale_bbox / scale`, `scores > conf_thresh`, descending
+ * order (ties: higher prior index first), first top_k.  loc_dev (P,4), conf_dev (P,2) softmax output, P =
+ * syn_faceboxes_num_priors.  dets_dev (top_k,5), *n_dets_dev = rows written.  cand_ws_dev: P+1 int32. */
+int syn_faceboxes_decode(const float* loc_dev, const float* conf_dev, int im_height, int im_width, float box_scale_w,
+                         float box_scale_h, float scale, float conf_thresh, int top_k, int32_t* cand_ws_dev, float* dets_dev,
+                         int32_t* n_dets_dev, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------------*/
 /* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
 int64_t syn_launch_count(const syn_handle_t* h);

@@ -30,6 +30,15 @@ class ConvDesc(C.Structure):
                                          'h_in', 'h_out', 'residual')]
 
 
+class LightCfg(C.Structure):
+    """``syn_light_cfg_t`` (Sim3DR/lighting.py:24-32)."""
+    _fields_ = [('intensity_ambient', C.c_float), ('intensity_directional', C.c_float), ('intensity_specular', C.c_float),
+                ('color_ambient', C.c_float * 3), ('color_directional', C.c_float * 3), ('light_pos', C.c_float * 3),
+                ('view_pos', C.c_float * 3), ('specular_exp', C.c_int32)]
+
+
+NMS_CPU_NMS, NMS_PY_CPU_NMS = 0, 1
+
 _P, _F, _I, _L = C.c_void_p, C.c_void_p, C.c_int, C.c_int64
 # name -> (restype, argtypes); float*/void* travel as integer addresses (tensor.data_ptr()).
 SIGNATURES = {
@@ -71,6 +80,13 @@ SIGNATURES = {
     'syn_resnet_commit': (_I, [_P]),
     'syn_resnet50_forward': (_I, [_P, _F, _I, _F, _F, _P]),
     'syn_debug_heads_buffer': (_I, [_P, _I, _F, _L]),
+    'syn_mesh_incidence_host': (_I, [_F, _I, _I, _F, _F]),
+    'syn_mesh_normals': (_I, [_F, _L, _I, _I, _I, _I, _F, _I, _F, _F, _F, _F, _P]),
+    'syn_mesh_lighting': (_I, [_F, _L, _I, _I, _I, _I, _F, C.POINTER(LightCfg), _F, _F, _F, _P]),
+    'syn_rasterize': (_I, [_F, _I, _I, _I, _F, _L, _I, _I, _I, _I, _F, _I, _F, C.c_float, _I, _F, _F, _P]),
+    'syn_nms': (_I, [_F, _I, C.c_double, _I, _F, _F, _F, _P]),
+    'syn_faceboxes_num_priors': (_I, [_I, _I]),
+    'syn_faceboxes_decode': (_I, [_F, _F, _I, _I, C.c_float, C.c_float, C.c_float, C.c_float, _I, _F, _F, _F, _P]),
     'syn_launch_count': (_L, [_P]),
     'syn_set_timing': (_I, [_P, _I]),
     'syn_get_timings': (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_char_p), _I, C.POINTER(C.c_int)]),
@@ -86,7 +102,9 @@ SIGNATURES = {
 _CORE = {n for n in SIGNATURES if n not in ('syn_peek_error', 'syn_poll_saturation', 'syn_pointnet_set_layer',
                                              'syn_pointnet_commit', 'syn_mlp_for', 'syn_mlp_rev', 'syn_wing_loss',
                                              'syn_param_loss', 'syn_reconstruct_image', 'syn_pose_decode', 'syn_set_center_crop', 'syn_resnet_num_convs', 'syn_resnet_conv_desc',
-                                             'syn_resnet_set_conv', 'syn_resnet_set_heads', 'syn_resnet_commit', 'syn_resnet50_forward', 'syn_debug_heads_buffer')}
+                                             'syn_resnet_set_conv', 'syn_resnet_set_heads', 'syn_resnet_commit', 'syn_resnet50_forward', 'syn_debug_heads_buffer',
+                                             'syn_mesh_incidence_host', 'syn_mesh_normals', 'syn_mesh_lighting', 'syn_rasterize', 'syn_nms',
+                                             'syn_faceboxes_num_priors', 'syn_faceboxes_decode')}
 
 
 def declared_symbols(header: str = HEADER_PATH):

@@ -109,3 +109,12 @@ def predict_pose_batch(params: np.ndarray, param_mean: np.ndarray, param_std: np
         t[1] = t[1] * ((ey - sy) / STD_SIZE) + sy
         out.append([[float(a) for a in ang[i]], t])
     return out
+
+
+# lighting of the solid-mesh overlay (utils/render.py:18-27), consumed by synergynet_b200.Sim3DR.render
+RENDER_CFG = {
+    'intensity_ambient': 0.75, 'color_ambient': (1, 1, 1),
+    'intensity_directional': 0.7, 'color_directional': (1, 1, 1),
+    'intensity_specular': 0.2, 'specular_exp': 5,
+    'light_pos': (0, 0, 5), 'view_pos': (0, 0, 5),
+}

@@ -146,3 +146,36 @@ def seeded_init_(module: torch.nn.Module, seed: int = 0) -> None:
         elif isinstance(m, torch.nn.Linear):
             m.weight.copy_(torch.randn(m.weight.shape, generator=g) * 0.05)
             m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.05)
+
+
+# ---- meshes for the Sim3DR stage ----------------------------------------------------------------
+RENDER_ROWS, RENDER_COLS = 145, 367          # 145 * 367 = 53 215 = NVER vertices, 2 * 144 * 366 = 105 408 triangles
+
+
+def make_render_topology(rows: int = RENDER_ROWS, cols: int = RENDER_COLS) -> np.ndarray:
+    """(ntri,3) int32, 0-based: two triangles per cell of a rows x cols vertex grid (the real ``tri.mat`` is an external
+    download; the random triangles of ``make_3dmm`` span the whole face and are useless for rendering)."""
+    idx = np.arange(rows * cols, dtype=np.int32).reshape(rows, cols)
+    a, b, c, d = idx[:-1, :-1], idx[1:, :-1], idx[:-1, 1:], idx[1:, 1:]
+    return np.ascontiguousarray(np.concatenate([np.stack([a, b, c], -1).reshape(-1, 3), np.stack([b, d, c], -1).reshape(-1, 3)]))
+
+
+def make_render_meshes(batch: int, height: int, width: int, seed: int = 0, rows: int = RENDER_ROWS, cols: int = RENDER_COLS,
+                       size: float = 0.0) -> np.ndarray:
+    """(B,3,rows*cols) float32 vertices in image coordinates, plane-major like the dense output of the 3DMM stage: a
+    grid wrapped over 3/4 of an ellipsoid (so that parts of every mesh face away and occlude each other), randomly
+    posed, ``size`` pixels across (default: a third of the shorter image side), scattered over the image."""
+    rng = np.random.default_rng(7000 + seed)
+    size = size or min(height, width) / 3.0
+    th = np.linspace(-0.75 * np.pi, 0.75 * np.pi, cols)[None, :]
+    ph = np.linspace(-0.42 * np.pi, 0.42 * np.pi, rows)[:, None]
+    base = np.stack([np.cos(ph) * np.sin(th) * 0.8, np.sin(ph) * np.ones_like(th), np.cos(ph) * np.cos(th) * 0.7], 0).reshape(3, -1)
+    out = np.empty((batch, 3, rows * cols), np.float32)
+    for b in range(batch):
+        bump = 1.0 + 0.03 * np.sin(7 * th + rng.uniform(0, 6)) * np.cos(5 * ph + rng.uniform(0, 6))
+        r = _rot(rng.uniform(-0.6, 0.6), rng.uniform(-0.4, 0.4), rng.uniform(-0.3, 0.3))
+        p = r @ (base * bump.reshape(1, -1)) * (size / 2.0) * rng.uniform(0.8, 1.2)
+        p[0] += rng.uniform(0.25, 0.75) * width
+        p[1] += rng.uniform(0.25, 0.75) * height
+        out[b] = p
+    return out
