@@ -340,6 +340,109 @@ def config5_measurement(dev, peaks, B=512):
                     'algorithmic FLOP (2 x MAC; the shared per-face part of conv6 counted once) / CUDA-event time'}
 
 
+def render_detect_measurement(dev, peaks, cpu_too=True):
+    """SURVEY.md section 8 rows f2 / f3, the stages either side of the 3DMM path.
+    render: B = 8 meshes of 53 215 vertices / 105 408 triangles (synthetic.make_render_meshes: the dense stage's (B,3,N)
+    layout, read in place) lit and drawn onto one 720 x 1080 x 3 uint8 canvas = utils/render.py:40-45 for 8 faces.
+    detect: FaceBoxes.py:98-127 for a 720 x 1080 network input (16 680 priors), ~1 500 boxes above the score threshold.
+    CPU legs: the reference's own rasterize_kernel.cpp compiled in place (oracle/_ref, kind "reference"; else the C port) +
+    its numpy lighting; the torch / numpy post-processing with py_cpu_nms (the reference's Cython NMS does not build)."""
+    from oracle import render_port as rp
+    from synergynet_b200 import Sim3DR, detect, synthetic
+    from synergynet_b200.inference import RENDER_CFG
+    out = {}
+    B, H, W = 8, 720, 1080
+    tri = synthetic.make_render_topology()
+    verts = synthetic.make_render_meshes(B, H, W, seed=0)
+    r = Sim3DR.MeshRenderer(tri, verts.shape[2], dev)
+    vd = torch.from_numpy(verts).to(dev)
+    v = vd.transpose(1, 2)
+    cfg = Sim3DR._light_cfg(**RENDER_CFG)
+    bg = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
+    nrm = r.normals(v)
+    col = r.colors(v, nrm, cfg)
+    ms_n = _time_cuda(lambda: r.normals(v), iters=50, warmup=5)
+    ms_l = _time_cuda(lambda: r.colors(v, nrm, cfg), iters=50, warmup=5)
+    ms_r = _time_cuda(lambda: r.rasterize(bg, v, col), iters=50, warmup=5)
+    ms_all = _time_cuda(lambda: r.render(bg, v, cfg), iters=50, warmup=5)
+    vh = torch.from_numpy(verts).pin_memory()
+    img_h = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+    bg_h = torch.zeros((H, W, 3), dtype=torch.uint8).pin_memory()
+
+    def e2e():
+        vd.copy_(vh, non_blocking=True)
+        bg.copy_(bg_h, non_blocking=True)
+        r.render(bg, v, cfg)
+        img_h.copy_(bg, non_blocking=True)
+    for _ in range(3):
+        e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        e2e()
+        torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
+    nver, ntri = verts.shape[2], tri.shape[0]
+    alg_bytes = B * nver * 12 + ntri * 12 + 2 * H * W * 3
+    out['render'] = {
+        'workload': f'{B} meshes x {nver} vertices / {ntri} triangles -> one {H}x{W}x3 uint8 canvas (normals + lighting + z-buffer), '
+                    'vertices read in place from the (B,3,N) layout of the dense stage',
+        'normals_ms': ms_n, 'lighting_ms': ms_l, 'rasterize_ms': ms_r, 'total_ms': ms_all, 'meshes_per_s': B / ms_all * 1e3,
+        'triangles_per_s': B * ntri / ms_r * 1e3, 'gpu_launches_per_call': 6,
+        'e2e': {'ms': e2e_ms, 'meshes_per_s': B / e2e_ms * 1e3, 'h2d_bytes': int(verts.nbytes + H * W * 3), 'd2h_bytes': H * W * 3,
+                'what': 'pinned host vertices + canvas in, image out, synchronised per call'},
+        'roofline': {'bound': 'hbm', 'achieved': alg_bytes / (ms_all * 1e-3) / 1e9, 'peak': peaks['hbm'], 'unit': 'GB/s',
+                     'frac': alg_bytes / (ms_all * 1e-3) / 1e9 / peaks['hbm'], 'traffic': None,
+                     'what': f'algorithmic {alg_bytes} B per call (vertices + triangle list once + canvas in and out) / CUDA-event time of '
+                             'the six launches; the stage is gather / atomic-latency work far below the HBM ceiling'}}
+    # ---- detect ---------------------------------------------------------------------------------------------------------------
+    ih, iw = 720, 1080
+    P = detect.num_priors(ih, iw)
+    g = torch.Generator().manual_seed(21)
+    loc_h = torch.randn((P, 4), generator=g) * 0.6
+    logit = torch.randn((P, 2), generator=g) * 2.0
+    logit[:, 0] += 3.4                                                         # ~9 % of the priors pass the 0.05 threshold
+    conf_h = torch.softmax(logit, dim=-1)
+    loc, conf = loc_h.to(dev), conf_h.to(dev)
+
+    def post():
+        dets, n = detect.decode_device(loc, conf, ih, iw)
+        return detect.nms_device(dets, detect.nms_threshold, n=int(n.item()))
+    n_cand = int((conf_h[:, 1] > detect.confidence_threshold).sum())
+    ms_d = _time_cuda(lambda: detect.decode_device(loc, conf, ih, iw), iters=50, warmup=5)
+    ms_p = _time_cuda(post, iters=50, warmup=5)
+    keep, nk = post()
+    out['detect'] = {'workload': f'FaceBoxes post-processing for a {ih}x{iw} input: {P} priors, {n_cand} above the score threshold -> '
+                                 f'decode + order + greedy NMS(0.3) -> {int(nk.item())} boxes',
+                     'decode_ms': ms_d, 'decode_plus_nms_ms': ms_p, 'images_per_s': 1e3 / ms_p, 'gpu_launches_per_call': 4}
+    if cpu_too:
+        ver0 = [np.ascontiguousarray(verts[b].T) for b in range(B)]
+        kind = 'ref' if rp.have_ref() else 'port'
+        img = np.zeros((H, W, 3), np.uint8)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 3.0:
+            rp.render_faces(img, list(verts), tri, kind=kind)
+            reps += 1
+        cpu_ms = (time.perf_counter() - t0) / reps * 1e3
+        out['render']['cpu_baseline'] = {'value': B / cpu_ms * 1e3, 'unit': 'meshes/s', 'cores': 1,
+                                         'kind': 'reference' if kind == 'ref' else 'port', 'ms_per_call': cpu_ms,
+                                         'sample': f'{reps} calls of utils/render.py:40-45 on the same {B} meshes: Sim3DR C++ '
+                                                   '(single-threaded by construction) + numpy lighting'}
+        del ver0
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 2.0:
+            d = rp.faceboxes_dets(loc_h.numpy(), conf_h.numpy(), ih, iw)
+            k = rp.py_cpu_nms(d, detect.nms_threshold)
+            reps += 1
+        cpu_ms = (time.perf_counter() - t0) / reps * 1e3
+        assert len(k) == int(nk.item()), (len(k), int(nk.item()))
+        out['detect']['cpu_baseline'] = {'value': 1e3 / cpu_ms, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                         'ms_per_call': cpu_ms, 'sample': f'{reps} calls: PriorBox + decode (torch CPU) + argsort + py_cpu_nms (numpy)'}
+    return out
+
+
 def run_b200(args):
     import torch.distributed as dist
     from synergynet_b200 import distributed as sdist
@@ -551,6 +654,12 @@ def run_b200(args):
                 extra['config5'] = config5_measurement(dev, peaks)
             except Exception as e:
                 extra['config5'] = {'unavailable': f'{type(e).__name__}: {e}'}
+        if not args.no_render:
+            # ---- Sim3DR and FaceBoxes post-processing ---------------------------------------
+            try:
+                extra.update(render_detect_measurement(dev, peaks, cpu_too=not args.no_cpu_baseline))
+            except Exception as e:
+                extra['render'] = {'unavailable': f'{type(e).__name__}: {e}'}
         if args.engine is None and not args.no_single_pass:
             # ---- single-pass fp16 engine (NOT parity grade): how much of the step is the 3x precision tax ----
             ref_l, ref_p = eng.forward_landmarks(xs[0][:256], want_params=True)
@@ -655,6 +764,7 @@ def main():
     ap.add_argument('--profile', action='store_true', help='device-resident steps only (for ncu runs)')
     ap.add_argument('--no-gpu-reference', action='store_true', help='skip the same-box PyTorch GPU comparator')
     ap.add_argument('--no-config5', action='store_true', help='skip the ResNet-50 / PointNet heads measurement')
+    ap.add_argument('--no-render', action='store_true', help='skip the Sim3DR / FaceBoxes post-processing measurement')
     ap.add_argument('--no-single-pass', action='store_true', help='skip the single-pass fp16 engine measurement')
     args = ap.parse_args()
     if args.impl == 'reference':
