@@ -233,7 +233,7 @@ int syn_rasterize(uint8_t* image_dev, int height, int width, int channels, const
                   const float* colors_dev, float alpha, int reverse, uint64_t* keys_ws_dev, float* depth_out_dev, void* stream);
 
 /* ---- FaceBoxes post-processing -----------------------------------------------------------
- * The detector's CNN (FaceBoxes/models/faceboxes.py) is not part of this library; these entries take its outputs. */
+ * These entries take the detector network's outputs (syn_fb_forward below, or any other producer). */
 enum {
   SYN_NMS_CPU_NMS = 0,     /* FaceBoxes/utils/nms/cpu_nms.pyx:17-68, the path nms_wrapper.py:13-18 takes: suppress on   */
                            /* ovr >= thresh, compared in double                                                       */
@@ -253,6 +253,30 @@ int syn_faceboxes_num_priors(int im_height, int im_width);
 int syn_faceboxes_decode(const float* loc_dev, const float* conf_dev, int im_height, int im_width, float box_scale_w,
                          float box_scale_h, float scale, float conf_thresh, int top_k, int32_t* cand_ws_dev, float* dets_dev,
                          int32_t* n_dets_dev, void* stream);
+
+/* The detector network (FaceBoxes/models/faceboxes.py:68-150, FaceBoxesNet in 'test' phase) on ONE image of any size.
+ * A separate handle: the detector has its own weights and workspace and does not touch syn_handle_t.
+ * 33 convolutions in execution order (syn_fb_layer_desc names them with the reference's state_dict prefixes:
+ * "conv1", "inception2.branch3x3_2", "loc.0" ...): layers with has_bn take the conv weight (OIHW fp32, no bias) and
+ * the eval-mode BatchNorm2d of the same block (<name>.conv.weight / <name>.bn.*), the six head layers take weight +
+ * bias.  activation: 0 none, 1 ReLU (BasicConv2d, :8-18), 2 CReLU (:50-64, output has 2*cout channels). */
+typedef struct syn_fb syn_fb_t;
+typedef struct {
+  const char* name;
+  int32_t cin, cout, ksize, stride, pad, has_bn, activation;
+} syn_fb_layer_desc_t;
+int  syn_fb_num_layers(void);                                 /* 33 */
+int  syn_fb_layer_desc(int idx, syn_fb_layer_desc_t* out);
+int  syn_fb_create(int device, syn_fb_t** out);
+void syn_fb_destroy(syn_fb_t* f);
+int  syn_fb_set_layer(syn_fb_t* f, int idx, const float* w_host, int64_t w_numel, const float* bias_host, const float* bn_weight_host,
+                      const float* bn_bias_host, const float* bn_mean_host, const float* bn_var_host, float eps);
+int  syn_fb_commit(syn_fb_t* f);
+/* FaceBoxes.__call__ lines 88-96: image_dev (height,width,3) uint8 BGR as cv2 delivers it (already rescaled by the caller,
+ * :62-79); the mean (104,117,123) is subtracted on the fly.  loc_dev (P,4) and conf_dev (P,2, softmax applied) are what
+ * `self.net(img)` returns, P = syn_faceboxes_num_priors(height, width); feed them to syn_faceboxes_decode + syn_nms. */
+int  syn_fb_forward(syn_fb_t* f, const uint8_t* image_dev, int height, int width, float* loc_dev, float* conf_dev, void* stream);
+int64_t syn_fb_launch_count(const syn_fb_t* f);
 
 /* ---- introspection ---------------------------------------------------------------------------*/
 /* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */

@@ -83,3 +83,131 @@ __global__ void faceboxes_rank_decode_kernel(const float* __restrict__ loc, cons
 }
 
 }  // namespace syn
+
+// ---- the detector network (FaceBoxes/models/faceboxes.py:8-150) -------------------------------------------------------
+// 33 small convolutions on one image of arbitrary size (0.7 GMAC at 720 x 1080).  A first, plain B200 path: fp32 FMA on
+// CUDA cores as a shared-memory-tiled implicit GEMM (M = output pixels, N = output channels, K = kh*kw*cin), BatchNorm
+// folded into weights and bias on the host in float64, activation and the channel concatenations fused into the store
+// (every layer writes its slice of the NHWC tensor the next layer reads).  NHWC is also how the image arrives (H,W,3
+// BGR uint8): the mean subtraction of FaceBoxes.py:92 happens in the first layer's gather.
+namespace syn {
+
+struct FbConvArgs {
+  const float* x;          // NHWC input (h, w, cin_stride channels per pixel; this layer reads channels [cin_off, cin_off + cin))
+  const uint8_t* x_u8;     // first layer: raw image (h, w, 3); value = (float)u8 - mean[c]
+  const float* wk;         // [K = kh*kw*cin][cout] fp32, BN scale folded
+  const float* bias;       // [cout]
+  float* y;                // NHWC output, cout_stride channels per pixel, written at channel offset cout_off
+  int h, w, cin, cin_stride, cin_off;
+  int ho, wo, cout, cout_stride, cout_off;
+  int k, stride, pad;
+  int act;                 // 0 linear, 1 ReLU, 2 CReLU: channel c gets relu(v), channel c + cout gets relu(-v)  (faceboxes.py:60-64)
+  float mean[3];
+};
+
+constexpr int FB_BM = 64, FB_BN = 64, FB_BK = 16;
+
+__global__ void __launch_bounds__(256) fb_conv_kernel(const FbConvArgs a) {
+  __shared__ float sA[FB_BK][FB_BM + 4];
+  __shared__ float sB[FB_BK][FB_BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;            // thread = 4 pixels (ty) x 4 channels (tx)
+  const int m0 = blockIdx.x * FB_BM, n0 = blockIdx.y * FB_BN;
+  const int M = a.ho * a.wo, K = a.k * a.k * a.cin;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += FB_BK) {
+    // A tile: FB_BK x FB_BM gathered input values (zero outside the image = the convolution's padding)
+    for (int e = tid; e < FB_BK * FB_BM; e += 256) {
+      const int kk = e / FB_BM, mm = e - kk * FB_BM;
+      const int kidx = k0 + kk, m = m0 + mm;
+      float v = 0.f;
+      if (kidx < K && m < M) {
+        const int ci = kidx % a.cin, kw = (kidx / a.cin) % a.k, kh = kidx / (a.cin * a.k);
+        const int oy = m / a.wo, ox = m - oy * a.wo;
+        const int iy = oy * a.stride - a.pad + kh, ix = ox * a.stride - a.pad + kw;
+        if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) {
+          if (a.x_u8) v = (float)a.x_u8[((size_t)iy * a.w + ix) * 3 + ci] - a.mean[ci];
+          else v = a.x[((size_t)iy * a.w + ix) * a.cin_stride + a.cin_off + ci];
+        }
+      }
+      sA[kk][mm] = v;
+    }
+    for (int e = tid; e < FB_BK * FB_BN; e += 256) {
+      const int kk = e / FB_BN, nn = e - kk * FB_BN;
+      const int kidx = k0 + kk, n = n0 + nn;
+      sB[kk][nn] = (kidx < K && n < a.cout) ? a.wk[(size_t)kidx * a.cout + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < FB_BK; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = sB[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    float* o = a.y + (size_t)m * a.cout_stride + a.cout_off;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.cout) continue;
+      const float v = acc[i][j] + a.bias[n];
+      if (a.act == 0) o[n] = v;
+      else if (a.act == 1) o[n] = fmaxf(v, 0.f);
+      else { o[n] = fmaxf(v, 0.f); o[n + a.cout] = fmaxf(-v, 0.f); }
+    }
+  }
+}
+
+// F.max_pool2d(x, 3, stride 2, padding 1) (faceboxes.py:121,123), NHWC
+__global__ void fb_maxpool_kernel(const float* __restrict__ x, int h, int w, int c, float* __restrict__ y, int ho, int wo) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)ho * wo * c) return;
+  const int ch = (int)(i % c), ox = (int)((i / c) % wo), oy = (int)(i / ((size_t)c * wo));
+  float m = -INFINITY;
+  for (int dy = 0; dy < 3; ++dy)
+    for (int dx = 0; dx < 3; ++dx) {
+      const int iy = oy * 2 - 1 + dy, ix = ox * 2 - 1 + dx;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) m = fmaxf(m, x[((size_t)iy * w + ix) * c + ch]);
+    }
+  y[i] = m;
+}
+
+// F.avg_pool2d(x, 3, stride 1, padding 1) (faceboxes.py:37): count_include_pad defaults to True, the divisor is always 9
+__global__ void fb_avgpool_kernel(const float* __restrict__ x, int h, int w, int c, float* __restrict__ y) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)h * w * c) return;
+  const int ch = (int)(i % c), ox = (int)((i / c) % w), oy = (int)(i / ((size_t)c * w));
+  float s = 0.f;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int iy = oy + dy, ix = ox + dx;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w) s += x[((size_t)iy * w + ix) * c + ch];
+    }
+  y[i] = s / 9.0f;
+}
+
+// nn.Softmax(dim=-1) over the (P, 2) class scores (faceboxes.py:92,143)
+__global__ void fb_softmax2_kernel(float* __restrict__ conf, int np) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const float a = conf[2 * i], b = conf[2 * i + 1], m = fmaxf(a, b);
+  const float ea = expf(a - m), eb = expf(b - m), s = ea + eb;
+  conf[2 * i] = ea / s;
+  conf[2 * i + 1] = eb / s;
+}
+
+}  // namespace syn
