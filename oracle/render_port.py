@@ -200,3 +200,59 @@ def cpu_nms(dets: np.ndarray, thresh: float, ge: bool = True):
     fn.restype = C.c_int
     cnt = fn(_p(d), _p(order), C.c_int(n), C.c_double(thresh), C.c_int(1 if ge else 0), _p(keep))
     return [int(k) for k in keep[:cnt]]
+
+
+# ---- the detector network (FaceBoxes/models/faceboxes.py) ----------------------------------------------------------------
+def faceboxes_forward(sd, img_u8: np.ndarray):
+    """``FaceBoxesNet(phase='test').forward`` (faceboxes.py:112-150) on ``img - (104,117,123)`` (FaceBoxes.py:86-96), restated
+    with torch.nn.functional on CPU fp32 -- the ATen kernels the reference's modules dispatch to.  ``sd``: reference-schema
+    state dict.  Returns ``(loc (P,4), conf (P,2))`` numpy arrays."""
+    import torch
+    import torch.nn.functional as F
+
+    def bn_conv(x, name, stride=1, padding=0):
+        y = F.conv2d(x, sd[f'{name}.conv.weight'], None, stride, padding)
+        return F.batch_norm(y, sd[f'{name}.bn.running_mean'], sd[f'{name}.bn.running_var'], sd[f'{name}.bn.weight'],
+                            sd[f'{name}.bn.bias'], False, 0.0, 1e-5)
+
+    def basic(x, name, stride=1, padding=0):                       # BasicConv2d :8-18
+        return F.relu(bn_conv(x, name, stride, padding))
+
+    def crelu(x, name, stride, padding):                           # CRelu :50-64
+        y = bn_conv(x, name, stride, padding)
+        return F.relu(torch.cat([y, -y], 1))
+
+    def inception(x, p):                                           # Inception :21-47
+        a = basic(x, f'{p}.branch1x1')
+        b = basic(F.avg_pool2d(x, 3, 1, 1), f'{p}.branch1x1_2')
+        c = basic(basic(x, f'{p}.branch3x3_reduce'), f'{p}.branch3x3', 1, 1)
+        d = basic(basic(basic(x, f'{p}.branch3x3_reduce_2'), f'{p}.branch3x3_2', 1, 1), f'{p}.branch3x3_3', 1, 1)
+        return torch.cat([a, b, c, d], 1)
+
+    with torch.no_grad():
+        x = torch.from_numpy(np.ascontiguousarray((np.float32(img_u8) - (104, 117, 123)).transpose(2, 0, 1), dtype=np.float32))[None]
+        x = F.max_pool2d(crelu(x, 'conv1', 4, 3), 3, 2, 1)
+        x = F.max_pool2d(crelu(x, 'conv2', 2, 2), 3, 2, 1)
+        for p in ('inception1', 'inception2', 'inception3'):
+            x = inception(x, p)
+        s0 = x
+        s1 = basic(basic(s0, 'conv3_1'), 'conv3_2', 2, 1)
+        s2 = basic(basic(s1, 'conv4_1'), 'conv4_2', 2, 1)
+        loc, conf = [], []
+        for k, s in enumerate((s0, s1, s2)):
+            loc.append(F.conv2d(s, sd[f'loc.{k}.weight'], sd[f'loc.{k}.bias'], 1, 1).permute(0, 2, 3, 1).reshape(-1))
+            conf.append(F.conv2d(s, sd[f'conf.{k}.weight'], sd[f'conf.{k}.bias'], 1, 1).permute(0, 2, 3, 1).reshape(-1))
+        loc = torch.cat(loc).view(-1, 4)
+        conf = torch.softmax(torch.cat(conf).view(-1, 2), dim=-1)
+    return loc.numpy(), conf.numpy()
+
+
+def faceboxes_detect(sd, img_u8: np.ndarray, conf_thresh=0.05, top_k=5000, nms_thresh=0.3, keep_top_k=750, vis_thres=0.5):
+    """``FaceBoxes.__call__`` (FaceBoxes.py:57-143) for an image that needs no rescaling; NMS = py_cpu_nms' convention with the
+    `>=` of the Cython path (identical unless an overlap equals the threshold)."""
+    loc, conf = faceboxes_forward(sd, img_u8)
+    h, w = img_u8.shape[:2]
+    d = faceboxes_dets(loc, conf, h, w, 1.0, conf_thresh, top_k)
+    keep = cpu_nms(d, nms_thresh) if d.shape[0] else []
+    kept = d[keep][:keep_top_k]
+    return [list(b) for b in kept if b[4] > vis_thres]

@@ -37,6 +37,11 @@ class LightCfg(C.Structure):
                 ('view_pos', C.c_float * 3), ('specular_exp', C.c_int32)]
 
 
+class FbLayerDesc(C.Structure):
+    """``syn_fb_layer_desc_t``."""
+    _fields_ = [('name', C.c_char_p)] + [(n, C.c_int32) for n in ('cin', 'cout', 'ksize', 'stride', 'pad', 'has_bn', 'activation')]
+
+
 NMS_CPU_NMS, NMS_PY_CPU_NMS = 0, 1
 
 _P, _F, _I, _L = C.c_void_p, C.c_void_p, C.c_int, C.c_int64
@@ -86,6 +91,14 @@ SIGNATURES = {
     'syn_rasterize': (_I, [_F, _I, _I, _I, _F, _L, _I, _I, _I, _I, _F, _I, _F, C.c_float, _I, _F, _F, _P]),
     'syn_nms': (_I, [_F, _I, C.c_double, _I, _F, _F, _F, _P]),
     'syn_faceboxes_num_priors': (_I, [_I, _I]),
+    'syn_fb_num_layers': (_I, []),
+    'syn_fb_layer_desc': (_I, [_I, C.POINTER(FbLayerDesc)]),
+    'syn_fb_create': (_I, [_I, C.POINTER(_P)]),
+    'syn_fb_destroy': (None, [_P]),
+    'syn_fb_set_layer': (_I, [_P, _I, _F, _L, _F, _F, _F, _F, _F, C.c_float]),
+    'syn_fb_commit': (_I, [_P]),
+    'syn_fb_forward': (_I, [_P, _F, _I, _I, _F, _F, _P]),
+    'syn_fb_launch_count': (_L, [_P]),
     'syn_faceboxes_decode': (_I, [_F, _F, _I, _I, C.c_float, C.c_float, C.c_float, C.c_float, _I, _F, _F, _F, _P]),
     'syn_launch_count': (_L, [_P]),
     'syn_set_timing': (_I, [_P, _I]),
@@ -104,7 +117,8 @@ _CORE = {n for n in SIGNATURES if n not in ('syn_peek_error', 'syn_poll_saturati
                                              'syn_param_loss', 'syn_reconstruct_image', 'syn_pose_decode', 'syn_set_center_crop', 'syn_resnet_num_convs', 'syn_resnet_conv_desc',
                                              'syn_resnet_set_conv', 'syn_resnet_set_heads', 'syn_resnet_commit', 'syn_resnet50_forward', 'syn_debug_heads_buffer',
                                              'syn_mesh_incidence_host', 'syn_mesh_normals', 'syn_mesh_lighting', 'syn_rasterize', 'syn_nms',
-                                             'syn_faceboxes_num_priors', 'syn_faceboxes_decode')}
+                                             'syn_faceboxes_num_priors', 'syn_faceboxes_decode', 'syn_fb_num_layers', 'syn_fb_layer_desc', 'syn_fb_create',
+                                             'syn_fb_destroy', 'syn_fb_set_layer', 'syn_fb_commit', 'syn_fb_forward', 'syn_fb_launch_count')}
 
 
 def declared_symbols(header: str = HEADER_PATH):

@@ -179,3 +179,44 @@ def make_render_meshes(batch: int, height: int, width: int, seed: int = 0, rows:
         p[1] += rng.uniform(0.25, 0.75) * height
         out[b] = p
     return out
+
+
+# ---- detector weights ---------------------------------------------------------------------------
+def make_faceboxes_state_dict(seed: int = 0):
+    """Seeded stand-in for ``FaceBoxes/weights/FaceBoxesProd.pth`` in the reference's key schema: He-scaled conv weights
+    (activations keep O(1) magnitude through the 12-layer-deep paths), non-trivial BatchNorm statistics so that folding is
+    exercised, small head weights so that the class scores spread over (0,1)."""
+    from .faceboxes import layer_plan
+    g = torch.Generator().manual_seed(9000 + seed)
+    sd = {}
+    for L in layer_plan():
+        fan_in = L['cin'] * L['ksize'] ** 2
+        shape = (L['cout'], L['cin'], L['ksize'], L['ksize'])
+        n = L['name']
+        if L['has_bn']:
+            sd[f'{n}.conv.weight'] = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
+            sd[f'{n}.bn.weight'] = torch.rand(L['cout'], generator=g) * 0.5 + 0.75
+            sd[f'{n}.bn.bias'] = torch.randn(L['cout'], generator=g) * 0.1
+            sd[f'{n}.bn.running_mean'] = torch.randn(L['cout'], generator=g) * 0.1
+            sd[f'{n}.bn.running_var'] = torch.rand(L['cout'], generator=g) * 0.5 + 0.75
+            if n == 'conv1':        # pixels minus the channel means are O(60): the first BatchNorm brings activations to O(1)
+                sd[f'{n}.bn.running_var'] *= 7000.0
+                sd[f'{n}.bn.running_mean'] *= 80.0
+            sd[f'{n}.bn.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+        else:
+            sd[f'{n}.weight'] = torch.randn(shape, generator=g) * (0.6 / fan_in) ** 0.5
+            sd[f'{n}.bias'] = torch.randn(L['cout'], generator=g) * 0.05
+    return sd
+
+
+def make_scene_u8(height: int, width: int, seed: int = 0) -> np.ndarray:
+    """(H,W,3) uint8 BGR test image: smooth gradients, a few ellipses, noise."""
+    rng = np.random.default_rng(8000 + seed)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
+    img = np.stack([90 + 60 * np.sin(xx / 37.0 + c) + 40 * np.cos(yy / 23.0 - c) for c in range(3)], -1)
+    for _ in range(4):
+        cy, cx, r = rng.uniform(0.2, 0.8) * height, rng.uniform(0.2, 0.8) * width, rng.uniform(0.08, 0.2) * min(height, width)
+        inside = ((yy - cy) / (1.25 * r)) ** 2 + ((xx - cx) / r) ** 2 < 1
+        img[inside] = img[inside] * 0.3 + rng.uniform(60, 220, 3)
+    img += rng.normal(0, 5, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)

@@ -143,6 +143,21 @@ def main():
         out[f'fb_{tag}_dets_sorted'] = d
         out[f'fb_{tag}_keep'] = np.array(keep, np.int64)
         out[f'fb_{tag}_final'] = np.array([b for b in kept if b[4] > fb_mod.vis_thres], np.float32).reshape(-1, 5)
+    # the detector with the seeded synthetic checkpoint the GPU tests can rebuild (the shipped weights cannot travel):
+    # reference network class, strict load, its forward; then the reference's own FaceBoxes.__call__ with that network
+    sd = synthetic.make_faceboxes_state_dict(0)
+    ref_keys = list(net.net.state_dict().keys())
+    assert ref_keys == __import__('synergynet_b200.faceboxes', fromlist=['x']).state_dict_keys(), 'key schema differs from the reference'
+    net.net.load_state_dict(sd, strict=True)
+    net.net.eval()
+    for (sh, sw, seed) in ((250, 333, 0), (120, 96, 1)):
+        scene = synthetic.make_scene_u8(sh, sw, seed)
+        xs = torch.from_numpy(np.ascontiguousarray((np.float32(scene) - (104, 117, 123)).transpose(2, 0, 1), dtype=np.float32)).unsqueeze(0)
+        with torch.no_grad():
+            l_s, c_s = net.net(xs)
+        out[f'fbs_loc_{sh}x{sw}'] = l_s.squeeze(0).numpy()
+        out[f'fbs_conf_{sh}x{sw}'] = c_s.squeeze(0).numpy()
+        out[f'fbs_final_{sh}x{sw}'] = np.array(net(scene), np.float32).reshape(-1, 5)            # FaceBoxes.__call__, unmodified
     path = os.path.join(ROOT, 'tests', 'golden', 'render_vectors.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, {k: v.shape for k, v in out.items()})

@@ -111,3 +111,31 @@ def test_faceboxes_chain(gold):
         if d.shape[0]:
             assert np.allclose(d, want, rtol=1e-6, atol=1e-5)
             assert rp.py_cpu_nms(d, 0.3) == gold[f'fb_{tag}_keep'].tolist()
+
+
+# ---- the detector network ------------------------------------------------------------------------------------------------
+def _max_rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+@pytest.mark.parametrize('hw', [(250, 333, 0), (120, 96, 1)])
+def test_detector_network_oracle(gold, hw):
+    h, w, seed = hw
+    sd = synthetic.make_faceboxes_state_dict(0)
+    loc, conf = rp.faceboxes_forward(sd, synthetic.make_scene_u8(h, w, seed))
+    assert loc.shape == gold[f'fbs_loc_{h}x{w}'].shape
+    assert _max_rel(loc, gold[f'fbs_loc_{h}x{w}']) <= 2e-5 and _max_rel(conf, gold[f'fbs_conf_{h}x{w}']) <= 2e-5
+
+
+def test_detector_end_to_end_oracle(gold):
+    sd = synthetic.make_faceboxes_state_dict(0)
+    got = np.array(rp.faceboxes_detect(sd, synthetic.make_scene_u8(120, 96, 1)), np.float32).reshape(-1, 5)
+    want = gold['fbs_final_120x96']
+    assert got.shape == want.shape and np.allclose(got, want, rtol=1e-5, atol=1e-4)
+
+
+def test_detector_key_schema():
+    from synergynet_b200 import faceboxes
+    keys = faceboxes.state_dict_keys()
+    assert len(keys) == 27 * 6 + 6 * 2 and keys[0] == 'conv1.conv.weight' and keys[-1] == 'conf.2.bias'
+    assert set(keys) == set(synthetic.make_faceboxes_state_dict(0).keys())
