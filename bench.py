@@ -415,6 +415,36 @@ def render_detect_measurement(dev, peaks, cpu_too=True):
     out['detect'] = {'workload': f'FaceBoxes post-processing for a {ih}x{iw} input: {P} priors, {n_cand} above the score threshold -> '
                                  f'decode + order + greedy NMS(0.3) -> {int(nk.item())} boxes',
                      'decode_ms': ms_d, 'decode_plus_nms_ms': ms_p, 'images_per_s': 1e3 / ms_p, 'gpu_launches_per_call': 4}
+    # the detector network itself (FaceBoxes/models/faceboxes.py) on one 720 x 1080 image: seeded synthetic checkpoint
+    from synergynet_b200 import faceboxes
+    fsd = synthetic.make_faceboxes_state_dict(0)
+    fnet = faceboxes.FaceBoxesNet(fsd, dev)
+    scene = synthetic.make_scene_u8(ih, iw, 0)
+    scene_d = torch.from_numpy(scene).to(dev)
+    ms_net = _time_cuda(lambda: fnet.forward(scene_d), iters=20, warmup=3)
+    fb = faceboxes.FaceBoxes(weights=fsd, device=dev)
+    fb(scene)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        boxes = fb(scene)
+    ms_call = (time.perf_counter() - t0) / 10 * 1e3
+    plan = faceboxes.layer_plan()
+    g32 = [-(-ih // 32) * -(-iw // 32), -(-ih // 64) * -(-iw // 64), -(-ih // 128) * -(-iw // 128)]
+    px = {0: -(-ih // 4) * -(-iw // 4), 1: -(-ih // 16) * -(-iw // 16)}
+    mac = 0
+    for L in plan:
+        n = L['name']
+        pix = px.get(L['index'], g32[0])
+        if n in ('conv3_2', 'conv4_1', 'loc.1', 'conf.1'):
+            pix = g32[1]
+        if n in ('conv4_2', 'loc.2', 'conf.2'):
+            pix = g32[2]
+        mac += pix * L['cin'] * L['cout'] * L['ksize'] ** 2
+    out['detect']['network'] = {'workload': f'FaceBoxesNet forward on one {ih}x{iw}x3 uint8 image (33 convs, pools, softmax; {mac / 1e6:.0f} MMAC)',
+                                'ms': ms_net, 'tflops': 2.0 * mac / (ms_net * 1e-3) / 1e12, 'gpu_launches_per_call': 39,
+                                'detector_call_ms': ms_call, 'detector_images_per_s': 1e3 / ms_call, 'boxes': len(boxes),
+                                'note': 'fp32 CUDA-core implicit GEMM (first correct path, not tensor-core code); detector_call = '
+                                        'FaceBoxes.__call__ from a host uint8 image to the box list (H2D, network, decode, NMS, D2H)'}
     if cpu_too:
         ver0 = [np.ascontiguousarray(verts[b].T) for b in range(B)]
         kind = 'ref' if rp.have_ref() else 'port'
@@ -438,6 +468,13 @@ def render_detect_measurement(dev, peaks, cpu_too=True):
             reps += 1
         cpu_ms = (time.perf_counter() - t0) / reps * 1e3
         assert len(k) == int(nk.item()), (len(k), int(nk.item()))
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 2.0:
+            rp.faceboxes_forward(fsd, scene)
+            reps += 1
+        out['detect']['network']['cpu_baseline'] = {'value': reps / (time.perf_counter() - t0), 'unit': 'images/s', 'cores': torch.get_num_threads(),
+                                                    'kind': 'port', 'sample': f'{reps} forwards of the torch CPU restatement of FaceBoxesNet'}
         out['detect']['cpu_baseline'] = {'value': 1e3 / cpu_ms, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                                          'ms_per_call': cpu_ms, 'sample': f'{reps} calls: PriorBox + decode (torch CPU) + argsort + py_cpu_nms (numpy)'}
     return out

@@ -39,7 +39,7 @@ def test_network_outputs_match_reference(gold, net, hw):
     img = torch.from_numpy(synthetic.make_scene_u8(h, w, seed)).cuda()
     n0 = net.launch_count
     loc, conf = net.forward(img)
-    assert net.launch_count - n0 == 41                                   # 33 convolutions, 2 + 3 pools, softmax ... all ours
+    assert net.launch_count - n0 == 39                                   # 33 convolutions, 2 + 3 pools, softmax: all ours
     assert _max_rel(loc.cpu().numpy(), gold[f'fbs_loc_{h}x{w}']) <= TOL
     assert _max_rel(conf.cpu().numpy(), gold[f'fbs_conf_{h}x{w}']) <= TOL
     assert np.allclose(conf.sum(1).cpu().numpy(), 1.0, atol=1e-6)
