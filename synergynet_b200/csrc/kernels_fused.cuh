@@ -42,6 +42,15 @@ constexpr int ceil_div_c(int a, int b) { return (a + b - 1) / b; }
 #ifndef SYN_NC_B4
 #define SYN_NC_B4 16
 #endif
+#ifndef SYN_NC_B2
+#define SYN_NC_B2 32
+#endif
+#ifndef SYN_NC_B3
+#define SYN_NC_B3 16
+#endif
+#ifndef SYN_RO_B3
+#define SYN_RO_B3 15
+#endif
 #ifndef SYN_RO_B4
 #define SYN_RO_B4 15
 #endif
@@ -217,7 +226,7 @@ template <class C, int NWW>
 __global__ void __launch_bounds__((NWW + 1) * 32, 1) fused_mbconv_kernel(const FusedArgs p) {
   constexpr int NWT = NWW * 32;          // worker threads
   constexpr int NWG = NWW / 4;           // worker groups: group g owns every NWG-th (tile, column-chunk) pair
-  static_assert(NWW % 4 == 0 && NWW >= 4 && NWW <= 16, "worker warps");
+  static_assert(NWW % 4 == 0 && NWW >= 4 && NWW <= 24, "worker warps");
   // Channel groups: the hidden channels of a chunk are split between NG groups of worker warps.  A group
   // drains ITS channels from TMEM (EPI1) and runs the depthwise conv on ITS channels, so the only
   // synchronisation between EPI1 and DW is a named barrier among the group's warps, and the groups drift
@@ -1104,8 +1113,8 @@ inline void fused_tile_plan(int batch, int sms, int& split, int& face_groups) {
 // ---- the instantiations used by the backbone (SURVEY.md section 8(a) shape table) -------------------
 //                          CIN CHID NC COUT  W  S  RO FACES RES    STEM   weight ring slots (0 = resident)
 using FusedStemB1 = FusedCfg<27, 32, 32, 16, 60, 1, SYN_RO_STEM, 1, false, true, 0>;    // features[0] + features[1]
-using FusedB2 = FusedCfg<16, 96, 32, 24, 60, 2, SYN_RO_B2, 1, false, false, 0>;       // features[2]
-using FusedB3 = FusedCfg<24, 144, 16, 24, 30, 1, 15, 1, true, false, 0>;      // features[3]
+using FusedB2 = FusedCfg<16, 96, SYN_NC_B2, 24, 60, 2, SYN_RO_B2, 1, false, false, 0>;       // features[2]
+using FusedB3 = FusedCfg<24, 144, SYN_NC_B3, 24, 30, 1, SYN_RO_B3, 1, true, false, 0>;      // features[3]
 using FusedB4 = FusedCfg<24, 144, SYN_NC_B4, 32, 30, 2, SYN_RO_B4, 1, false, false, 0>;      // features[4]
 using FusedB56 = FusedCfg<32, 192, SYN_NC_B56, 32, 15, 1, 15, 1, true, false, 0>;     // features[5], [6]
 using FusedB7 = FusedCfg<32, 192, SYN_NC_B7, 64, 15, 2, 8, 1, false, false, 0>;      // features[7]

@@ -545,13 +545,28 @@ void pack_fused(std::vector<uint8_t>& img, const float* w1, int K, const float* 
 
 // Worker warps of the fused kernel: 16 by default (4 per SM sub-partition, measured best); SYN_FUSED_WARPS=8|12|16
 // selects another instantiation for tuning runs.
-inline int fused_worker_warps() {
-  static const int v = [] {
-    const char* e = getenv("SYN_FUSED_WARPS");
-    const int n = e ? atoi(e) : 16;
-    return (n == 8 || n == 12 || n == 16) ? n : 16;
-  }();
-  return v;
+inline int fused_worker_warps(int block) {
+  static const struct Table {
+    int v[18];
+    Table() {
+      const char* e = getenv("SYN_FUSED_WARPS");
+      const int n = e ? atoi(e) : 16;
+      const int all = (n == 8 || n == 12 || n == 16 || n == 20 || n == 24) ? n : 16;
+      for (int i = 0; i < 18; ++i) v[i] = all;
+      // per block: SYN_FUSED_WARPS_MAP="1:24,2:20" (tuning runs)
+      const char* m = getenv("SYN_FUSED_WARPS_MAP");
+      while (m && *m) {
+        const int b = atoi(m);
+        const char* c = strchr(m, ':');
+        if (!c) break;
+        const int w = atoi(c + 1);
+        if (b >= 1 && b <= 17 && (w == 8 || w == 12 || w == 16 || w == 20 || w == 24)) v[b] = w;
+        m = strchr(c, ',');
+        if (m) ++m;
+      }
+    }
+  } t;
+  return t.v[block];
 }
 
 template <class C, int NWW>
@@ -599,9 +614,13 @@ int launch_fused(syn_handle* h, const float* x, int block, float* y, int batch, 
   const int ntiles = a.face_groups * C::STRIPS;
   const int grid = std::min(ntiles, h->sm_count);
   int rc;
-  switch (fused_worker_warps()) {
+  switch (fused_worker_warps(block)) {
     case 8: rc = launch_fused_nww<C, 8>(h, a, grid, st); break;
     case 12: rc = launch_fused_nww<C, 12>(h, a, grid, st); break;
+#ifdef SYN_MORE_WARPS
+    case 20: rc = launch_fused_nww<C, 20>(h, a, grid, st); break;
+    case 24: rc = launch_fused_nww<C, 24>(h, a, grid, st); break;
+#endif
     default: rc = launch_fused_nww<C, 16>(h, a, grid, st); break;
   }
   if (rc != SYN_OK) return rc;
