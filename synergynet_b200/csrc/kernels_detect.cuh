@@ -107,9 +107,26 @@ struct FbConvArgs {
 
 constexpr int FB_BM = 64, FB_BN = 64, FB_BK = 16;
 
+// One input value of the implicit GEMM: element `kidx` = (kh, kw, ci) of output pixel m's patch (0 outside the image)
+__device__ __forceinline__ float fb_gather1(const FbConvArgs& a, int kidx, int m, int K, int M) {
+  if (kidx >= K || m >= M) return 0.f;
+  const int ci = kidx % a.cin, t = kidx / a.cin, kw = t % a.k, kh = t / a.k;
+  const int oy = m / a.wo, ox = m - oy * a.wo;
+  const int iy = oy * a.stride - a.pad + kh, ix = ox * a.stride - a.pad + kw;
+  if (iy < 0 || iy >= a.h || ix < 0 || ix >= a.w) return 0.f;
+  if (a.x_u8) return (float)a.x_u8[((size_t)iy * a.w + ix) * 3 + ci] - (ci == 0 ? a.mean[0] : ci == 1 ? a.mean[1] : a.mean[2]);
+  return a.x[((size_t)iy * a.w + ix) * a.cin_stride + a.cin_off + ci];
+}
+
+// VEC: cin, cin_stride, cin_off and cout are multiples of 4 (every layer but conv1 and the 42- / 2-channel heads): a
+// thread fetches ONE float4 of the A tile (4 consecutive input channels of one patch position: contiguous in NHWC) and
+// one float4 of the B tile per K step instead of four scalars each.  Either way the next step's operands are fetched
+// into registers before the current step's FMAs and stored to shared memory after them, so the global-load latency of
+// the long-K, small-M layers (conv2, the stride-2 3x3s, the heads: 72-144 K steps on a few dozen CTAs) is hidden.
+template <bool VEC>
 __global__ void __launch_bounds__(256) fb_conv_kernel(const FbConvArgs a) {
-  __shared__ float sA[FB_BK][FB_BM + 4];
-  __shared__ float sB[FB_BK][FB_BN + 4];
+  __shared__ __align__(16) float sA[FB_BK][FB_BM + 4];
+  __shared__ __align__(16) float sB[FB_BK][FB_BN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;            // thread = 4 pixels (ty) x 4 channels (tx)
   const int m0 = blockIdx.x * FB_BM, n0 = blockIdx.y * FB_BN;
   const int M = a.ho * a.wo, K = a.k * a.k * a.cin;
@@ -118,42 +135,71 @@ __global__ void __launch_bounds__(256) fb_conv_kernel(const FbConvArgs a) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += FB_BK) {
-    // A tile: FB_BK x FB_BM gathered input values (zero outside the image = the convolution's padding)
-    for (int e = tid; e < FB_BK * FB_BM; e += 256) {
-      const int kk = e / FB_BM, mm = e - kk * FB_BM;
-      const int kidx = k0 + kk, m = m0 + mm;
-      float v = 0.f;
-      if (kidx < K && m < M) {
-        const int ci = kidx % a.cin, kw = (kidx / a.cin) % a.k, kh = kidx / (a.cin * a.k);
-        const int oy = m / a.wo, ox = m - oy * a.wo;
-        const int iy = oy * a.stride - a.pad + kh, ix = ox * a.stride - a.pad + kw;
-        if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) {
-          if (a.x_u8) v = (float)a.x_u8[((size_t)iy * a.w + ix) * 3 + ci] - a.mean[ci];
-          else v = a.x[((size_t)iy * a.w + ix) * a.cin_stride + a.cin_off + ci];
-        }
+  float ra[4], rb[4];
+  // VEC mapping: A -- pixel tid / 4, K quad tid % 4 (four neighbouring threads read 64 contiguous bytes);
+  //              B -- K row tid / 16, channel quad tid % 16
+  const int a_mm = tid >> 2, a_kq = tid & 3, b_kk = tid >> 4, b_nq = tid & 15;
+  int v_oy = 0, v_ox = 0;
+  if (VEC) { const int m = m0 + a_mm; v_oy = m / a.wo; v_ox = m - v_oy * a.wo; }
+  auto fetch = [&](int k0) {
+    if (VEC) {
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int kidx = k0 + a_kq * 4;
+      if (kidx < K && m0 + a_mm < M) {
+        const int ci = kidx % a.cin, t = kidx / a.cin, kw = t % a.k, kh = t / a.k;
+        const int iy = v_oy * a.stride - a.pad + kh, ix = v_ox * a.stride - a.pad + kw;
+        if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w)
+          va = __ldg(reinterpret_cast<const float4*>(a.x + ((size_t)iy * a.w + ix) * a.cin_stride + a.cin_off + ci));
       }
-      sA[kk][mm] = v;
+      const int kb = k0 + b_kk, n = n0 + b_nq * 4;
+      if (kb < K && n < a.cout) vb = __ldg(reinterpret_cast<const float4*>(a.wk + (size_t)kb * a.cout + n));
+      ra[0] = va.x; ra[1] = va.y; ra[2] = va.z; ra[3] = va.w;
+      rb[0] = vb.x; rb[1] = vb.y; rb[2] = vb.z; rb[3] = vb.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = tid + j * 256, kk = e / FB_BM, mm = e - kk * FB_BM;
+        ra[j] = fb_gather1(a, k0 + kk, m0 + mm, K, M);
+        const int kb = k0 + e / FB_BN, n = n0 + e % FB_BN;
+        rb[j] = (kb < K && n < a.cout) ? a.wk[(size_t)kb * a.cout + n] : 0.f;
+      }
     }
-    for (int e = tid; e < FB_BK * FB_BN; e += 256) {
-      const int kk = e / FB_BN, nn = e - kk * FB_BN;
-      const int kidx = k0 + kk, n = n0 + nn;
-      sB[kk][nn] = (kidx < K && n < a.cout) ? a.wk[(size_t)kidx * a.cout + n] : 0.f;
+  };
+  auto stash = [&]() {
+    if (VEC) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sA[a_kq * 4 + j][a_mm] = ra[j];
+      *reinterpret_cast<float4*>(&sB[b_kk][b_nq * 4]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = tid + j * 256;
+        sA[e / FB_BM][e % FB_BM] = ra[j];
+        sB[e / FB_BN][e % FB_BN] = rb[j];
+      }
     }
-    __syncthreads();
+  };
+  fetch(0);
+  stash();
+  __syncthreads();
+  for (int k0 = 0; k0 < K; k0 += FB_BK) {
+    const bool more = k0 + FB_BK < K;
+    if (more) fetch(k0 + FB_BK);
 #pragma unroll
     for (int kk = 0; kk < FB_BK; ++kk) {
-      float av[4], bv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = sA[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = sB[kk][tx * 4 + j];
+      const float4 a4 = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
+    if (more) {
+      stash();
+      __syncthreads();
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -169,6 +215,40 @@ __global__ void __launch_bounds__(256) fb_conv_kernel(const FbConvArgs a) {
       else if (a.act == 1) o[n] = fmaxf(v, 0.f);
       else { o[n] = fmaxf(v, 0.f); o[n + a.cout] = fmaxf(-v, 0.f); }
     }
+  }
+}
+
+// Layers with at most 8 output channels and a long K (the 4- / 2-channel heads on the stride-64 / -128 maps: K = 2304,
+// 204 or 54 pixels): a 64 x 64 tile would run 144 serial K steps on one or two CTAs.  Here a CTA of 128 threads owns ONE
+// output pixel, the threads stride over K and the partial sums meet in a warp-shuffle + shared-memory reduction.
+constexpr int FB_SMALLN = 8;
+__global__ void __launch_bounds__(128) fb_conv_smalln_kernel(const FbConvArgs a) {
+  __shared__ float red[4][FB_SMALLN];
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const int M = a.ho * a.wo, K = a.k * a.k * a.cin;
+  float acc[FB_SMALLN];
+#pragma unroll
+  for (int n = 0; n < FB_SMALLN; ++n) acc[n] = 0.f;
+  for (int k = tid; k < K; k += 128) {
+    const float v = fb_gather1(a, k, m, K, M);
+    const float* wr = a.wk + (size_t)k * a.cout;
+#pragma unroll
+    for (int n = 0; n < FB_SMALLN; ++n)
+      if (n < a.cout) acc[n] = fmaf(v, wr[n], acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < FB_SMALLN; ++n) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc[n] += __shfl_xor_sync(0xFFFFFFFFu, acc[n], off);
+    if ((tid & 31) == 0) red[tid >> 5][n] = acc[n];
+  }
+  __syncthreads();
+  if (tid < a.cout) {
+    const float v = ((red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid])) + a.bias[tid];
+    float* o = a.y + (size_t)m * a.cout_stride + a.cout_off;
+    if (a.act == 0) o[tid] = v;
+    else if (a.act == 1) o[tid] = fmaxf(v, 0.f);
+    else { o[tid] = fmaxf(v, 0.f); o[tid + a.cout] = fmaxf(-v, 0.f); }
   }
 }
 

@@ -245,7 +245,12 @@ int fb_conv(syn_fb* f, int idx, const float* x, const uint8_t* x_u8, int h, int 
   a.k = L.k; a.stride = L.stride; a.pad = L.pad; a.act = L.act;
   a.mean[0] = 104.f; a.mean[1] = 117.f; a.mean[2] = 123.f;          // FaceBoxes.py:92
   const int M = a.ho * a.wo;
-  fb_conv_kernel<<<dim3((M + FB_BM - 1) / FB_BM, (L.cout + FB_BN - 1) / FB_BN), 256, 0, st>>>(a);
+  const dim3 grid((M + FB_BM - 1) / FB_BM, (L.cout + FB_BN - 1) / FB_BN);
+  const bool vec = x_u8 == nullptr && L.cin % 4 == 0 && cin_stride % 4 == 0 && cin_off % 4 == 0 && L.cout % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (L.cout <= FB_SMALLN && L.k * L.k * L.cin >= 512) fb_conv_smalln_kernel<<<M, 128, 0, st>>>(a);
+  else if (vec) fb_conv_kernel<true><<<grid, 256, 0, st>>>(a);
+  else fb_conv_kernel<false><<<grid, 256, 0, st>>>(a);
   SYN_LAUNCH_CHECK("fb_conv_kernel");
   ++f->launches;
   return SYN_OK;
