@@ -55,16 +55,29 @@ __global__ void faceboxes_rank_decode_kernel(const float* __restrict__ loc, cons
                                              const int32_t* __restrict__ cand, float* __restrict__ dets, int32_t* __restrict__ n_dets) {
   const int n = cand[0];
   if (blockIdx.x == 0 && threadIdx.x == 0) *n_dets = min(n, top_k);
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-    const int i = cand[1 + c];
-    const float s = conf[2 * i + 1];
+  if ((int)(blockIdx.x * blockDim.x) >= n) return;                       // whole CTA: the grid is sized for every prior
+  __shared__ float ss[512];
+  __shared__ int si[512];
+  {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c < n;
+    const int i = live ? cand[1 + c] : 0;
+    const float s = live ? conf[2 * i + 1] : 0.f;
     int rank = 0;
-    for (int q = 0; q < n; ++q) {
-      const int j = cand[1 + q];
-      const float sj = conf[2 * j + 1];
-      rank += (sj > s) || (sj == s && j > i);
+    for (int t0 = 0; t0 < n; t0 += 512) {                                 // all candidates, 512 at a time through shared memory
+      const int tn = min(512, n - t0);
+      for (int e = threadIdx.x; e < tn; e += blockDim.x) {
+        const int j = cand[1 + t0 + e];
+        si[e] = j;
+        ss[e] = conf[2 * j + 1];
+      }
+      __syncthreads();
+      if (live)
+        for (int q = 0; q < tn; ++q) rank += (ss[q] > s) || (ss[q] == s && si[q] > i);
+      __syncthreads();
     }
-    if (rank >= top_k) continue;
+    if (!live) return;
+    if (rank >= top_k) return;
     float p[4];
     prior_of(i, h, w, p);
     const float* l = loc + 4 * (size_t)i;

@@ -230,24 +230,69 @@ __global__ void nms_mask_kernel(const float* __restrict__ dets, int n, double th
   mask[(size_t)i * words + wj] = bits;
 }
 
-// The greedy scan itself: one warp; lane l owns words l, l+32, ... of the running "suppressed" set.
-// keep (n) int32 receives the kept indices in visiting order, *n_keep their number.
-__global__ void nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int32_t* __restrict__ keep, int32_t* __restrict__ n_keep) {
-  extern __shared__ unsigned long long removed[];
-  const int words = (n + 63) / 64, lane = threadIdx.x;
-  for (int wq = lane; wq < words; wq += 32) removed[wq] = 0ull;
-  __syncwarp();
-  int cnt = 0;
-  for (int i = 0; i < n; ++i) {
-    const bool gone = (removed[i >> 6] >> (i & 63)) & 1ull;     // same address for all lanes: broadcast
-    if (gone) continue;
-    if (lane == 0) keep[cnt] = i;
-    ++cnt;
-    const unsigned long long* row = mask + (size_t)i * words;
-    for (int wq = (i >> 6) + lane; wq < words; wq += 32) removed[wq] |= row[wq];
-    __syncwarp();
+// The greedy scan itself, 64 boxes (one mask word) at a time, one CTA:
+//   A  warp 0 resolves the block: the 64 x 64 diagonal of the bit matrix sits in two registers per lane, box b of the
+//      block survives iff its bit in `removed` is still clear when its turn comes, and then its diagonal word joins the
+//      running word -- 64 shuffle steps, no memory traffic;
+//   B  all threads OR the rows of the boxes that survived into `removed` for the words to the right of the block, four
+//      independent loads in flight per thread (a box-by-box scan would pay one dependent L2 round trip per kept box).
+// keep (n) int32 receives the kept indices in visiting order, *n_keep their number: the serial greedy list, exactly.
+constexpr int kNmsScanThreads = 1024;
+__global__ void __launch_bounds__(kNmsScanThreads) nms_scan_kernel(const unsigned long long* __restrict__ mask, int n,
+                                                                   int32_t* __restrict__ keep, int32_t* __restrict__ n_keep) {
+  extern __shared__ unsigned long long removed[];          // words entries
+  __shared__ int rows[64];
+  __shared__ int n_rows, total;
+  const int words = (n + 63) / 64, tid = threadIdx.x, lane = tid & 31;
+  for (int wq = tid; wq < words; wq += kNmsScanThreads) removed[wq] = 0ull;
+  if (tid == 0) total = 0;
+  __syncthreads();
+  for (int blk = 0; blk < words; ++blk) {
+    const int base = blk * 64, cnt = min(64, n - base);
+    if (tid < 32) {
+      const unsigned long long d0 = (lane < cnt) ? mask[(size_t)(base + lane) * words + blk] : 0ull;
+      const unsigned long long d1 = (lane + 32 < cnt) ? mask[(size_t)(base + 32 + lane) * words + blk] : 0ull;
+      unsigned long long cur = removed[blk], keepbits = 0ull;
+      for (int b = 0; b < cnt; ++b) {
+        const unsigned long long db = __shfl_sync(0xFFFFFFFFu, (b < 32) ? d0 : d1, b & 31);
+        if (!((cur >> b) & 1ull)) { keepbits |= 1ull << b; cur |= db; }
+      }
+      const int t0 = total;
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const int b = lane + 32 * hlf;
+        if ((keepbits >> b) & 1ull) {
+          const int pos = __popcll(keepbits & ((1ull << b) - 1ull));
+          keep[t0 + pos] = base + b;
+          rows[pos] = base + b;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) { n_rows = __popcll(keepbits); total = t0 + __popcll(keepbits); }
+    }
+    __syncthreads();
+    const int nr = n_rows, rem = words - blk - 1;
+    const int pairs = nr * rem;
+    for (int p0 = tid; p0 < pairs; p0 += 4 * kNmsScanThreads) {
+      unsigned long long v[4];
+      int wq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + u * kNmsScanThreads;
+        v[u] = 0ull; wq[u] = 0;
+        if (p < pairs) {
+          const int r = p / rem;
+          wq[u] = blk + 1 + (p - r * rem);
+          v[u] = mask[(size_t)rows[r] * words + wq[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (v[u]) atomicOr(&removed[wq[u]], v[u]);
+    }
+    __syncthreads();
   }
-  if (lane == 0) *n_keep = cnt;
+  if (tid == 0) *n_keep = total;
 }
 
 }  // namespace syn

@@ -118,7 +118,7 @@ int syn_nms(const float* dets_dev, int n, double thresh, int mode, uint64_t* mas
   SYN_LAUNCH_CHECK("nms_mask_kernel");
   if (words * 8 > 48 * 1024)
     SYN_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, words * 8));
-  nms_scan_kernel<<<1, 32, words * 8, st>>>(reinterpret_cast<const unsigned long long*>(mask_ws_dev), n, keep_dev, n_keep_dev);
+  nms_scan_kernel<<<1, kNmsScanThreads, words * 8, st>>>(reinterpret_cast<const unsigned long long*>(mask_ws_dev), n, keep_dev, n_keep_dev);
   SYN_LAUNCH_CHECK("nms_scan_kernel");
   return SYN_OK;
 }

@@ -107,11 +107,19 @@ int emul_nms(const float* dets, int n, double thresh, int ge, int32_t* keep) {
       if (ge ? ((double)ovr >= thresh) : (ovr > thr_f)) mask[(size_t)i * words + j / 64] |= 1ull << (j % 64);
     }
   }
+  // the scan of nms_scan_kernel: one 64-box block at a time -- resolve the block against its diagonal word, then OR the
+  // rows of the survivors into the words to its right
   int cnt = 0;
-  for (int i = 0; i < n; ++i) {
-    if ((removed[i >> 6] >> (i & 63)) & 1ull) continue;
-    keep[cnt++] = i;
-    for (int q = 0; q < words; ++q) removed[q] |= mask[(size_t)i * words + q];
+  for (int blk = 0; blk < words; ++blk) {
+    const int base = blk * 64, c = (n - base < 64) ? n - base : 64;
+    uint64_t cur = removed[blk], keepbits = 0;
+    for (int b = 0; b < c; ++b)
+      if (!((cur >> b) & 1ull)) { keepbits |= 1ull << b; cur |= mask[(size_t)(base + b) * words + blk]; }
+    for (int b = 0; b < c; ++b)
+      if ((keepbits >> b) & 1ull) {
+        keep[cnt++] = base + b;
+        for (int q = blk + 1; q < words; ++q) removed[q] |= mask[(size_t)(base + b) * words + q];
+      }
   }
   return cnt;
 }
