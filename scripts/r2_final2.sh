@@ -1,9 +1,8 @@
 #!/bin/bash
-# Closing run of round 2 (second session): the whole GPU test-suite, smoke(), the bench line, the reference arm, and ncu
+# Closing run of round 2 (second session): the whole GPU test-suite, the bench line, and ncu
 # evidence for the kernels added in this session (Sim3DR, FaceBoxes): launch list + one `--set full` capture of each.
 OUT=gpurun_out; mkdir -p $OUT
 echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6
-echo "== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5
 echo "== bench"; timeout 900 python bench.py > $OUT/r2b_bench.json 2> $OUT/r2b_bench.err; echo rc=$?; tail -n 2 $OUT/r2b_bench.err; python - <<'PY'
 import json
 d = json.loads(open('gpurun_out/r2b_bench.json').read().strip().splitlines()[-1])
@@ -14,8 +13,8 @@ print('detect', {k: v for k, v in d.get('detect', {}).items() if k.endswith('_ms
 print('cpu', d.get('cpu_baseline')); print('clocks', d.get('clocks'))
 PY
 echo "== ncu launch list (render / detect)"
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled --csv --log-file $OUT/r2_render_launches.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:syn:: --csv --log-file $OUT/r2_render_launches.csv \
     python scripts/ncu_render_once.py > $OUT/ncu_render_list.log 2>&1; echo rc=$?
 echo "== ncu full (render / detect)"
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -o $OUT/r2_render_full -f \
+timeout 400 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:syn:: -c 26 -o $OUT/r2_render_full -f \
     python scripts/ncu_render_once.py > $OUT/ncu_render_full.log 2>&1; echo rc=$?; ls -la $OUT/r2_render_full.ncu-rep
