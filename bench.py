@@ -384,6 +384,11 @@ def render_detect_measurement(dev, peaks, cpu_too=True):
     e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
     nver, ntri = verts.shape[2], tri.shape[0]
     alg_bytes = B * nver * 12 + ntri * 12 + 2 * H * W * 3
+    try:      # DRAM bytes of one call from the committed ncu capture (profiles/r2_ncu_full_render.txt)
+        with open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')) as f:
+            render_traffic = json.load(f).get('render_call')
+    except Exception:
+        render_traffic = None
     out['render'] = {
         'workload': f'{B} meshes x {nver} vertices / {ntri} triangles -> one {H}x{W}x3 uint8 canvas (normals + lighting + z-buffer), '
                     'vertices read in place from the (B,3,N) layout of the dense stage',
@@ -392,9 +397,11 @@ def render_detect_measurement(dev, peaks, cpu_too=True):
         'e2e': {'ms': e2e_ms, 'meshes_per_s': B / e2e_ms * 1e3, 'h2d_bytes': int(verts.nbytes + H * W * 3), 'd2h_bytes': H * W * 3,
                 'what': 'pinned host vertices + canvas in, image out, synchronised per call'},
         'roofline': {'bound': 'hbm', 'achieved': alg_bytes / (ms_all * 1e-3) / 1e9, 'peak': peaks['hbm'], 'unit': 'GB/s',
-                     'frac': alg_bytes / (ms_all * 1e-3) / 1e9 / peaks['hbm'], 'traffic': None,
+                     'frac': alg_bytes / (ms_all * 1e-3) / 1e9 / peaks['hbm'], 'traffic': render_traffic,
                      'what': f'algorithmic {alg_bytes} B per call (vertices + triangle list once + canvas in and out) / CUDA-event time of '
-                             'the six launches; the stage is gather / atomic-latency work far below the HBM ceiling'}}
+                             'the six launches; the stage is instruction-issue / atomic work (raster_depth_kernel: issue slots 82 % busy, '
+                             'DRAM 3 %) far below the HBM ceiling; traffic is 13x the algorithmic bytes because the (B,H,W) 64-bit key '
+                             'image is cleared and read back whole (100 MB of the 141 MB)'}}
     # ---- detect ---------------------------------------------------------------------------------------------------------------
     ih, iw = 720, 1080
     P = detect.num_priors(ih, iw)
