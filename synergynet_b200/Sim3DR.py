@@ -137,6 +137,8 @@ _renderers = {}
 
 
 def _renderer_for(triangles: np.ndarray, nver: int) -> MeshRenderer:
+    if not torch.cuda.is_available():
+        raise RuntimeError('synergynet_b200.Sim3DR needs a CUDA device (B200, sm_100a); there is no CPU fallback')
     tri = np.ascontiguousarray(triangles, dtype=np.int32)
     key = (hash(tri.tobytes()), tri.shape, int(nver), torch.cuda.current_device())
     r = _renderers.get(key)

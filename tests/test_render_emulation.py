@@ -159,3 +159,22 @@ def test_cabi_argument_checks():
     assert lib.syn_rasterize(None, 8, 8, 3, one, 24, 3, 1, 1, 8, one, 1, one, C.c_float(1.0), 0, one, None, None) == 1
     assert lib.syn_mesh_normals(one, 24, 0, 1, 1, 8, one, 1, one, one, one, one, None) == 1      # zero vertex stride
     assert lib.syn_nms(one, 4, C.c_double(0.3), 7, one, one, one, None) == 1                       # unknown mode
+
+
+def test_product_modules_fail_loudly_without_a_gpu():
+    """No CPU fallback in the Sim3DR / FaceBoxes modules: without a CUDA device every entry raises instead of computing."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('this host has a GPU')
+    from synergynet_b200 import Sim3DR, detect, faceboxes
+    tri = np.array([[0, 1, 2]], np.int32)
+    ver = np.zeros((3, 3), np.float32)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        Sim3DR.get_normal(ver, tri)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        Sim3DR.rasterize(ver, tri, ver, bg=np.zeros((4, 4, 3), np.uint8))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        detect.nms(np.zeros((2, 5), np.float32), 0.3)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        faceboxes.FaceBoxes(weights=synthetic.make_faceboxes_state_dict(0))
+    assert detect.nms(np.zeros((0, 5), np.float32), 0.3) == []            # nms_wrapper.py:16-17 needs no device
