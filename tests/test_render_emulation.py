@@ -178,3 +178,64 @@ def test_product_modules_fail_loudly_without_a_gpu():
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         faceboxes.FaceBoxes(weights=synthetic.make_faceboxes_state_dict(0))
     assert detect.nms(np.zeros((0, 5), np.float32), 0.3) == []            # nms_wrapper.py:16-17 needs no device
+
+
+# ---- property tests: random meshes / boxes through the kernels' algorithms vs the oracle ---------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=st.integers(0, 10_000), nver=st.integers(3, 40), ntri=st.integers(1, 60), h=st.integers(1, 40), w=st.integers(1, 48),
+       spread=st.sampled_from([0.5, 1.0, 3.0]), quantise=st.booleans(), reverse=st.booleans())
+def test_rasterizer_algorithm_on_random_meshes(emul, seed, nver, ntri, h, w, spread, quantise, reverse):
+    """Random triangles -- partly or wholly outside the image, sliver and zero-area ones, integer coordinates that put
+    pixel centres exactly on edges and make depth ties -- in natural and scrambled order: image and depth buffer must be
+    the serial reference's, bit for bit."""
+    rng = np.random.default_rng(seed)
+    ver = np.stack([rng.uniform(-spread * w * 0.3, w * (1 + 0.3 * spread), nver), rng.uniform(-spread * h * 0.3, h * (1 + 0.3 * spread), nver),
+                    rng.uniform(-5, 5, nver)], 1).astype(np.float32)
+    if quantise:
+        ver = np.round(ver)
+    tri = rng.integers(0, nver, (ntri, 3)).astype(np.int32)
+    col = rng.uniform(0, 1, (nver, 3)).astype(np.float32)
+    bg = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    want, dwant = rp.rasterize(ver, tri, col, bg.copy(), reverse=reverse, return_depth=True)
+    for shuffle in (0, 1):
+        img = bg.copy()
+        depth = np.zeros((1, h, w), np.float32)
+        emul.emul_rasterize(P(img), h, w, 3, P(ver), C.c_longlong(0), 3, 1, 1, nver, P(tri), ntri, P(col), C.c_float(1.0), int(reverse),
+                            P(depth), shuffle)
+        assert np.array_equal(img, want) and np.array_equal(depth[0], dwant)
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=st.integers(0, 10_000), nver=st.integers(3, 30), ntri=st.integers(1, 80))
+def test_normals_algorithm_on_random_topologies(emul, seed, nver, ntri):
+    """Random triangle lists (repeated corners, isolated vertices -> NaN like the reference) through the incidence-list sum."""
+    rng = np.random.default_rng(seed)
+    ver = rng.normal(0, 10, (nver, 3)).astype(np.float32)
+    tri = rng.integers(0, nver, (ntri, 3)).astype(np.int32)
+    start, lst = incidence(tri, nver)
+    out = np.zeros((nver, 3), np.float32)
+    emul.emul_normals(P(ver), 3, 1, nver, P(tri), ntri, P(start), P(lst), P(out))
+    assert np.array_equal(out, rp.get_normal(ver, tri), equal_nan=True)
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=st.integers(0, 10_000), n=st.integers(1, 300), grid=st.sampled_from([1.0, 4.0, 16.0]), thr=st.sampled_from([0.3, 0.5, 1.0 / 3.0]))
+def test_nms_algorithm_on_random_boxes(emul, seed, n, grid, thr):
+    """Boxes snapped to a grid (many overlaps are exact small fractions, some equal to the threshold) through the bit-matrix
+    + block scan, both comparison conventions, vs the serial C restatement and numpy's py_cpu_nms."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(0, 200, (n, 2))
+    wh = rng.uniform(8, 90, (n, 2))
+    d = np.hstack([np.round((c - wh / 2) / grid) * grid, np.round((c + wh / 2) / grid) * grid, (rng.permutation(n)[:, None] + 1.0) / (n + 1)])
+    d = d.astype(np.float32)
+    order = d[:, 4].argsort()[::-1]
+    ds = np.ascontiguousarray(d[order])
+    keep = np.zeros(n, np.int32)
+    for ge in (1, 0):
+        k = emul.emul_nms(P(ds), n, C.c_double(thr), ge, P(keep))
+        assert order[keep[:k]].tolist() == rp.cpu_nms(d, thr, ge=bool(ge))
+    k = emul.emul_nms(P(ds), n, C.c_double(thr), 0, P(keep))
+    assert order[keep[:k]].tolist() == rp.py_cpu_nms(d, np.float32(thr))
