@@ -37,8 +37,8 @@ def main():
     if args.checkpoint:
         model.load_weights(args.checkpoint)
     else:
-        from oracle import synth_model                      # demo only: the calibrated synthetic checkpoint lives with the tests
-        model.load_state_dict(synth_model.build_state_dict(0), strict=True)
+        synthetic.seeded_init_(model, 0)                     # random-init weights of the reference architecture, as bench.py uses
+        synthetic.randomize_batchnorm_(model, 0)
     model.eval()
     det = faceboxes.FaceBoxes(weights=args.detector_weights or synthetic.make_faceboxes_state_dict(0))
     model.face_detector = lambda im: det(im)[:args.max_faces]
