@@ -164,3 +164,17 @@ def test_shared_memory_lane_mappings_are_conflict_free():
         if s == 1 and w in (8, 15, 30):                                         # register-blocked path
             assert bc.dw_quad_loads(nc, w, mirrored=True) == 1 and bc.dw_quad_loads(nc, w, mirrored=False) == 2, name
             assert bc.a2_quad_stores(w, mirrored=True) == 1 and bc.a2_quad_stores(w, mirrored=False) == 2, name
+
+
+def test_render_module_has_the_reference_signature(synth_pack):
+    """utils/render.py:31 -- same positional / keyword arguments and defaults; triangles come from the parameter pack."""
+    import inspect
+    from synergynet_b200 import render
+    sig = inspect.signature(render.render)
+    assert list(sig.parameters) == ['img', 'ver_lst', 'alpha', 'wfp', 'tex', 'connectivity']
+    assert sig.parameters['alpha'].default == 0.6 and sig.parameters['wfp'].default is None
+    assert render.cfg['intensity_ambient'] == 0.75 and render.cfg['specular_exp'] == 5          # utils/render.py:18-27
+    assert callable(render.render_app) and hasattr(render.render_app, 'update_light_pos')
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match='no CPU fallback'):
+            render.render(np.zeros((8, 8, 3), np.uint8), [np.zeros((3, synth_pack.tri.shape[1] and 53215), np.float32)])
