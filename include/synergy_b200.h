@@ -255,7 +255,9 @@ int syn_faceboxes_decode(const float* loc_dev, const float* conf_dev, int im_hei
                          int32_t* n_dets_dev, void* stream);
 
 /* The detector network (FaceBoxes/models/faceboxes.py:68-150, FaceBoxesNet in 'test' phase) on ONE image of any size.
- * A separate handle: the detector has its own weights and workspace and does not touch syn_handle_t.
+ * A separate handle: the detector has its own weights and workspace and does not touch syn_handle_t.  Like syn_handle_t
+ * it is bound to one device and is not re-entrant (its activation workspace is shared by consecutive calls, which are
+ * ordered by the stream they are enqueued on; a change of image size synchronises the device and reallocates).
  * 33 convolutions in execution order (syn_fb_layer_desc names them with the reference's state_dict prefixes:
  * "conv1", "inception2.branch3x3_2", "loc.0" ...): layers with has_bn take the conv weight (OIHW fp32, no bias) and
  * the eval-mode BatchNorm2d of the same block (<name>.conv.weight / <name>.bn.*), the six head layers take weight +
